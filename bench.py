@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py -- shuffled rows/sec of reduceByKey end-to-end (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one pass of the shuffle hot path over one batch of synthetic input:
+map-side hash-partition -> exchange (NCCL alltoallv when N>1) -> reduce-side
+merge.  Workload at N=1 is BASELINE.json configs[1]: reduceByKey(sum) over 1e8
+(int64,int64) rows, uniform keys in [0, 2^31), 8 map splits, 8 reduce partitions.
+For N>1 the per-GPU work is fixed (weak scaling): 1e8 rows and 8 partitions per
+GPU.  One JSON line is printed by rank 0.
+
+--impl reference times the reference's CPU implementation of the same path: the
+reference is pure CPython (dict per bucket, dict merge; dpark/task.py:209-226,
+dpark/shuffle.py:600-608) and cannot travel to the GPU box, so the arm runs the
+oracle's line-by-line Python port (oracle/oracle.py) on all host cores with the
+reference's own map-task / reduce-task process structure.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "shuffled rows/sec (reduceByKey end-to-end)"
+UNIT = "rows/s"
+KEY_BYTES, VAL_BYTES = 8, 8
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows-per-gpu", type=int, default=100_000_000)
+    ap.add_argument("--parts-per-gpu", type=int, default=8)
+    ap.add_argument("--map-splits", type=int, default=8)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-sample-rows", type=int, default=4_000_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(args, world):
+    return {
+        "workload": "reduceByKey(sum) over %.0e (int64,int64) rows/GPU, uniform keys in [0,2^31), "
+                    "%d map splits/GPU, %d reduce partitions/GPU (BASELINE.json configs[1] at 1 GPU)"
+                    % (args.rows_per_gpu, args.map_splits, args.parts_per_gpu),
+        "rows_per_gpu": args.rows_per_gpu, "partitions": args.parts_per_gpu * world,
+        "map_splits_per_gpu": args.map_splits, "parallelism": "dp%d" % world,
+        "l2_policy": "inputs_larger_than_l2 (1.6 GB of rows per GPU per step vs 126 MB L2)",
+    }
+
+
+# ------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi in the background, exact PID killed afterwards)
+# ------------------------------------------------------------------------------
+class Clocks(object):
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.path = tempfile.mktemp(prefix="dpk_clocks_", suffix=".csv")
+        self.proc = None
+        try:
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50",
+                 "-i", str(index)], stdout=self.fh, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+        except Exception:
+            try:
+                self.proc.kill()
+            except Exception:
+                pass
+        self.fh.close()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    clk, cmax, pw = float(f[2]), float(f[3]), float(f[4])
+                except ValueError:
+                    continue
+                mx.append(cmax)
+                if pw > 250.0:          # under load
+                    sm.append(clk)
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                      "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            sm.sort()
+            out["sm_mhz"] = sm[len(sm) // 2]
+        if mx:
+            out["sm_max_mhz"] = max(mx)
+        out["reasons"] = sorted(reasons)
+        out["samples"] = len(sm)
+        return out
+
+
+def hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------
+# CPU arm: the reference's algorithm, CPython, reference process structure
+# ------------------------------------------------------------------------------
+def _cpu_map_task(arg):
+    """One ShuffleMapTask (dpark/task.py:209-226) + its dump (marshal, as
+    BucketDumper task.py:332-343 does for marshalable rows)."""
+    import marshal
+    import numpy as np
+    from oracle import oracle as orc
+    seed, n, P = arg
+    rng = np.random.default_rng(seed)
+    keys = rng.integers(0, 2 ** 31, n, dtype=np.int64).tolist()
+    vals = rng.integers(0, 2 ** 16, n, dtype=np.int64).tolist()
+    rows = list(zip(keys, vals))
+    t0 = time.perf_counter()
+    import operator
+    buckets = orc.py_shuffle_map_task(rows, P, lambda x: x, operator.add, None, hash)  # ints: portable_hash == hash()
+    blobs = [marshal.dumps(list(b.items())) for b in buckets]
+    return blobs, time.perf_counter() - t0
+
+
+def _cpu_reduce_task(blobs):
+    """One reducer: fetch every map's bucket and merge (dpark/shuffle.py:247-289, 600-608)."""
+    import marshal
+    import operator
+    from oracle import oracle as orc
+    t0 = time.perf_counter()
+    d = orc.py_merge((marshal.loads(b) for b in blobs), operator.add)
+    return len(d), time.perf_counter() - t0
+
+
+def cpu_port_run(rows, P, procs):
+    """Throughput of the CPython port on `procs` cores: M=procs map tasks in
+    parallel, then P reduce tasks in parallel, like the reference's
+    MultiProcessScheduler (dpark/schedule.py:841-910).  Input generation is not timed."""
+    import multiprocessing as mp
+    M = max(1, procs)
+    per = rows // M
+    args = [(1000 + i, per, P) for i in range(M)]
+    if procs <= 1:
+        t0 = time.perf_counter()
+        outs = [_cpu_map_task(a) for a in args]
+        gen_excl = sum(t for _, t in outs)
+        blobs = [o for o, _ in outs]
+        red = [_cpu_reduce_task([b[r] for b in blobs]) for r in range(P)]
+        secs = gen_excl + sum(t for _, t in red)
+        return per * M / secs, per * M, secs
+    ctx = mp.get_context("fork")
+    with ctx.Pool(procs) as pool:
+        outs = pool.map(_cpu_map_task, args)
+        map_wall = max(t for _, t in outs)           # tasks run concurrently, one per core
+        blobs = [o for o, _ in outs]
+        t0 = time.perf_counter()
+        pool.map(_cpu_reduce_task, [[b[r] for b in blobs] for r in range(P)])
+        red_wall = time.perf_counter() - t0
+    secs = map_wall + red_wall
+    return per * M / secs, per * M, secs
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    P = args.parts_per_gpu * args.gpus
+    sample = min(args.cpu_sample_rows * max(1, min(cores, 32)) // 4, 64_000_000)
+    vals, t_all = [], 0.0
+    steps = max(1, min(args.steps, 3))
+    for _ in range(min(args.warmup, 1)):
+        cpu_port_run(sample // 4, P, cores)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        v, nrows, secs = cpu_port_run(sample, P, cores)
+        vals.append(v)
+        t_all += secs
+    value = sum(vals) / len(vals)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * t_all / steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64",
+        "data": "synthetic", "config": workload_config(args, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d rows per step (same generator as the GPU arm), M=%d map tasks then "
+                                   "P=%d reduce tasks in a fork pool; CPython port of task.py:209-226 + "
+                                   "shuffle.py:600-608 with marshal dumps" % (sample, cores, P)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from dpark_b200 import _native as nv
+    from dpark_b200 import shuffle
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    n, P, M = args.rows_per_gpu, args.parts_per_gpu * world, args.map_splits
+
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    keys = torch.randint(0, 2 ** 31, (n,), dtype=torch.int64, device=dev, generator=g)
+    g.manual_seed(1235 + rank)
+    vals = torch.randint(0, 2 ** 16, (n,), dtype=torch.int64, device=dev, generator=g)
+    per = (n + M - 1) // M
+    kc = [keys[i * per:min(n, (i + 1) * per)] for i in range(M)]
+    vc = [vals[i * per:min(n, (i + 1) * per)] for i in range(M)]
+
+    def step():
+        mo = shuffle.map_side(kc, vc, P)
+        rx = shuffle.exchange(mo)
+        return shuffle.reduce_side(rx, "sum", P)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        out = step()
+    barrier()
+    # one-time sanity inside the bench: the value checksum survives the shuffle
+    ok, ov, po, cnt = out
+    po_h, cnt_h = po.cpu().tolist(), cnt.cpu().tolist()
+    local_sum = sum(int(ov[po_h[j]:po_h[j] + cnt_h[j]].sum()) for j in range(len(cnt_h)))
+    distinct = sum(cnt_h)
+    tot = torch.tensor([local_sum, int(vals.sum()), distinct], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot)
+    assert int(tot[0]) == int(tot[1]), "value checksum changed across the shuffle"
+    del out, ok, ov
+
+    clocks = Clocks(local) if rank == 0 else None
+    launches0 = nv.launch_count()
+    nv.prof_enable(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    nv.prof_enable(False)
+    launches = nv.launch_count() - launches0
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_step = float(ms) / args.steps
+    value = n * world / (ms_step * 1e-3)
+
+    # per-kernel device times from the library's own CUDA events (same stream)
+    prof = nv.prof_collect()
+    agg = {}
+    for name, t in prof:
+        a = agg.setdefault(name, [0.0, 0])
+        a[0] += t
+        a[1] += 1
+    rows_step = n
+    kv = KEY_BYTES + VAL_BYTES
+    nrecv = n  # uniform keys: every rank receives ~n rows
+    alg = {  # algorithmic bytes per STEP for each kernel
+        "part_count": KEY_BYTES * rows_step,          # the two-pass histogram re-read: not credited to the map side
+        "part_scatter": 2 * kv * rows_step,           # read each pair once, write it once
+        "tbl_init": 0,
+        "tbl_insert": kv * nrecv,                     # read every received pair once
+        "tbl_compact": kv * int(tot[2]) // world,     # write one pair per distinct key
+    }
+    kernels = []
+    ktotal = sum(a[0] for a in agg.values()) or 1.0
+    for name, (t, c) in sorted(agg.items(), key=lambda x: -x[1][0]):
+        per_step_ms = t / args.steps
+        kernels.append({"kernel": name, "launches_per_step": c / args.steps, "ms_per_step": per_step_ms,
+                        "share": t / ktotal,
+                        "alg_gbs": (alg.get(name, 0) / (per_step_ms * 1e-3) / 1e9) if per_step_ms > 0 else None})
+    peak, peak_src = hbm_peak()
+    dom = "part_scatter"
+    dom_ms, dom_cnt = agg.get(dom, [0.0, 1])
+    dom_launch_ms = dom_ms / max(1, dom_cnt)
+    dom_bytes_launch = 2 * kv * (rows_step / M)
+    achieved = dom_bytes_launch / (dom_launch_ms * 1e-3) / 1e9 if dom_launch_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "k_part_scatter (map-side stable multisplit)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src,
+                "alg_bytes_per_launch": dom_bytes_launch, "ms_per_launch": dom_launch_ms,
+                "share_of_step": dom_ms / ktotal}
+    red_ms = sum(agg.get(k, [0.0, 0])[0] for k in ("tbl_init", "tbl_insert", "tbl_compact")) / args.steps
+    if red_ms > 0:
+        red_bytes = alg["tbl_insert"] + alg["tbl_compact"]
+        roofline_reduce = {"bound": "hbm", "kernel": "reduce side (tbl_init+tbl_insert+tbl_compact)",
+                           "achieved": red_bytes / (red_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                           "frac": red_bytes / (red_ms * 1e-3) / 1e9 / peak, "ms_per_step": red_ms}
+    else:
+        roofline_reduce = None
+
+    # ---- e2e: host buffers through the public HostShuffle call ------------------
+    hs = shuffle.HostShuffle(n, torch.int64, torch.int64, P, "sum", splits=M)
+    hs.h_keys.copy_(keys.cpu())
+    hs.h_vals.copy_(vals.cpu())
+    del keys, vals, kc, vc
+    torch.cuda.empty_cache()
+    hs.run()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    f0.record()
+    for _ in range(args.e2e_steps):
+        hs.run()
+    f1.record()
+    barrier()
+    wall = (time.perf_counter() - t0) * 1e3
+    e2e_ms = torch.tensor([max(f0.elapsed_time(f1), wall)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_step = float(e2e_ms) / args.e2e_steps
+    e2e = {"value": n * world / (e2e_step * 1e-3), "unit": UNIT, "ms_per_step": e2e_step,
+           "steps": args.e2e_steps, "h2d_bytes_per_step": hs.h2d_bytes * world,
+           "d2h_bytes_per_step": hs.d2h_bytes * world,
+           "api": "dpark_b200.shuffle.HostShuffle.run (pinned host in, pinned host out)"}
+    clk = clocks.stop() if clocks else None
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, nrows, secs = cpu_port_run(args.cpu_sample_rows, P, 1)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                        "sample": "%d rows (same generator), CPython port of task.py:209-226 + "
+                                  "shuffle.py:600-608, %.1f s" % (nrows, secs)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+            "config": workload_config(args, world), "gpu_launches": launches, "e2e": e2e,
+            "roofline": roofline, "roofline_reduce": roofline_reduce, "kernels": kernels,
+            "cpu_baseline": cpu_baseline, "clocks": clk,
+            "distinct_keys": int(tot[2]),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,176 @@
+// dpk_common.cuh -- shared pieces of the B200 shuffle kernels: error plumbing,
+// the portable_hash device functions (a1) and the partitioner functor (a2).
+// Hash/partition functions are __host__ __device__ so tests/hostcheck can run
+// the very same code on the CPU against the oracle without a GPU.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <math.h>
+
+#include "dpark_b200.h"
+
+#define DPK_HD __host__ __device__ __forceinline__
+
+namespace dpk {
+
+// ------------------------------------------------------------------ errors
+extern thread_local char g_err[512];
+int fail(int code, const char *fmt, ...);
+#define DPK_CUDA_TRY(expr)                                                        \
+    do {                                                                          \
+        cudaError_t _e = (expr);                                                  \
+        if (_e != cudaSuccess)                                                    \
+            return dpk::fail(DPK_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,        \
+                             cudaGetErrorString(_e), __FILE__, __LINE__);         \
+    } while (0)
+#define DPK_LAUNCH_CHECK() DPK_CUDA_TRY(cudaGetLastError())
+
+int sm_count();
+
+// every kernel launch goes through DPK_LAUNCH: counts it and, when profiling
+// is on, brackets it with CUDA events on the launching stream.
+struct ProfScope {
+    int idx;
+    cudaStream_t st;
+    ProfScope(const char *label, cudaStream_t s);
+    ~ProfScope();
+};
+#define DPK_LAUNCH(label, st, ...)              \
+    do {                                        \
+        {                                       \
+            dpk::ProfScope _ps(label, st);      \
+            __VA_ARGS__;                        \
+        }                                       \
+        DPK_LAUNCH_CHECK();                     \
+    } while (0)
+
+// ------------------------------------------------------------- a1: hashing
+constexpr uint64_t kPyMod = (1ull << 61) - 1;  // CPython _PyHASH_MODULUS
+
+// hash(int) for an int64 value -- dpark/portable_hash.pyx:61-62 (CPython
+// long_hash: sign * (|x| mod 2^61-1); -1 -> -2).
+DPK_HD int64_t hash_i64(int64_t x) {
+    uint64_t a = x < 0 ? 0ull - (uint64_t)x : (uint64_t)x;  // |INT64_MIN| = 2^63 ok
+    uint64_t r = (a & kPyMod) + (a >> 61);                   // hi <= 4
+    if (r >= kPyMod) r -= kPyMod;
+    int64_t h = x < 0 ? -(int64_t)r : (int64_t)r;
+    return h == -1 ? -2 : h;
+}
+DPK_HD int64_t hash_u64(uint64_t a) {
+    uint64_t r = (a & kPyMod) + (a >> 61);                   // hi <= 7
+    if (r >= kPyMod) r -= kPyMod;
+    return (int64_t)r;
+}
+// hash(float) -- CPython _Py_HashDouble (NaN unsupported: hashed by identity there)
+DPK_HD int64_t hash_f64(double v) {
+    if (isinf(v)) return v > 0 ? 314159 : -314159;
+    if (v != v) return 0;
+    int e;
+    double m = frexp(v, &e);
+    bool neg = m < 0;
+    if (neg) m = -m;
+    uint64_t x = 0;
+    while (m != 0.0) {
+        x = ((x << 28) & kPyMod) | (x >> (61 - 28));
+        m *= 268435456.0;
+        e -= 28;
+        uint64_t y = (uint64_t)m;
+        m -= (double)y;
+        x += y;
+        if (x >= kPyMod) x -= kPyMod;
+    }
+    e = e >= 0 ? e % 61 : 61 - 1 - ((-1 - e) % 61);
+    x = ((x << e) & kPyMod) | (x >> (61 - e));
+    int64_t h = neg ? -(int64_t)x : (int64_t)x;
+    return h == -1 ? -2 : h;
+}
+
+template <typename T> struct KeyHash;
+template <> struct KeyHash<int64_t> { static DPK_HD int64_t of(int64_t k) { return hash_i64(k); } };
+template <> struct KeyHash<int32_t> { static DPK_HD int64_t of(int32_t k) { return hash_i64((int64_t)k); } };
+template <> struct KeyHash<uint64_t> { static DPK_HD int64_t of(uint64_t k) { return hash_u64(k); } };
+template <> struct KeyHash<double> { static DPK_HD int64_t of(double k) { return hash_f64(k); } };
+template <> struct KeyHash<float> { static DPK_HD int64_t of(float k) { return hash_f64((double)k); } };
+
+// string_hash over signed chars -- dpark/portable_hash.pyx:17-32
+DPK_HD int64_t hash_bytes_signed(const uint8_t *s, int64_t len) {
+    if (len == 0) return 0;
+    uint64_t value = (uint64_t)(int64_t)(int8_t)s[0] << 7;
+    for (int64_t i = 0; i < len; i++)
+        value = (1000003ull * value) ^ (uint64_t)(int64_t)(int8_t)s[i];
+    value ^= (uint64_t)len;
+    return (int64_t)value == -1 ? -2 : (int64_t)value;
+}
+// unicode_hash over the code points of a UTF-8 encoded str -- portable_hash.pyx:34-48
+DPK_HD int64_t hash_utf8_codepoints(const uint8_t *s, int64_t nbytes) {
+    if (nbytes == 0) return 0;
+    uint64_t value = 0;
+    int64_t ncp = 0, i = 0;
+    while (i < nbytes) {
+        uint32_t c = s[i], cp;
+        int extra;
+        if (c < 0x80) { cp = c; extra = 0; }
+        else if (c < 0xE0) { cp = c & 0x1F; extra = 1; }
+        else if (c < 0xF0) { cp = c & 0x0F; extra = 2; }
+        else { cp = c & 0x07; extra = 3; }
+        for (int j = 1; j <= extra && i + j < nbytes; j++) cp = (cp << 6) | (s[i + j] & 0x3F);
+        i += extra + 1;
+        if (ncp == 0) value = (uint64_t)cp << 7;
+        value = (1000003ull * value) ^ (uint64_t)cp;
+        ncp++;
+    }
+    value ^= (uint64_t)ncp;
+    return (int64_t)value == -1 ? -2 : (int64_t)value;
+}
+
+// ------------------------------------------------- a2: HashPartitioner functor
+// getPartition = portable_hash(key) floor-mod P, or bisect_right(thresholds, h)
+// (dpark/dependency.py:229-233).  floor-mod by an arbitrary P without a 64-bit
+// divide: power-of-two mask, else multiply-high by a precomputed magic
+// (round-up method, Granlund-Montgomery / libdivide "branchfree" form).
+struct PartFn {
+    int32_t P;
+    int32_t mode;  // 0: P==1, 1: power of two, 2: magic, 3: thresholds
+    uint64_t magic;
+    int32_t shift;
+    int32_t nthr;
+    const int64_t *thresholds;
+
+    DPK_HD int32_t operator()(int64_t h) const {
+        if (mode == 1) return (int32_t)((uint64_t)h & (uint64_t)(P - 1));  // two's complement == floor-mod
+        if (mode == 2) {
+            uint64_t a = h < 0 ? 0ull - (uint64_t)h : (uint64_t)h;
+#ifdef __CUDA_ARCH__
+            uint64_t q = __umul64hi(magic, a);
+#else
+            uint64_t q = (uint64_t)(((unsigned __int128)magic * a) >> 64);
+#endif
+            uint64_t t = ((a - q) >> 1) + q;
+            q = t >> shift;
+            uint32_t r = (uint32_t)(a - q * (uint64_t)P);
+            return h < 0 ? (r ? P - (int32_t)r : 0) : (int32_t)r;
+        }
+        if (mode == 3) {
+            int32_t lo = 0, hi = nthr;
+            while (lo < hi) {
+                int32_t mid = (lo + hi) >> 1;
+                if (h < thresholds[mid]) hi = mid; else lo = mid + 1;
+            }
+            return lo;
+        }
+        return 0;
+    }
+};
+// host: build the functor (thresholds is a device pointer, only stored)
+int make_partfn(int32_t P, const int64_t *thresholds, int32_t nthr, PartFn *out);
+
+// murmur3 fmix64 -- slot hash for the reduce-side tables (not part of the
+// reference semantics; only spreads keys over table slots)
+DPK_HD uint64_t mix64(uint64_t x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull;
+    return x ^ (x >> 33);
+}
+
+}  // namespace dpk

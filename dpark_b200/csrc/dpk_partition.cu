@@ -1,0 +1,437 @@
+// dpk_partition.cu -- map side of the shuffle: ShuffleMapTask._run's
+// hash-partition (dpark/task.py:209-226, dpark/dependency.py:229-233) as a
+// STABLE multisplit of a columnar chunk into P bucket-major ranges.
+//
+// Data layout in HBM: struct-of-arrays.  keys[n], vals[n] in; out_keys[*],
+// out_vals[*] bucket-major (bucket p occupies [base[p], base[p]+count[p])), rows
+// of a bucket in input order.  The bucket-major buffer IS the alltoallv send
+// buffer (buckets owned by one peer are adjacent).
+//
+// Kernels (HBM-bound integer work, no tensor cores):
+//   k_part_count   : each CTA owns one contiguous row range ("chunk" of the grid),
+//                    hashes keys, counts rows per bucket -> tile_counts[P][T].
+//   k_part_scan    : per bucket, exclusive scan over the T CTAs.
+//   k_part_scatter : each CTA re-reads its range tile by tile (4096 rows): fused
+//                    hash -> pid -> warp-level match ranks -> block multisplit in
+//                    shared memory -> coalesced run-wise stores to HBM.
+// Algorithmic bytes: 2*(K+V) per row (read once, write once); this two-pass
+// form re-reads K once more for the histogram (not credited).
+#include "dpk_common.cuh"
+
+namespace dpk {
+
+constexpr int PT_THREADS = 256;
+constexpr int PT_WARPS = PT_THREADS / 32;
+constexpr int PT_ITEMS = 16;
+constexpr int PT_TILE = PT_THREADS * PT_ITEMS;  // 4096 rows per tile
+
+struct NoVal {};
+
+struct Plan {
+    int32_t T;  // CTAs (row ranges)
+    int64_t L;  // rows per CTA, multiple of PT_TILE
+};
+
+static Plan make_plan(int64_t n) {
+    Plan pl;
+    int64_t tiles = (n + PT_TILE - 1) / PT_TILE;
+    if (tiles < 1) tiles = 1;
+    int64_t maxT = (int64_t)sm_count() * 4;
+    int64_t T = tiles < maxT ? tiles : maxT;
+    int64_t per = (tiles + T - 1) / T;
+    pl.L = per * PT_TILE;
+    pl.T = (int32_t)((n + pl.L - 1) / pl.L);
+    if (pl.T < 1) pl.T = 1;
+    return pl;
+}
+
+static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+// workspace: int32 tile_counts[P][Tmax] | int64 totals[P] | int64 offsets[P+1]
+static int64_t ws_counts_bytes(int32_t P) { return align_up((int64_t)P * sm_count() * 4 * 4, 256); }
+static int64_t ws_total_bytes(int32_t P) {
+    return ws_counts_bytes(P) + align_up((int64_t)P * 8, 256) + align_up((int64_t)(P + 1) * 8, 256);
+}
+
+template <typename KeyT, bool PRE>
+__device__ __forceinline__ int64_t key_hash(KeyT k) {
+    if constexpr (PRE) return (int64_t)k;
+    else return KeyHash<KeyT>::of(k);
+}
+
+// exclusive scan of one int per thread over the 256-thread CTA; returns the
+// exclusive prefix, *total gets the CTA sum.  s_warp: >= PT_WARPS ints.
+__device__ __forceinline__ int block_excl_scan(int v, int *s_warp, int *total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    int base = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < PT_WARPS; w++) {
+        int t = s_warp[w];
+        if (w < warp) base += t;
+        tot += t;
+    }
+    __syncthreads();
+    *total = tot;
+    return base + inc - v;
+}
+
+// ------------------------------------------------------------------ count
+template <typename KeyT, bool PRE>
+__global__ void __launch_bounds__(PT_THREADS)
+k_part_count(const KeyT *__restrict__ keys, int64_t n, int64_t L, PartFn f,
+             int32_t *__restrict__ tile_counts, int32_t T) {
+    extern __shared__ int32_t s_cnt[];  // [P]
+    const int P = f.P;
+    for (int p = threadIdx.x; p < P; p += PT_THREADS) s_cnt[p] = 0;
+    __syncthreads();
+    const int64_t beg = (int64_t)blockIdx.x * L;
+    const int64_t end = min(n, beg + L);
+    const int lane = threadIdx.x & 31;
+    constexpr int U = 4;
+    for (int64_t i0 = beg; i0 < end; i0 += (int64_t)PT_THREADS * U) {
+        KeyT k[U];
+        bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            int64_t i = i0 + (int64_t)u * PT_THREADS + threadIdx.x;
+            ok[u] = i < end;
+            k[u] = ok[u] ? keys[i] : KeyT(0);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            int pid = ok[u] ? f(key_hash<KeyT, PRE>(k[u])) : -1;
+            unsigned m = __match_any_sync(0xffffffffu, pid);
+            if (ok[u] && lane == __ffs(m) - 1) atomicAdd(&s_cnt[pid], __popc(m));
+        }
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < P; p += PT_THREADS)
+        tile_counts[(int64_t)p * T + blockIdx.x] = s_cnt[p];
+}
+
+// one CTA per bucket: exclusive scan of its T per-CTA counts, total -> totals[p]
+__global__ void __launch_bounds__(PT_THREADS)
+k_part_scan(int32_t *__restrict__ tile_counts, int32_t T, int64_t *__restrict__ totals) {
+    __shared__ int s_warp[PT_WARPS];
+    int32_t *row = tile_counts + (int64_t)blockIdx.x * T;
+    const int E = (T + PT_THREADS - 1) / PT_THREADS;
+    const int b = threadIdx.x * E;
+    int sum = 0;
+    for (int i = b; i < min(b + E, T); i++) sum += row[i];
+    int tot;
+    int run = block_excl_scan(sum, s_warp, &tot);
+    for (int i = b; i < min(b + E, T); i++) {
+        int t = row[i];
+        row[i] = run;
+        run += t;
+    }
+    if (threadIdx.x == 0) totals[blockIdx.x] = (int64_t)tot;
+}
+
+// single CTA: offsets[0..P] = exclusive scan of totals (int64)
+__global__ void __launch_bounds__(PT_THREADS)
+k_part_offsets(const int64_t *__restrict__ totals, int32_t P, int64_t *__restrict__ offsets) {
+    __shared__ long long s_part[PT_THREADS];
+    const int E = (P + PT_THREADS - 1) / PT_THREADS;
+    const int b = threadIdx.x * E;
+    long long sum = 0;
+    for (int i = b; i < min(b + E, P); i++) sum += totals[i];
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    long long base = 0;
+    for (int t = 0; t < (int)threadIdx.x; t++) base += s_part[t];
+    for (int i = b; i < min(b + E, P); i++) {
+        offsets[i] = base;
+        base += totals[i];
+    }
+    if (b < P && min(b + E, P) == P) offsets[P] = base;
+    if (P == 0 && threadIdx.x == 0) offsets[0] = 0;
+}
+
+// ---------------------------------------------------------------- scatter
+struct ScatterSmem {
+    int64_t key_off, val_off, pid_off, gpos_off, tstart_off, tcount_off, whist_off, total;
+};
+static ScatterSmem scatter_smem(int kb, int vb, int32_t P) {
+    ScatterSmem s;
+    int64_t o = 0;
+    s.key_off = o; o += align_up((int64_t)PT_TILE * kb, 16);
+    s.val_off = o; o += align_up((int64_t)PT_TILE * vb, 16);
+    s.gpos_off = o; o += align_up((int64_t)P * 8, 16);
+    s.tstart_off = o; o += align_up((int64_t)P * 4, 16);
+    s.tcount_off = o; o += align_up((int64_t)P * 4, 16);
+    s.pid_off = o; o += align_up((int64_t)PT_TILE * 2, 16);
+    s.whist_off = o; o += align_up((int64_t)PT_WARPS * P * 2, 16);
+    s.total = o;
+    return s;
+}
+
+template <typename KeyT, typename ValT, bool PRE>
+__global__ void __launch_bounds__(PT_THREADS, 2)
+k_part_scatter(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, int64_t n, int64_t L,
+               PartFn f, const int32_t *__restrict__ tile_off, int32_t T,
+               const int64_t *__restrict__ bucket_base, KeyT *__restrict__ out_keys,
+               ValT *__restrict__ out_vals, ScatterSmem lay) {
+    constexpr bool HAS_VAL = !std::is_same<ValT, NoVal>::value;
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ int s_warp[PT_WARPS];
+    KeyT *s_key = reinterpret_cast<KeyT *>(smem + lay.key_off);
+    ValT *s_val = reinterpret_cast<ValT *>(smem + lay.val_off);
+    int64_t *s_gpos = reinterpret_cast<int64_t *>(smem + lay.gpos_off);   // global pos of next row of bucket p
+    int32_t *s_tstart = reinterpret_cast<int32_t *>(smem + lay.tstart_off);
+    int32_t *s_tcount = reinterpret_cast<int32_t *>(smem + lay.tcount_off);
+    uint16_t *s_pid = reinterpret_cast<uint16_t *>(smem + lay.pid_off);
+    uint16_t *s_whist = reinterpret_cast<uint16_t *>(smem + lay.whist_off);  // [PT_WARPS][P]
+
+    const int P = f.P;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int64_t beg = (int64_t)blockIdx.x * L;
+    const int64_t end = min(n, beg + L);
+
+    for (int p = threadIdx.x; p < P; p += PT_THREADS)
+        s_gpos[p] = bucket_base[p] + (int64_t)tile_off[(int64_t)p * T + blockIdx.x];
+
+    const int E = (P + PT_THREADS - 1) / PT_THREADS;  // buckets per thread in the scan
+
+    for (int64_t tile = beg; tile < end; tile += PT_TILE) {
+        const int rows = (int)min((int64_t)PT_TILE, end - tile);
+        for (int i = threadIdx.x; i < PT_WARPS * P; i += PT_THREADS) s_whist[i] = 0;
+
+        // ---- load: warp w owns rows [w*512, w*512+512) of the tile, item j = 32 consecutive rows
+        KeyT k[PT_ITEMS];
+        ValT v[PT_ITEMS];
+        const int64_t wbase = tile + (int64_t)warp * (32 * PT_ITEMS) + lane;
+#pragma unroll
+        for (int j = 0; j < PT_ITEMS; j++) {
+            int64_t idx = wbase + j * 32;
+            k[j] = idx < end ? keys[idx] : KeyT(0);
+        }
+        if constexpr (HAS_VAL) {
+#pragma unroll
+            for (int j = 0; j < PT_ITEMS; j++) {
+                int64_t idx = wbase + j * 32;
+                if (idx < end) v[j] = vals[idx];
+            }
+        }
+        __syncthreads();  // whist zeroed; previous tile's copy-out done with the staging buffers
+
+        // ---- warp-level ranks (stable: lanes in order, items in order)
+        uint16_t pid[PT_ITEMS], rank[PT_ITEMS];
+        uint16_t *wh = s_whist + warp * P;
+#pragma unroll
+        for (int j = 0; j < PT_ITEMS; j++) {
+            const bool ok = (wbase + j * 32) < end;
+            const int p = ok ? f(key_hash<KeyT, PRE>(k[j])) : P;  // P = "no row"
+            const unsigned m = __match_any_sync(0xffffffffu, p);
+            int base = 0;
+            if (ok) base = wh[p];
+            __syncwarp();
+            pid[j] = (uint16_t)p;
+            rank[j] = (uint16_t)(base + __popc(m & lt_mask));
+            if (ok && lane == __ffs(m) - 1) wh[p] = (uint16_t)(base + __popc(m));
+            __syncwarp();
+        }
+        __syncthreads();
+
+        // ---- per bucket: exclusive scan over the 8 warps, tile count
+        for (int p = threadIdx.x; p < P; p += PT_THREADS) {
+            int run = 0;
+#pragma unroll
+            for (int w = 0; w < PT_WARPS; w++) {
+                int t = s_whist[w * P + p];
+                s_whist[w * P + p] = (uint16_t)run;
+                run += t;
+            }
+            s_tcount[p] = run;
+        }
+        __syncthreads();
+        // ---- exclusive scan of tile counts over buckets -> start of each bucket's run in the tile
+        {
+            const int b = threadIdx.x * E;
+            int sum = 0;
+            for (int i = b; i < min(b + E, P); i++) sum += s_tcount[i];
+            int tot;
+            int run = block_excl_scan(sum, s_warp, &tot);
+            for (int i = b; i < min(b + E, P); i++) {
+                s_tstart[i] = run;
+                run += s_tcount[i];
+            }
+        }
+        __syncthreads();
+
+        // ---- place rows at their sorted position in the staging tile
+#pragma unroll
+        for (int j = 0; j < PT_ITEMS; j++) {
+            const int p = pid[j];
+            if (p < P) {
+                const int pos = s_tstart[p] + s_whist[warp * P + p] + rank[j];
+                s_key[pos] = k[j];
+                if constexpr (HAS_VAL) s_val[pos] = v[j];
+                s_pid[pos] = (uint16_t)p;
+            }
+        }
+        __syncthreads();
+
+        // ---- copy out: consecutive threads -> consecutive addresses inside each bucket run
+        for (int i = threadIdx.x; i < rows; i += PT_THREADS) {
+            const int p = s_pid[i];
+            const int64_t dst = s_gpos[p] + (int64_t)(i - s_tstart[p]);
+            out_keys[dst] = s_key[i];
+            if constexpr (HAS_VAL) out_vals[dst] = s_val[i];
+        }
+        __syncthreads();
+        for (int p = threadIdx.x; p < P; p += PT_THREADS) s_gpos[p] += s_tcount[p];
+        // (next iteration's first __syncthreads orders this against later reads)
+    }
+}
+
+// ------------------------------------------------------------ host dispatch
+template <typename KeyT, bool PRE>
+static int launch_count(const void *keys, int64_t n, const Plan &pl, const PartFn &f,
+                        int32_t *tile_counts, cudaStream_t st) {
+    size_t sh = (size_t)f.P * sizeof(int32_t);
+    DPK_LAUNCH("part_count", st, k_part_count<KeyT, PRE><<<pl.T, PT_THREADS, sh, st>>>((const KeyT *)keys, n, pl.L, f, tile_counts, pl.T));
+    return DPK_OK;
+}
+
+static int dispatch_count(const void *keys, int key_kind, int64_t n, const Plan &pl, const PartFn &f,
+                          int32_t *tile_counts, cudaStream_t st) {
+    switch (key_kind) {
+    case -1: return launch_count<int64_t, true>(keys, n, pl, f, tile_counts, st);
+    case DPK_K_I64: return launch_count<int64_t, false>(keys, n, pl, f, tile_counts, st);
+    case DPK_K_I32: return launch_count<int32_t, false>(keys, n, pl, f, tile_counts, st);
+    case DPK_K_F64: return launch_count<double, false>(keys, n, pl, f, tile_counts, st);
+    case DPK_K_U64: return launch_count<uint64_t, false>(keys, n, pl, f, tile_counts, st);
+    case DPK_K_F32: return launch_count<float, false>(keys, n, pl, f, tile_counts, st);
+    }
+    return fail(DPK_ERR_UNSUPPORTED, "key kind %d is unhashable by portable_hash", key_kind);
+}
+
+template <typename KeyT, typename ValT, bool PRE>
+static int launch_scatter(const void *keys, const void *vals, int64_t n, const Plan &pl, const PartFn &f,
+                          const int32_t *tile_off, const int64_t *bucket_base, void *out_keys,
+                          void *out_vals, cudaStream_t st) {
+    constexpr int vb = std::is_same<ValT, NoVal>::value ? 0 : (int)sizeof(ValT);
+    ScatterSmem lay = scatter_smem((int)sizeof(KeyT), vb, f.P);
+    auto kern = k_part_scatter<KeyT, ValT, PRE>;
+    if (lay.total > 227 * 1024)
+        return fail(DPK_ERR_UNSUPPORTED, "P=%d needs %lld B of shared memory", f.P, (long long)lay.total);
+    DPK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
+    DPK_LAUNCH("part_scatter", st,
+               kern<<<pl.T, PT_THREADS, (size_t)lay.total, st>>>((const KeyT *)keys, (const ValT *)vals, n, pl.L, f,
+                                                                tile_off, pl.T, bucket_base, (KeyT *)out_keys,
+                                                                (ValT *)out_vals, lay));
+    return DPK_OK;
+}
+
+template <typename KeyT, bool PRE>
+static int dispatch_val(const void *keys, const void *vals, int32_t val_bytes, int64_t n, const Plan &pl,
+                        const PartFn &f, const int32_t *tile_off, const int64_t *bucket_base,
+                        void *out_keys, void *out_vals, cudaStream_t st) {
+    if (vals == nullptr || val_bytes == 0)
+        return launch_scatter<KeyT, NoVal, PRE>(keys, nullptr, n, pl, f, tile_off, bucket_base, out_keys, nullptr, st);
+    if (val_bytes == 8)
+        return launch_scatter<KeyT, int64_t, PRE>(keys, vals, n, pl, f, tile_off, bucket_base, out_keys, out_vals, st);
+    if (val_bytes == 4)
+        return launch_scatter<KeyT, int32_t, PRE>(keys, vals, n, pl, f, tile_off, bucket_base, out_keys, out_vals, st);
+    return fail(DPK_ERR_UNSUPPORTED, "val_bytes must be 0, 4 or 8, got %d", val_bytes);
+}
+
+static int dispatch_scatter(const void *keys, int key_kind, const void *vals, int32_t val_bytes, int64_t n,
+                            const Plan &pl, const PartFn &f, const int32_t *tile_off,
+                            const int64_t *bucket_base, void *out_keys, void *out_vals, cudaStream_t st) {
+    // the scatter only moves bits: 8-byte keys share the int64/uint64/double code
+    // paths for hashing, so dispatch on the hash kind
+    switch (key_kind) {
+    case -1: return dispatch_val<int64_t, true>(keys, vals, val_bytes, n, pl, f, tile_off, bucket_base, out_keys, out_vals, st);
+    case DPK_K_I64: return dispatch_val<int64_t, false>(keys, vals, val_bytes, n, pl, f, tile_off, bucket_base, out_keys, out_vals, st);
+    case DPK_K_I32: return dispatch_val<int32_t, false>(keys, vals, val_bytes, n, pl, f, tile_off, bucket_base, out_keys, out_vals, st);
+    case DPK_K_F64: return dispatch_val<double, false>(keys, vals, val_bytes, n, pl, f, tile_off, bucket_base, out_keys, out_vals, st);
+    case DPK_K_U64: return dispatch_val<uint64_t, false>(keys, vals, val_bytes, n, pl, f, tile_off, bucket_base, out_keys, out_vals, st);
+    case DPK_K_F32: return dispatch_val<float, false>(keys, vals, val_bytes, n, pl, f, tile_off, bucket_base, out_keys, out_vals, st);
+    }
+    return fail(DPK_ERR_UNSUPPORTED, "key kind %d is unhashable by portable_hash", key_kind);
+}
+
+static int check_common(const void *keys, int64_t n, int32_t P, void *ws, int64_t ws_bytes) {
+    if (n < 0 || n >= ((int64_t)1 << 31)) return fail(DPK_ERR_INVALID, "n=%lld out of range [0, 2^31)", (long long)n);
+    if (P < 1 || P > DPK_MAX_PARTITIONS) return fail(DPK_ERR_UNSUPPORTED, "P=%d out of range [1, %d]", P, DPK_MAX_PARTITIONS);
+    if (n > 0 && !keys) return fail(DPK_ERR_INVALID, "keys is NULL");
+    if (!ws || ws_bytes < ws_total_bytes(P)) return fail(DPK_ERR_WORKSPACE, "workspace needs %lld B, got %lld", (long long)ws_total_bytes(P), (long long)ws_bytes);
+    return DPK_OK;
+}
+
+}  // namespace dpk
+
+using namespace dpk;
+
+extern "C" {
+
+int64_t dpk_partition_workspace_bytes(int64_t n, int32_t P) {
+    (void)n;
+    if (P < 1) P = 1;
+    return ws_total_bytes(P);
+}
+
+int dpk_partition_count(const void *keys, int key_kind, int64_t n, int32_t P, const int64_t *thresholds,
+                        int32_t nthr, int64_t *out_counts, void *ws, int64_t ws_bytes,
+                        dpk_stream_t stream) {
+    int rc = check_common(keys, n, P, ws, ws_bytes);
+    if (rc) return rc;
+    if (!out_counts) return fail(DPK_ERR_INVALID, "out_counts is NULL");
+    PartFn f;
+    rc = make_partfn(P, thresholds, nthr, &f);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    int32_t *tile_counts = (int32_t *)ws;
+    Plan pl = make_plan(n);
+    if (n == 0) {
+        DPK_CUDA_TRY(cudaMemsetAsync(tile_counts, 0, (size_t)P * pl.T * 4, st));
+    } else {
+        rc = dispatch_count(keys, key_kind, n, pl, f, tile_counts, st);
+        if (rc) return rc;
+    }
+    DPK_LAUNCH("part_scan", st, k_part_scan<<<P, PT_THREADS, 0, st>>>(tile_counts, pl.T, out_counts));
+    return DPK_OK;
+}
+
+int dpk_partition_scatter(const void *keys, int key_kind, const void *vals, int32_t val_bytes, int64_t n,
+                          int32_t P, const int64_t *thresholds, int32_t nthr, const int64_t *bucket_base,
+                          void *out_keys, void *out_vals, void *ws, int64_t ws_bytes, dpk_stream_t stream) {
+    int rc = check_common(keys, n, P, ws, ws_bytes);
+    if (rc) return rc;
+    if (n == 0) return DPK_OK;
+    if (!bucket_base || !out_keys) return fail(DPK_ERR_INVALID, "NULL pointer");
+    PartFn f;
+    rc = make_partfn(P, thresholds, nthr, &f);
+    if (rc) return rc;
+    Plan pl = make_plan(n);
+    return dispatch_scatter(keys, key_kind, vals, val_bytes, n, pl, f, (const int32_t *)ws, bucket_base,
+                            out_keys, out_vals, (cudaStream_t)stream);
+}
+
+int dpk_partition(const void *keys, int key_kind, const void *vals, int32_t val_bytes, int64_t n, int32_t P,
+                  const int64_t *thresholds, int32_t nthr, void *out_keys, void *out_vals,
+                  int64_t *out_offsets, void *ws, int64_t ws_bytes, dpk_stream_t stream) {
+    int rc = check_common(keys, n, P, ws, ws_bytes);
+    if (rc) return rc;
+    if (!out_offsets) return fail(DPK_ERR_INVALID, "out_offsets is NULL");
+    int64_t *totals = (int64_t *)((char *)ws + ws_counts_bytes(P));
+    rc = dpk_partition_count(keys, key_kind, n, P, thresholds, nthr, totals, ws, ws_bytes, stream);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    DPK_LAUNCH("part_offsets", st, k_part_offsets<<<1, PT_THREADS, 0, st>>>(totals, P, out_offsets));
+    return dpk_partition_scatter(keys, key_kind, vals, val_bytes, n, P, thresholds, nthr, out_offsets,
+                                 out_keys, out_vals, ws, ws_bytes, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,143 @@
+/*
+ * dpark_b200.h -- C ABI of the B200-native DPark shuffle hot path.
+ *
+ * The reference (douban/dpark) has NO FFI on this path: the boundary is
+ * Python-level.  This header is therefore the net-new plugin
+ * ABI a maintainer would bind from dpark/task.py and dpark/shuffle.py (see
+ * INTEGRATION.md for the ctypes stub).  Every entry point names the reference
+ * code it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch / C++ types.
+ *   - every pointer is a DEVICE pointer into caller-owned memory unless the
+ *     parameter name starts with `h_`.
+ *   - every call takes a cudaStream_t (as void*), is stream-ordered, never
+ *     allocates device memory and never synchronises unless stated.
+ *   - returns 0 on success, <0 on error (DPK_ERR_*); dpk_last_error() gives a
+ *     thread-local message.
+ *   - sizes: a single call handles n < 2^31 rows; callers chunk above that.
+ */
+#ifndef DPARK_B200_H
+#define DPARK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DPK_ABI_VERSION 1
+
+typedef void *dpk_stream_t; /* cudaStream_t */
+
+enum {
+    DPK_OK = 0,
+    DPK_ERR_INVALID = -1,     /* bad argument (NULL pointer, n<0, P<1 ...)            */
+    DPK_ERR_UNSUPPORTED = -2, /* unsupported dtype/op/size -> Python TypeError        */
+    DPK_ERR_WORKSPACE = -3,   /* workspace too small                                  */
+    DPK_ERR_CUDA = -4         /* CUDA runtime error (message in dpk_last_error)       */
+};
+
+/* key column kinds.  The hash of each follows dpark/portable_hash.pyx:51-70:
+ * ints and floats -> Python's builtin hash(); see dpk_hash_keys. */
+enum { DPK_K_I64 = 0, DPK_K_I32 = 1, DPK_K_F64 = 2, DPK_K_U64 = 3, DPK_K_F32 = 4 };
+/* value column kinds */
+enum { DPK_V_I64 = 0, DPK_V_F64 = 1, DPK_V_I32 = 2, DPK_V_F32 = 3 };
+/* combiner ops a reduceByKey(func) lowers to (dpark/rdd.py:543-545 builds
+ * Aggregator(identity, func, func); dpark/dependency.py:121-161) */
+enum { DPK_OP_SUM = 0, DPK_OP_MIN = 1, DPK_OP_MAX = 2, DPK_OP_PROD = 3,
+       DPK_OP_AND = 4, DPK_OP_OR = 5, DPK_OP_XOR = 6 };
+/* byte-string key modes for dpk_hash_bytes */
+enum { DPK_BYTES_SIGNED = 0,   /* bytes keys: string_hash over signed chars, portable_hash.pyx:17-32 */
+       DPK_STR_UTF8 = 1 };     /* str keys stored as UTF-8: unicode_hash over code points, :34-48   */
+
+int dpk_abi_version(void);
+const char *dpk_last_error(void);
+/* h_info: int32[4] = {sm_count, cc_major, cc_minor, l2_bytes>>20} of the current device */
+int dpk_device_info(int32_t *h_info);
+
+/* ---- a1: portable_hash (dpark/portable_hash.pyx:51-70) ------------------- */
+/* out_hash[i] = portable_hash(keys[i]); ints: sign(x)*(|x| mod 2^61-1), -1 -> -2;
+ * floats: CPython _Py_HashDouble. */
+int dpk_hash_keys(const void *keys, int key_kind, int64_t n, int64_t *out_hash,
+                  dpk_stream_t stream);
+/* variable-length keys: data[offsets[i] .. offsets[i+1]) */
+int dpk_hash_bytes(const uint8_t *data, const int64_t *offsets, int64_t n, int mode,
+                   int64_t *out_hash, dpk_stream_t stream);
+
+/* ---- a2: HashPartitioner.getPartition (dpark/dependency.py:229-233) ------ */
+/* out_pid[i] = hash[i] floor-mod P, or bisect_right(thresholds, hash[i]) when
+ * thresholds != NULL (nthr = P-1 ascending int64 on device). */
+int dpk_partition_ids(const int64_t *hash, int64_t n, int32_t P, const int64_t *thresholds,
+                      int32_t nthr, int32_t *out_pid, dpk_stream_t stream);
+
+/* ---- a4: map side, ShuffleMapTask._run hash-partition (dpark/task.py:209-226)
+ * Stable multisplit of one input chunk into P buckets: rows keep their input
+ * order inside each bucket (this is what makes ordered groupByKey exact).
+ * Keys may be a key column (key_kind = DPK_K_*) or, with key_kind = -1,
+ * precomputed int64 hashes `hash` for variable-length keys (then `keys` is the
+ * int64 payload that travels, e.g. the row index).
+ *
+ *   ws = dpk_partition_workspace_bytes(n, P)
+ *   dpk_partition_count  : out_counts[P] (int64) = rows per bucket of this chunk;
+ *                          leaves per-CTA counts in ws for the scatter.
+ *   dpk_partition_scatter: writes row i to out_keys/out_vals[bucket_base[p] + rank],
+ *                          bucket_base[P] int64 on device (caller-computed from the
+ *                          counts of all chunks, so several chunks can interleave
+ *                          into one bucket-major buffer = the alltoallv send buffer).
+ *                          Must follow dpk_partition_count with the same
+ *                          (keys, n, P, thresholds, ws).
+ *   dpk_partition        : count + exclusive scan + scatter for a single chunk;
+ *                          out_offsets[P+1] int64.
+ * key_bytes/val_bytes in {4, 8}.  vals may be NULL (keys only).  P <= DPK_MAX_PARTITIONS.
+ */
+#define DPK_MAX_PARTITIONS 4096
+int64_t dpk_partition_workspace_bytes(int64_t n, int32_t P);
+int dpk_partition_count(const void *keys, int key_kind, int64_t n, int32_t P,
+                        const int64_t *thresholds, int32_t nthr, int64_t *out_counts, void *ws,
+                        int64_t ws_bytes, dpk_stream_t stream);
+int dpk_partition_scatter(const void *keys, int key_kind, const void *vals, int32_t val_bytes,
+                          int64_t n, int32_t P, const int64_t *thresholds, int32_t nthr,
+                          const int64_t *bucket_base, void *out_keys, void *out_vals, void *ws,
+                          int64_t ws_bytes, dpk_stream_t stream);
+int dpk_partition(const void *keys, int key_kind, const void *vals, int32_t val_bytes, int64_t n,
+                  int32_t P, const int64_t *thresholds, int32_t nthr, void *out_keys,
+                  void *out_vals, int64_t *out_offsets, void *ws, int64_t ws_bytes,
+                  dpk_stream_t stream);
+
+/* ---- a9: reduce side, DiskHashMerger._merge (dpark/shuffle.py:600-608) ----
+ * combined[k] = op(combined[k], v) over the n rows fetched for the reduce
+ * partitions this GPU owns.  Rows of several partitions may be passed at once
+ * (bucket-major, part_offsets[nparts+1] on device): distinct keys of partition
+ * p are written to out_keys/out_vals[part_offsets[p] ...] and their count to
+ * out_counts[p] (int64).  Order inside a partition is unspecified (the
+ * reference iterates a dict).  Accumulation type: I64/I32 values -> int64
+ * (exact while |sum| < 2^63, like the reference's big ints); F64/F32 values ->
+ * float64 (the reference adds Python floats); out_vals is 8 bytes per row.
+ * part_pid_P / thresholds describe the partitioner again (needed to route each
+ * distinct key to its partition's output range).
+ */
+int64_t dpk_combine_workspace_bytes(int64_t n);
+int dpk_combine(const void *keys, int key_kind, const void *vals, int val_kind, int64_t n, int op,
+                int32_t P, const int64_t *thresholds, int32_t nthr, int32_t part_first,
+                int32_t nparts, const int64_t *part_offsets, void *out_keys, void *out_vals,
+                int64_t *out_counts, void *ws, int64_t ws_bytes, dpk_stream_t stream);
+
+/* ---- measurement hooks (SURVEY.md §5 tracing: TaskStats -> CUDA events) -----
+ * dpk_launch_count: kernels launched by this library since load.
+ * dpk_prof_enable(1): from now on every kernel launch is bracketed by CUDA
+ * events on its stream (up to DPK_PROF_MAX launches are kept, later ones are
+ * counted but not timed); dpk_prof_enable(0) stops.  dpk_prof_count() = entries
+ * kept; dpk_prof_get(i, h_name[64], &h_ms) synchronises entry i's stop event and
+ * returns the kernel label and its device time in milliseconds. */
+#define DPK_PROF_MAX 4096
+int64_t dpk_launch_count(void);
+int dpk_prof_enable(int on);
+int dpk_prof_count(void);
+int dpk_prof_get(int i, char *h_name, float *h_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPARK_B200_H */
