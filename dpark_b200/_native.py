@@ -1,8 +1,8 @@
 """ctypes binding of libdpark_b200.so (include/dpark_b200.h).
 
-The CUDA extension is the product: if the library is missing or the device is
-not CUDA this module raises -- there is no CPU fallback for the shuffle path.
-torch is used only for device memory and streams.
+The CUDA extension is the product: if the library is missing or a tensor is not
+on a CUDA device this module raises -- there is no CPU fallback for the shuffle
+path.  torch is used only for device memory and streams.
 """
 import ctypes as C
 import os
@@ -25,15 +25,15 @@ if hasattr(torch, "uint64"):
     _KEY_KIND[torch.uint64] = K_U64
 _VAL_KIND = {torch.int64: V_I64, torch.float64: V_F64, torch.int32: V_I32, torch.float32: V_F32}
 
+# every symbol include/dpark_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
     "dpk_abi_version", "dpk_last_error", "dpk_device_info", "dpk_hash_keys", "dpk_hash_bytes",
     "dpk_partition_ids", "dpk_partition_workspace_bytes", "dpk_partition_count",
     "dpk_partition_scatter", "dpk_partition", "dpk_combine_workspace_bytes", "dpk_combine",
+    "dpk_launch_count", "dpk_prof_enable", "dpk_prof_count", "dpk_prof_get",
 ]
 
 _lib = None
-launches = 0   # number of C-ABI compute calls made (bench.py reports kernel launches from it)
-kernel_launches = 0
 
 
 class NativeError(RuntimeError):
@@ -49,23 +49,25 @@ def lib():
                 "`python -c 'import __graft_entry__ as g; g.build()'` (there is no CPU fallback)" % LIB_PATH)
         L = C.CDLL(LIB_PATH)
         i64, i32, vp, ci = C.c_int64, C.c_int32, C.c_void_p, C.c_int
-        L.dpk_abi_version.restype = ci
+        for name in EXPORTS:
+            getattr(L, name).restype = ci
         L.dpk_last_error.restype = C.c_char_p
+        L.dpk_partition_workspace_bytes.restype = i64
+        L.dpk_combine_workspace_bytes.restype = i64
+        L.dpk_launch_count.restype = i64
         L.dpk_device_info.argtypes = [vp]
         L.dpk_hash_keys.argtypes = [vp, ci, i64, vp, vp]
         L.dpk_hash_bytes.argtypes = [vp, vp, i64, ci, vp, vp]
         L.dpk_partition_ids.argtypes = [vp, i64, i32, vp, i32, vp, vp]
-        L.dpk_partition_workspace_bytes.restype = i64
         L.dpk_partition_workspace_bytes.argtypes = [i64, i32]
-        L.dpk_partition_count.argtypes = [vp, ci, i64, i32, vp, i32, vp, vp, i64, vp]
-        L.dpk_partition_scatter.argtypes = [vp, ci, vp, i32, i64, i32, vp, i32, vp, vp, vp, vp, i64, vp]
-        L.dpk_partition.argtypes = [vp, ci, vp, i32, i64, i32, vp, i32, vp, vp, vp, vp, i64, vp]
-        L.dpk_combine_workspace_bytes.restype = i64
-        L.dpk_combine_workspace_bytes.argtypes = [i64]
-        L.dpk_combine.argtypes = [vp, ci, vp, ci, i64, ci, i32, vp, i32, i32, i32, vp, vp, vp, vp, vp, i64, vp]
-        for name in EXPORTS:
-            if name not in ("dpk_last_error", "dpk_partition_workspace_bytes", "dpk_combine_workspace_bytes"):
-                getattr(L, name).restype = ci
+        L.dpk_partition_count.argtypes = [vp, ci, i64, i32, vp, i32, i32, vp, vp, i64, vp]
+        L.dpk_partition_scatter.argtypes = [vp, ci, vp, i32, i64, i32, vp, i32, i32, vp, vp, vp, vp, i64, vp]
+        L.dpk_partition.argtypes = [vp, ci, vp, i32, i64, i32, vp, i32, i32, vp, vp, vp, vp, i64, vp]
+        L.dpk_combine_workspace_bytes.argtypes = [i64, i32]
+        L.dpk_combine.argtypes = [vp, ci, vp, ci, i64, ci, i32, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp,
+                                  vp, i64, vp]
+        L.dpk_prof_enable.argtypes = [ci]
+        L.dpk_prof_get.argtypes = [ci, C.c_char_p, C.POINTER(C.c_float)]
         if L.dpk_abi_version() != 1:
             raise ImportError("dpark_b200: ABI version mismatch")
         _lib = L
@@ -133,127 +135,119 @@ def device_info():
     return {"sm_count": int(info[0]), "cc": (int(info[1]), int(info[2])), "l2_mb": int(info[3])}
 
 
+# ---- a1 / a2 -------------------------------------------------------------------
 def hash_keys(keys):
     """portable_hash of a key column (dpark/portable_hash.pyx:51-70)."""
-    global launches, kernel_launches
     _need_cuda(keys)
     out = torch.empty(keys.numel(), dtype=torch.int64, device=keys.device)
     _check(lib().dpk_hash_keys(_ptr(keys), key_kind(keys), keys.numel(), _ptr(out), _stream()))
-    launches += 1; kernel_launches += 1 if keys.numel() else 0
     return out
 
 
 def hash_bytes(data, offsets, mode):
-    global launches, kernel_launches
     _need_cuda(data, offsets)
     n = offsets.numel() - 1
     out = torch.empty(n, dtype=torch.int64, device=offsets.device)
     _check(lib().dpk_hash_bytes(_ptr(data), _ptr(offsets), n, mode, _ptr(out), _stream()))
-    launches += 1; kernel_launches += 1 if n else 0
     return out
 
 
 def partition_ids(hashes, P, thresholds=None):
     """HashPartitioner.getPartition over a hash column (dpark/dependency.py:229-233)."""
-    global launches, kernel_launches
     _need_cuda(hashes)
     thr, nthr = _thr(thresholds, hashes.device)
     out = torch.empty(hashes.numel(), dtype=torch.int32, device=hashes.device)
     _check(lib().dpk_partition_ids(_ptr(hashes), hashes.numel(), P, _ptr(thr), nthr, _ptr(out), _stream()))
-    launches += 1; kernel_launches += 1 if hashes.numel() else 0
     return out
 
 
-def partition_workspace(P, device):
-    nbytes = lib().dpk_partition_workspace_bytes(0, P)
+# ---- a4: map side --------------------------------------------------------------
+def partition_workspace(nbuckets, device):
+    nbytes = lib().dpk_partition_workspace_bytes(0, nbuckets)
     return torch.empty(nbytes, dtype=torch.uint8, device=device)
 
 
-def partition_count(keys, P, thresholds=None, prehashed=False, ws=None):
-    """Rows per bucket of one chunk; returns (counts[P] int64 device, ws)."""
-    global launches, kernel_launches
+def partition_count(keys, P, thresholds=None, prehashed=False, sub_bits=0, ws=None):
+    """Rows per bucket of one chunk; returns (counts[P << sub_bits] int64 device, ws)."""
     _need_cuda(keys)
+    F = P << sub_bits
     thr, nthr = _thr(thresholds, keys.device)
     if ws is None:
-        ws = partition_workspace(P, keys.device)
-    counts = torch.empty(P, dtype=torch.int64, device=keys.device)
+        ws = partition_workspace(F, keys.device)
+    counts = torch.empty(F, dtype=torch.int64, device=keys.device)
     _check(lib().dpk_partition_count(_ptr(keys), key_kind(keys, prehashed), keys.numel(), P, _ptr(thr), nthr,
-                                     _ptr(counts), _ptr(ws), ws.numel(), _stream()))
-    launches += 1; kernel_launches += 2
+                                     sub_bits, _ptr(counts), _ptr(ws), ws.numel(), _stream()))
     return counts, ws
 
 
-def partition_scatter(keys, vals, P, bucket_base, out_keys, out_vals, ws, thresholds=None, prehashed=False):
-    global launches, kernel_launches
+def partition_scatter(keys, vals, P, bucket_base, out_keys, out_vals, ws, thresholds=None, prehashed=False,
+                      sub_bits=0):
     _need_cuda(keys, vals, bucket_base, out_keys, out_vals, ws)
     thr, nthr = _thr(thresholds, keys.device)
     vb = 0 if vals is None else vals.element_size()
     _check(lib().dpk_partition_scatter(_ptr(keys), key_kind(keys, prehashed), _ptr(vals), vb, keys.numel(), P,
-                                       _ptr(thr), nthr, _ptr(bucket_base), _ptr(out_keys), _ptr(out_vals),
-                                       _ptr(ws), ws.numel(), _stream()))
-    launches += 1; kernel_launches += 1 if keys.numel() else 0
+                                       _ptr(thr), nthr, sub_bits, _ptr(bucket_base), _ptr(out_keys),
+                                       _ptr(out_vals), _ptr(ws), ws.numel(), _stream()))
 
 
-def partition(keys, vals, P, thresholds=None, prehashed=False):
+def partition(keys, vals, P, thresholds=None, prehashed=False, sub_bits=0):
     """Stable hash-partition of one chunk (ShuffleMapTask._run, dpark/task.py:209-226).
-    Returns (out_keys, out_vals, offsets[P+1] int64 device)."""
-    global launches, kernel_launches
+    Returns (out_keys, out_vals, offsets[(P << sub_bits) + 1] int64 device)."""
     _need_cuda(keys, vals)
     if vals is not None and vals.numel() != keys.numel():
         from .errors import DparkUserFatalError
         raise DparkUserFatalError("ragged pair columns: %d keys, %d values" % (keys.numel(), vals.numel()))
+    F = P << sub_bits
     thr, nthr = _thr(thresholds, keys.device)
-    ws = partition_workspace(P, keys.device)
+    ws = partition_workspace(F, keys.device)
     out_keys = torch.empty_like(keys)
     out_vals = None if vals is None else torch.empty_like(vals)
-    offsets = torch.empty(P + 1, dtype=torch.int64, device=keys.device)
+    offsets = torch.empty(F + 1, dtype=torch.int64, device=keys.device)
     vb = 0 if vals is None else vals.element_size()
     _check(lib().dpk_partition(_ptr(keys), key_kind(keys, prehashed), _ptr(vals), vb, keys.numel(), P,
-                               _ptr(thr), nthr, _ptr(out_keys), _ptr(out_vals), _ptr(offsets),
+                               _ptr(thr), nthr, sub_bits, _ptr(out_keys), _ptr(out_vals), _ptr(offsets),
                                _ptr(ws), ws.numel(), _stream()))
-    launches += 1; kernel_launches += 3 + (1 if keys.numel() else 0)
     return out_keys, out_vals, offsets
 
 
+# ---- a9: reduce side -----------------------------------------------------------
 def acc_dtype(vals_dtype):
     """Accumulator/output dtype of combine: ints -> int64, floats -> float64
     (the reference adds Python ints / Python floats)."""
     return torch.float64 if vals_dtype in (torch.float32, torch.float64) else torch.int64
 
 
-def combine(keys, vals, op, P, part_offsets, part_first=0, nparts=None, thresholds=None):
+def combine(keys, vals, op, P, bucket_rows, part_first=0, nparts=None, thresholds=None, sub_bits=0):
     """Reduce-side merge (DiskHashMerger._merge, dpark/shuffle.py:600-608) of the
-    rows of partitions [part_first, part_first+nparts), bucket-major in keys/vals
-    with part_offsets[nparts+1] (device int64).  Returns (out_keys, out_vals,
-    out_counts[nparts]); distinct keys of partition p are at
-    out[part_offsets[p] : part_offsets[p] + out_counts[p]]."""
-    global launches, kernel_launches
-    _need_cuda(keys, vals, part_offsets)
+    rows of partitions [part_first, part_first+nparts).  bucket_rows: device int64
+    [nparts << sub_bits] rows per local fine bucket.  Returns (out_keys, out_vals,
+    out_offsets[nparts+1], out_counts[nparts]); partition j's distinct keys are
+    out[out_offsets[j] : out_offsets[j] + out_counts[j]]."""
+    _need_cuda(keys, vals, bucket_rows)
     if nparts is None:
         nparts = P
     n = keys.numel()
+    F = nparts << sub_bits
+    if bucket_rows.numel() != F or bucket_rows.dtype != torch.int64:
+        raise ValueError("bucket_rows must be int64[%d]" % F)
     thr, nthr = _thr(thresholds, keys.device)
-    ws_bytes = lib().dpk_combine_workspace_bytes(n)
+    ws_bytes = lib().dpk_combine_workspace_bytes(n, F)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=keys.device)
     out_keys = torch.empty_like(keys)
     out_vals = torch.empty(n, dtype=acc_dtype(vals.dtype), device=keys.device)
+    out_offsets = torch.empty(nparts + 1, dtype=torch.int64, device=keys.device)
     out_counts = torch.empty(nparts, dtype=torch.int64, device=keys.device)
     _check(lib().dpk_combine(_ptr(keys), key_kind(keys), _ptr(vals), val_kind(vals), n, OPS[op], P,
-                             _ptr(thr), nthr, part_first, nparts, _ptr(part_offsets), _ptr(out_keys),
-                             _ptr(out_vals), _ptr(out_counts), _ptr(ws), ws_bytes, _stream()))
-    launches += 1; kernel_launches += 2 + (1 if n else 0)
-    return out_keys, out_vals, out_counts
+                             _ptr(thr), nthr, sub_bits, part_first, nparts, _ptr(bucket_rows), _ptr(out_keys),
+                             _ptr(out_vals), _ptr(out_offsets), _ptr(out_counts), _ptr(ws), ws_bytes,
+                             _stream()))
+    return out_keys, out_vals, out_offsets, out_counts
 
 
 # ---- measurement hooks ---------------------------------------------------------
-EXPORTS += ["dpk_launch_count", "dpk_prof_enable", "dpk_prof_count", "dpk_prof_get"]
-
-
 def launch_count():
     """Kernels launched by the library since load (exact, counted in C)."""
-    L = lib()
-    L.dpk_launch_count.restype = C.c_int64
-    return int(L.dpk_launch_count())
+    return int(lib().dpk_launch_count())
 
 
 def prof_enable(on=True):
@@ -263,7 +257,6 @@ def prof_enable(on=True):
 def prof_collect():
     """[(kernel label, device ms)] for every launch since prof_enable(True)."""
     L = lib()
-    L.dpk_prof_get.argtypes = [C.c_int, C.c_char_p, C.POINTER(C.c_float)]
     out = []
     name = C.create_string_buffer(64)
     ms = C.c_float()

@@ -2,12 +2,17 @@
 // (dpark/shuffle.py:600-608): combined[k] = mergeCombiners(combined[k], v) over
 // every row fetched for the reduce partitions this GPU owns.
 //
-// v1 design: one open-addressing table in HBM for all local partitions (keys of
-// different partitions are different keys, so they can share a table); 16-byte
-// slots {key bits, accumulator} so a probe + update touches one 32 B sector.
+// Design: open addressing in HBM with 16-byte slots {key bits, accumulator} (a
+// probe + update touches one 32 B sector), ONE TABLE REGION PER FINE BUCKET.
+// The map side already grouped rows by fine bucket (partition x 2^sub_bits), so
+// rows that are adjacent in memory hit the same small region: with ~0.5 M rows per
+// bucket the region (~12 MB) lives in the 126 MB L2 while it is being filled and
+// the atomics run at L2 speed instead of one random DRAM sector per row.
+//   k_tbl_plan    : per-bucket region offsets (1.5 x rows) + per-partition output offsets
 //   k_tbl_init    : slots <- {EMPTY, identity(op)}
-//   k_tbl_insert  : per row: claim slot with atomicCAS on the key word (linear
-//                   probing), then one native atomic on the accumulator.
+//   k_tbl_insert  : per row: bucket from the key's hash, claim a slot with atomicCAS
+//                   on the key word (linear probing inside the region), then one
+//                   native atomic on the accumulator.
 //   k_tbl_compact : per occupied slot: recompute its partition, reserve an output
 //                   index inside that partition's range (CTA-aggregated), write.
 // Accumulators: int64 for integer values (exact while |sum| < 2^63, as the
@@ -111,58 +116,101 @@ template <> struct Acc<double> {
 };
 
 // ---- kernels ---------------------------------------------------------------
+// plan (single CTA): bucket_rows[F] -> tbl_off[F+1] (slot offsets, region b holds
+// 1.5*rows_b + 32 slots rounded to 8) and part_off[nparts+1] (row offsets of the
+// partitions = upper bound of their output ranges).
 __global__ void __launch_bounds__(CB_THREADS)
-k_tbl_init(Slot *__restrict__ table, int64_t slots, int64_t ident) {
+k_tbl_plan(const int64_t *__restrict__ bucket_rows, int32_t F, int32_t sub_bits, int32_t nparts,
+           int64_t *__restrict__ tbl_off, int64_t *__restrict__ part_off) {
+    __shared__ long long s_slots[CB_THREADS], s_rows[CB_THREADS];
+    const int E = (F + CB_THREADS - 1) / CB_THREADS;
+    const int b0 = threadIdx.x * E, b1 = min(b0 + E, F);
+    long long slots = 0, rows = 0;
+    for (int b = b0; b < b1; b++) {
+        long long r = bucket_rows[b];
+        slots += ((r + (r >> 1) + 32 + 7) >> 3) << 3;
+        rows += r;
+    }
+    s_slots[threadIdx.x] = slots;
+    s_rows[threadIdx.x] = rows;
+    __syncthreads();
+    long long sbase = 0, rbase = 0;
+    for (int t = 0; t < (int)threadIdx.x; t++) { sbase += s_slots[t]; rbase += s_rows[t]; }
+    const int S = 1 << sub_bits;
+    for (int b = b0; b < b1; b++) {
+        tbl_off[b] = sbase;
+        if ((b & (S - 1)) == 0) part_off[b >> sub_bits] = rbase;
+        long long r = bucket_rows[b];
+        sbase += ((r + (r >> 1) + 32 + 7) >> 3) << 3;
+        rbase += r;
+    }
+    if (b0 < F && b1 == F) { tbl_off[F] = sbase; part_off[nparts] = rbase; }
+    if (F == 0 && threadIdx.x == 0) { tbl_off[0] = 0; part_off[0] = 0; }
+}
+
+// slots [0, tbl_off[F]) plus the side slot at index max_slots
+__global__ void __launch_bounds__(CB_THREADS)
+k_tbl_init(Slot *__restrict__ table, const int64_t *__restrict__ tbl_total, int64_t max_slots, int64_t ident) {
+    const int64_t slots = *tbl_total;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int4 fill = make_int4((int)(uint32_t)((uint64_t)kEmpty & 0xffffffffu), (int)(uint32_t)((uint64_t)kEmpty >> 32),
                                 (int)(uint32_t)((uint64_t)ident & 0xffffffffu), (int)(uint32_t)((uint64_t)ident >> 32));
+    if (i == 0) reinterpret_cast<int4 *>(table)[max_slots] = fill;
     for (; i < slots; i += stride) reinterpret_cast<int4 *>(table)[i] = fill;
 }
 
 template <typename KeyT, typename ValT, typename AccT>
 __global__ void __launch_bounds__(CB_THREADS)
-k_tbl_insert(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, int64_t n, int op,
-             Slot *__restrict__ table, uint64_t mask, Slot *__restrict__ side, int32_t *__restrict__ side_used) {
+k_tbl_insert(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, int64_t n, int op, PartFn f,
+             int32_t bucket_first, int32_t F, const int64_t *__restrict__ tbl_off, Slot *__restrict__ table,
+             Slot *__restrict__ side, int32_t *__restrict__ side_used) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
-        const int64_t kb = key_bits<KeyT>(keys[i]);
+        const KeyT key = keys[i];
+        const int64_t kb = key_bits<KeyT>(key);
         const AccT v = (AccT)vals[i];
         Slot *s;
         if (kb == kEmpty) {
             s = side;
             *side_used = 1;
         } else {
-            uint64_t h = mix64((uint64_t)kb) & mask;
+            int b = f.bucket(KeyHash<KeyT>::of(key)) - bucket_first;
+            b = min(max(b, 0), F - 1);  // rows of foreign partitions cannot occur; stay in bounds regardless
+            const int64_t base = __ldg(&tbl_off[b]);
+            const uint32_t size = (uint32_t)(__ldg(&tbl_off[b + 1]) - base);
+            uint32_t h = (uint32_t)(((mix64((uint64_t)kb) & 0xffffffffull) * (uint64_t)size) >> 32);
+            Slot *region = table + base;
             for (;;) {
-                int64_t cur = __ldcg(&table[h].key);
+                int64_t cur = __ldcg(&region[h].key);
                 if (cur == kb) break;
                 if (cur == kEmpty) {
-                    unsigned long long prev = atomicCAS((unsigned long long *)&table[h].key,
+                    unsigned long long prev = atomicCAS((unsigned long long *)&region[h].key,
                                                         (unsigned long long)kEmpty, (unsigned long long)kb);
                     if (prev == (unsigned long long)kEmpty || prev == (unsigned long long)kb) break;
                 }
-                h = (h + 1) & mask;
+                h = h + 1 == size ? 0 : h + 1;
             }
-            s = &table[h];
+            s = &region[h];
         }
         Acc<AccT>::apply(op, &s->acc, v);
     }
 }
 
-// slots [0, nslots) are the table; slot nslots is the side slot (valid iff *side_used)
+// slots [0, *tbl_total) are the tables; slot max_slots is the side slot (valid iff *side_used)
 template <typename KeyT>
 __global__ void __launch_bounds__(CB_THREADS)
-k_tbl_compact(const Slot *__restrict__ table, int64_t nslots, const int32_t *__restrict__ side_used,
-              PartFn f, int32_t part_first, int32_t nparts, const int64_t *__restrict__ part_offsets,
-              KeyT *__restrict__ out_keys, int64_t *__restrict__ out_vals,
-              unsigned long long *__restrict__ out_counts) {
+k_tbl_compact(const Slot *__restrict__ table, const int64_t *__restrict__ tbl_total, int64_t max_slots,
+              const int32_t *__restrict__ side_used, PartFn f, int32_t part_first, int32_t nparts,
+              const int64_t *__restrict__ part_offsets, KeyT *__restrict__ out_keys,
+              int64_t *__restrict__ out_vals, unsigned long long *__restrict__ out_counts) {
     extern __shared__ __align__(16) int32_t s_mem[];  // [nparts] counts, [nparts] 64-bit bases after
     int32_t *s_cnt = s_mem;
     long long *s_base = reinterpret_cast<long long *>(s_mem + ((nparts + 1) & ~1));
     const int lane = threadIdx.x & 31;
     constexpr int ITEMS = 4;
+    const int64_t nslots = *tbl_total;
     const int64_t total = nslots + 1;
     const int64_t tile = (int64_t)CB_THREADS * ITEMS;
     for (int64_t t0 = (int64_t)blockIdx.x * tile; t0 < total; t0 += (int64_t)gridDim.x * tile) {
@@ -175,7 +223,7 @@ k_tbl_compact(const Slot *__restrict__ table, int64_t nslots, const int32_t *__r
             int64_t i = t0 + (int64_t)j * CB_THREADS + threadIdx.x;
             lp[j] = -1;
             if (i < total) {
-                int4 raw = __ldcs(reinterpret_cast<const int4 *>(table) + i);
+                int4 raw = __ldcs(reinterpret_cast<const int4 *>(table) + (i < nslots ? i : max_slots));
                 kb[j] = (int64_t)(((uint64_t)(uint32_t)raw.y << 32) | (uint32_t)raw.x);
                 acc[j] = (int64_t)(((uint64_t)(uint32_t)raw.w << 32) | (uint32_t)raw.z);
                 bool occ = (i < nslots) ? (kb[j] != kEmpty) : (*side_used != 0);
@@ -210,12 +258,8 @@ k_tbl_compact(const Slot *__restrict__ table, int64_t nslots, const int32_t *__r
     }
 }
 
-static inline int64_t pow2ceil(int64_t x) {
-    int64_t p = 1024;
-    while (p < x) p <<= 1;
-    return p;
-}
-static inline int64_t table_slots_for(int64_t n) { return pow2ceil(2 * (n > 0 ? n : 1)); }
+// host-side upper bound of the slot count for n rows in F buckets
+static inline int64_t max_slots_for(int64_t n, int32_t F) { return n + (n >> 1) + (int64_t)F * 40 + 64; }
 
 static inline int grid_cap(int64_t items, int per_cta, int waves) {
     int64_t g = (items + per_cta - 1) / per_cta;
@@ -225,46 +269,62 @@ static inline int grid_cap(int64_t items, int per_cta, int waves) {
     return (int)g;
 }
 
+struct Ctx {
+    const void *keys, *vals;
+    int64_t n;
+    int op;
+    PartFn f;
+    int32_t part_first, nparts, F;
+    const int64_t *tbl_off;
+    Slot *table, *side;
+    int64_t max_slots;
+    int32_t *side_used;
+    cudaStream_t st;
+};
+
 template <typename KeyT, typename ValT, typename AccT>
-static int dispatch_op(int op, const void *keys, const void *vals, int64_t n, Slot *table, int64_t slots,
-                       Slot *side, int32_t *side_used, cudaStream_t st) {
-    if (!Acc<AccT>::supports(op)) return fail(DPK_ERR_UNSUPPORTED, "op %d unsupported for this value kind", op);
-    DPK_LAUNCH("tbl_init", st, k_tbl_init<<<grid_cap(slots + 1, CB_THREADS, 16), CB_THREADS, 0, st>>>(table, slots + 1, Acc<AccT>::identity(op)));
-    if (n > 0) {
-        DPK_LAUNCH("tbl_insert", st, k_tbl_insert<KeyT, ValT, AccT><<<grid_cap(n, CB_THREADS, 16), CB_THREADS, 0, st>>>(
-            (const KeyT *)keys, (const ValT *)vals, n, op, table, (uint64_t)(slots - 1), side, side_used));
+static int dispatch_op(const Ctx &c) {
+    if (!Acc<AccT>::supports(c.op)) return fail(DPK_ERR_UNSUPPORTED, "op %d unsupported for this value kind", c.op);
+    DPK_LAUNCH("tbl_init", c.st, k_tbl_init<<<grid_cap(c.max_slots, CB_THREADS, 16), CB_THREADS, 0, c.st>>>(
+        c.table, c.tbl_off + c.F, c.max_slots, Acc<AccT>::identity(c.op)));
+    if (c.n > 0) {
+        DPK_LAUNCH("tbl_insert", c.st, k_tbl_insert<KeyT, ValT, AccT><<<grid_cap(c.n, CB_THREADS, 16), CB_THREADS, 0, c.st>>>(
+            (const KeyT *)c.keys, (const ValT *)c.vals, c.n, c.op, c.f, c.part_first << c.f.sub_bits, c.F,
+            c.tbl_off, c.table, c.side, c.side_used));
     }
     return DPK_OK;
 }
 
 template <typename KeyT>
-static int dispatch_valkind(int val_kind, int op, const void *keys, const void *vals, int64_t n, Slot *table,
-                            int64_t slots, Slot *side, int32_t *side_used, cudaStream_t st) {
+static int dispatch_valkind(int val_kind, const Ctx &c) {
     switch (val_kind) {
-    case DPK_V_I64: return dispatch_op<KeyT, int64_t, int64_t>(op, keys, vals, n, table, slots, side, side_used, st);
-    case DPK_V_I32: return dispatch_op<KeyT, int32_t, int64_t>(op, keys, vals, n, table, slots, side, side_used, st);
-    case DPK_V_F64: return dispatch_op<KeyT, double, double>(op, keys, vals, n, table, slots, side, side_used, st);
-    case DPK_V_F32: return dispatch_op<KeyT, float, double>(op, keys, vals, n, table, slots, side, side_used, st);
+    case DPK_V_I64: return dispatch_op<KeyT, int64_t, int64_t>(c);
+    case DPK_V_I32: return dispatch_op<KeyT, int32_t, int64_t>(c);
+    case DPK_V_F64: return dispatch_op<KeyT, double, double>(c);
+    case DPK_V_F32: return dispatch_op<KeyT, float, double>(c);
     }
     return fail(DPK_ERR_UNSUPPORTED, "value kind %d unsupported", val_kind);
 }
 
 template <typename KeyT>
-static int run_combine(const void *keys, const void *vals, int val_kind, int64_t n, int op, const PartFn &f,
-                       int32_t part_first, int32_t nparts, const int64_t *part_offsets, void *out_keys,
-                       void *out_vals, int64_t *out_counts, void *ws, cudaStream_t st) {
-    const int64_t slots = table_slots_for(n);
-    Slot *table = (Slot *)ws;
-    Slot *side = table + slots;
-    int32_t *side_used = (int32_t *)(side + 1);
-    DPK_CUDA_TRY(cudaMemsetAsync(side_used, 0, 16, st));
-    DPK_CUDA_TRY(cudaMemsetAsync(out_counts, 0, (size_t)nparts * 8, st));
-    int rc = dispatch_valkind<KeyT>(val_kind, op, keys, vals, n, table, slots, side, side_used, st);
+static int run_combine(Ctx &c, int val_kind, const int64_t *bucket_rows, void *out_keys, void *out_vals,
+                       int64_t *out_offsets, int64_t *out_counts, void *ws) {
+    // workspace: Slot table[max_slots] | Slot side | int32 side_used[4] | int64 tbl_off[F+1]
+    c.table = (Slot *)ws;
+    c.side = c.table + c.max_slots;
+    c.side_used = (int32_t *)(c.side + 1);
+    int64_t *tbl_off = (int64_t *)(c.side_used + 4);
+    c.tbl_off = tbl_off;
+    DPK_CUDA_TRY(cudaMemsetAsync(c.side_used, 0, 16, c.st));
+    DPK_CUDA_TRY(cudaMemsetAsync(out_counts, 0, (size_t)c.nparts * 8, c.st));
+    DPK_LAUNCH("tbl_plan", c.st, k_tbl_plan<<<1, CB_THREADS, 0, c.st>>>(bucket_rows, c.F, c.f.sub_bits, c.nparts,
+                                                                       tbl_off, out_offsets));
+    int rc = dispatch_valkind<KeyT>(val_kind, c);
     if (rc) return rc;
-    size_t sh = (size_t)((nparts + 1) & ~1) * 4 + (size_t)nparts * 8;
-    DPK_LAUNCH("tbl_compact", st, k_tbl_compact<KeyT><<<grid_cap(slots + 1, CB_THREADS * 4, 8), CB_THREADS, sh, st>>>(
-        table, slots, side_used, f, part_first, nparts, part_offsets, (KeyT *)out_keys, (int64_t *)out_vals,
-        (unsigned long long *)out_counts));
+    size_t sh = (size_t)((c.nparts + 1) & ~1) * 4 + (size_t)c.nparts * 8;
+    DPK_LAUNCH("tbl_compact", c.st, k_tbl_compact<KeyT><<<grid_cap(c.max_slots, CB_THREADS * 4, 8), CB_THREADS, sh, c.st>>>(
+        c.table, tbl_off + c.F, c.max_slots, c.side_used, c.f, c.part_first, c.nparts, out_offsets,
+        (KeyT *)out_keys, (int64_t *)out_vals, (unsigned long long *)out_counts));
     return DPK_OK;
 }
 
@@ -274,33 +334,37 @@ using namespace dpk;
 
 extern "C" {
 
-int64_t dpk_combine_workspace_bytes(int64_t n) {
+int64_t dpk_combine_workspace_bytes(int64_t n, int32_t nbuckets) {
     if (n < 0) n = 0;
-    return (table_slots_for(n) + 2) * (int64_t)sizeof(Slot);
+    if (nbuckets < 1) nbuckets = 1;
+    return (max_slots_for(n, nbuckets) + 2) * (int64_t)sizeof(Slot) + ((int64_t)nbuckets + 2) * 8 + 64;
 }
 
 int dpk_combine(const void *keys, int key_kind, const void *vals, int val_kind, int64_t n, int op, int32_t P,
-                const int64_t *thresholds, int32_t nthr, int32_t part_first, int32_t nparts,
-                const int64_t *part_offsets, void *out_keys, void *out_vals, int64_t *out_counts, void *ws,
-                int64_t ws_bytes, dpk_stream_t stream) {
+                const int64_t *thresholds, int32_t nthr, int32_t sub_bits, int32_t part_first, int32_t nparts,
+                const int64_t *bucket_rows, void *out_keys, void *out_vals, int64_t *out_offsets,
+                int64_t *out_counts, void *ws, int64_t ws_bytes, dpk_stream_t stream) {
     if (n < 0 || n >= ((int64_t)1 << 31)) return fail(DPK_ERR_INVALID, "n=%lld out of range [0, 2^31)", (long long)n);
     if (nparts < 1 || part_first < 0 || part_first + nparts > P)
         return fail(DPK_ERR_INVALID, "bad partition range first=%d n=%d P=%d", part_first, nparts, P);
-    if (nparts > 4096) return fail(DPK_ERR_UNSUPPORTED, "nparts=%d > 4096", nparts);
-    if (!part_offsets || !out_counts || !ws) return fail(DPK_ERR_INVALID, "NULL pointer");
+    if (!bucket_rows || !out_counts || !out_offsets || !ws) return fail(DPK_ERR_INVALID, "NULL pointer");
     if (n > 0 && (!keys || !vals || !out_keys || !out_vals)) return fail(DPK_ERR_INVALID, "NULL pointer");
-    if (ws_bytes < dpk_combine_workspace_bytes(n))
-        return fail(DPK_ERR_WORKSPACE, "workspace needs %lld B, got %lld", (long long)dpk_combine_workspace_bytes(n), (long long)ws_bytes);
-    PartFn f;
-    int rc = make_partfn(P, thresholds, nthr, &f);
+    Ctx c;
+    int rc = make_partfn(P, thresholds, nthr, sub_bits, &c.f);
     if (rc) return rc;
-    cudaStream_t st = (cudaStream_t)stream;
+    c.F = nparts << sub_bits;
+    if (ws_bytes < dpk_combine_workspace_bytes(n, c.F))
+        return fail(DPK_ERR_WORKSPACE, "workspace needs %lld B, got %lld", (long long)dpk_combine_workspace_bytes(n, c.F), (long long)ws_bytes);
+    c.keys = keys; c.vals = vals; c.n = n; c.op = op;
+    c.part_first = part_first; c.nparts = nparts;
+    c.max_slots = max_slots_for(n, c.F);
+    c.st = (cudaStream_t)stream;
     switch (key_kind) {
-    case DPK_K_I64: return run_combine<int64_t>(keys, vals, val_kind, n, op, f, part_first, nparts, part_offsets, out_keys, out_vals, out_counts, ws, st);
-    case DPK_K_I32: return run_combine<int32_t>(keys, vals, val_kind, n, op, f, part_first, nparts, part_offsets, out_keys, out_vals, out_counts, ws, st);
-    case DPK_K_F64: return run_combine<double>(keys, vals, val_kind, n, op, f, part_first, nparts, part_offsets, out_keys, out_vals, out_counts, ws, st);
-    case DPK_K_U64: return run_combine<uint64_t>(keys, vals, val_kind, n, op, f, part_first, nparts, part_offsets, out_keys, out_vals, out_counts, ws, st);
-    case DPK_K_F32: return run_combine<float>(keys, vals, val_kind, n, op, f, part_first, nparts, part_offsets, out_keys, out_vals, out_counts, ws, st);
+    case DPK_K_I64: return run_combine<int64_t>(c, val_kind, bucket_rows, out_keys, out_vals, out_offsets, out_counts, ws);
+    case DPK_K_I32: return run_combine<int32_t>(c, val_kind, bucket_rows, out_keys, out_vals, out_offsets, out_counts, ws);
+    case DPK_K_F64: return run_combine<double>(c, val_kind, bucket_rows, out_keys, out_vals, out_offsets, out_counts, ws);
+    case DPK_K_U64: return run_combine<uint64_t>(c, val_kind, bucket_rows, out_keys, out_vals, out_offsets, out_counts, ws);
+    case DPK_K_F32: return run_combine<float>(c, val_kind, bucket_rows, out_keys, out_vals, out_offsets, out_counts, ws);
     }
     return fail(DPK_ERR_UNSUPPORTED, "key kind %d is unhashable by portable_hash", key_kind);
 }

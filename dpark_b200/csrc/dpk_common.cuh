@@ -137,6 +137,24 @@ struct PartFn {
     int32_t shift;
     int32_t nthr;
     const int64_t *thresholds;
+    // fine buckets: each reduce partition is split into 2^sub_bits sub-buckets by
+    // other bits of the key's hash (an internal layout detail -- partition p still
+    // owns exactly the keys the reference gives it; its rows are the concatenation
+    // of its sub-buckets).  Sub-buckets bound the reduce-side table working set so
+    // it stays resident in the 126 MB L2.
+    int32_t sub_bits;
+
+    DPK_HD int32_t nbuckets() const { return P << sub_bits; }
+    // bucket id = partition * 2^sub_bits + sub, sub a function of the hash only
+    // (equal keys -> equal hash -> same bucket)
+    DPK_HD int32_t bucket(int64_t h) const {
+        int32_t p = (*this)(h);
+        if (sub_bits == 0) return p;
+        uint64_t m = (uint64_t)h * 0x9E3779B97F4A7C15ull;
+        m ^= m >> 29;
+        m *= 0xBF58476D1CE4E5B9ull;
+        return (p << sub_bits) | (int32_t)(m >> (64 - sub_bits));
+    }
 
     DPK_HD int32_t operator()(int64_t h) const {
         if (mode == 1) return (int32_t)((uint64_t)h & (uint64_t)(P - 1));  // two's complement == floor-mod
@@ -164,7 +182,7 @@ struct PartFn {
     }
 };
 // host: build the functor (thresholds is a device pointer, only stored)
-int make_partfn(int32_t P, const int64_t *thresholds, int32_t nthr, PartFn *out);
+int make_partfn(int32_t P, const int64_t *thresholds, int32_t nthr, int32_t sub_bits, PartFn *out);
 
 // murmur3 fmix64 -- slot hash for the reduce-side tables (not part of the
 // reference semantics; only spreads keys over table slots)

@@ -53,10 +53,12 @@ ProfScope::~ProfScope() {
     if (idx >= 0) cudaEventRecord(g_ev1[idx], st);
 }
 
-int make_partfn(int32_t P, const int64_t *thresholds, int32_t nthr, PartFn *out) {
+int make_partfn(int32_t P, const int64_t *thresholds, int32_t nthr, int32_t sub_bits, PartFn *out) {
     if (P < 1) return fail(DPK_ERR_INVALID, "P must be >= 1, got %d", P);
+    if (sub_bits < 0 || sub_bits > 12 || ((int64_t)P << sub_bits) > DPK_MAX_PARTITIONS)
+        return fail(DPK_ERR_UNSUPPORTED, "P=%d with sub_bits=%d exceeds %d buckets", P, sub_bits, DPK_MAX_PARTITIONS);
     PartFn f;
-    f.P = P; f.magic = 0; f.shift = 0; f.nthr = 0; f.thresholds = nullptr;
+    f.P = P; f.magic = 0; f.shift = 0; f.nthr = 0; f.thresholds = nullptr; f.sub_bits = sub_bits;
     if (thresholds != nullptr) {
         if (nthr != P - 1) return fail(DPK_ERR_INVALID, "thresholds need P-1=%d entries, got %d", P - 1, nthr);
         f.mode = 3; f.nthr = nthr; f.thresholds = thresholds;
@@ -166,7 +168,7 @@ int dpk_partition_ids(const int64_t *hash, int64_t n, int32_t P, const int64_t *
                       int32_t nthr, int32_t *out_pid, dpk_stream_t stream) {
     if (n < 0) return fail(DPK_ERR_INVALID, "n < 0");
     PartFn f;
-    int rc = make_partfn(P, thresholds, nthr, &f);
+    int rc = make_partfn(P, thresholds, nthr, 0, &f);
     if (rc) return rc;
     if (n == 0) return DPK_OK;
     if (!hash || !out_pid) return fail(DPK_ERR_INVALID, "NULL pointer");

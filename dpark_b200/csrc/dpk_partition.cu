@@ -88,8 +88,8 @@ template <typename KeyT, bool PRE>
 __global__ void __launch_bounds__(PT_THREADS)
 k_part_count(const KeyT *__restrict__ keys, int64_t n, int64_t L, PartFn f,
              int32_t *__restrict__ tile_counts, int32_t T) {
-    extern __shared__ int32_t s_cnt[];  // [P]
-    const int P = f.P;
+    extern __shared__ int32_t s_cnt[];  // [buckets]
+    const int P = f.nbuckets();
     for (int p = threadIdx.x; p < P; p += PT_THREADS) s_cnt[p] = 0;
     __syncthreads();
     const int64_t beg = (int64_t)blockIdx.x * L;
@@ -107,7 +107,7 @@ k_part_count(const KeyT *__restrict__ keys, int64_t n, int64_t L, PartFn f,
         }
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            int pid = ok[u] ? f(key_hash<KeyT, PRE>(k[u])) : -1;
+            int pid = ok[u] ? f.bucket(key_hash<KeyT, PRE>(k[u])) : -1;
             unsigned m = __match_any_sync(0xffffffffu, pid);
             if (ok[u] && lane == __ffs(m) - 1) atomicAdd(&s_cnt[pid], __popc(m));
         }
@@ -191,7 +191,7 @@ k_part_scatter(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, int
     uint16_t *s_pid = reinterpret_cast<uint16_t *>(smem + lay.pid_off);
     uint16_t *s_whist = reinterpret_cast<uint16_t *>(smem + lay.whist_off);  // [PT_WARPS][P]
 
-    const int P = f.P;
+    const int P = f.nbuckets();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     const int64_t beg = (int64_t)blockIdx.x * L;
@@ -230,7 +230,7 @@ k_part_scatter(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, int
 #pragma unroll
         for (int j = 0; j < PT_ITEMS; j++) {
             const bool ok = (wbase + j * 32) < end;
-            const int p = ok ? f(key_hash<KeyT, PRE>(k[j])) : P;  // P = "no row"
+            const int p = ok ? f.bucket(key_hash<KeyT, PRE>(k[j])) : P;  // P = "no row"
             const unsigned m = __match_any_sync(0xffffffffu, p);
             int base = 0;
             if (ok) base = wh[p];
@@ -298,7 +298,7 @@ k_part_scatter(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, int
 template <typename KeyT, bool PRE>
 static int launch_count(const void *keys, int64_t n, const Plan &pl, const PartFn &f,
                         int32_t *tile_counts, cudaStream_t st) {
-    size_t sh = (size_t)f.P * sizeof(int32_t);
+    size_t sh = (size_t)f.nbuckets() * sizeof(int32_t);
     DPK_LAUNCH("part_count", st, k_part_count<KeyT, PRE><<<pl.T, PT_THREADS, sh, st>>>((const KeyT *)keys, n, pl.L, f, tile_counts, pl.T));
     return DPK_OK;
 }
@@ -321,10 +321,10 @@ static int launch_scatter(const void *keys, const void *vals, int64_t n, const P
                           const int32_t *tile_off, const int64_t *bucket_base, void *out_keys,
                           void *out_vals, cudaStream_t st) {
     constexpr int vb = std::is_same<ValT, NoVal>::value ? 0 : (int)sizeof(ValT);
-    ScatterSmem lay = scatter_smem((int)sizeof(KeyT), vb, f.P);
+    ScatterSmem lay = scatter_smem((int)sizeof(KeyT), vb, f.nbuckets());
     auto kern = k_part_scatter<KeyT, ValT, PRE>;
     if (lay.total > 227 * 1024)
-        return fail(DPK_ERR_UNSUPPORTED, "P=%d needs %lld B of shared memory", f.P, (long long)lay.total);
+        return fail(DPK_ERR_UNSUPPORTED, "%d buckets need %lld B of shared memory", f.nbuckets(), (long long)lay.total);
     DPK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
     DPK_LAUNCH("part_scatter", st,
                kern<<<pl.T, PT_THREADS, (size_t)lay.total, st>>>((const KeyT *)keys, (const ValT *)vals, n, pl.L, f,
@@ -362,9 +362,11 @@ static int dispatch_scatter(const void *keys, int key_kind, const void *vals, in
     return fail(DPK_ERR_UNSUPPORTED, "key kind %d is unhashable by portable_hash", key_kind);
 }
 
-static int check_common(const void *keys, int64_t n, int32_t P, void *ws, int64_t ws_bytes) {
+static int check_common(const void *keys, int64_t n, int32_t P, int32_t sub_bits, void *ws, int64_t ws_bytes) {
     if (n < 0 || n >= ((int64_t)1 << 31)) return fail(DPK_ERR_INVALID, "n=%lld out of range [0, 2^31)", (long long)n);
-    if (P < 1 || P > DPK_MAX_PARTITIONS) return fail(DPK_ERR_UNSUPPORTED, "P=%d out of range [1, %d]", P, DPK_MAX_PARTITIONS);
+    if (P < 1 || sub_bits < 0 || sub_bits > 12 || ((int64_t)P << sub_bits) > DPK_MAX_PARTITIONS)
+        return fail(DPK_ERR_UNSUPPORTED, "P=%d (x 2^%d sub-buckets) out of range [1, %d]", P, sub_bits, DPK_MAX_PARTITIONS);
+    P <<= sub_bits;
     if (n > 0 && !keys) return fail(DPK_ERR_INVALID, "keys is NULL");
     if (!ws || ws_bytes < ws_total_bytes(P)) return fail(DPK_ERR_WORKSPACE, "workspace needs %lld B, got %lld", (long long)ws_total_bytes(P), (long long)ws_bytes);
     return DPK_OK;
@@ -376,43 +378,45 @@ using namespace dpk;
 
 extern "C" {
 
-int64_t dpk_partition_workspace_bytes(int64_t n, int32_t P) {
+int64_t dpk_partition_workspace_bytes(int64_t n, int32_t nbuckets) {
     (void)n;
-    if (P < 1) P = 1;
-    return ws_total_bytes(P);
+    if (nbuckets < 1) nbuckets = 1;
+    return ws_total_bytes(nbuckets);
 }
 
 int dpk_partition_count(const void *keys, int key_kind, int64_t n, int32_t P, const int64_t *thresholds,
-                        int32_t nthr, int64_t *out_counts, void *ws, int64_t ws_bytes,
+                        int32_t nthr, int32_t sub_bits, int64_t *out_counts, void *ws, int64_t ws_bytes,
                         dpk_stream_t stream) {
-    int rc = check_common(keys, n, P, ws, ws_bytes);
+    int rc = check_common(keys, n, P, sub_bits, ws, ws_bytes);
     if (rc) return rc;
     if (!out_counts) return fail(DPK_ERR_INVALID, "out_counts is NULL");
     PartFn f;
-    rc = make_partfn(P, thresholds, nthr, &f);
+    rc = make_partfn(P, thresholds, nthr, sub_bits, &f);
     if (rc) return rc;
+    const int32_t F = f.nbuckets();
     cudaStream_t st = (cudaStream_t)stream;
     int32_t *tile_counts = (int32_t *)ws;
     Plan pl = make_plan(n);
     if (n == 0) {
-        DPK_CUDA_TRY(cudaMemsetAsync(tile_counts, 0, (size_t)P * pl.T * 4, st));
+        DPK_CUDA_TRY(cudaMemsetAsync(tile_counts, 0, (size_t)F * pl.T * 4, st));
     } else {
         rc = dispatch_count(keys, key_kind, n, pl, f, tile_counts, st);
         if (rc) return rc;
     }
-    DPK_LAUNCH("part_scan", st, k_part_scan<<<P, PT_THREADS, 0, st>>>(tile_counts, pl.T, out_counts));
+    DPK_LAUNCH("part_scan", st, k_part_scan<<<F, PT_THREADS, 0, st>>>(tile_counts, pl.T, out_counts));
     return DPK_OK;
 }
 
 int dpk_partition_scatter(const void *keys, int key_kind, const void *vals, int32_t val_bytes, int64_t n,
-                          int32_t P, const int64_t *thresholds, int32_t nthr, const int64_t *bucket_base,
-                          void *out_keys, void *out_vals, void *ws, int64_t ws_bytes, dpk_stream_t stream) {
-    int rc = check_common(keys, n, P, ws, ws_bytes);
+                          int32_t P, const int64_t *thresholds, int32_t nthr, int32_t sub_bits,
+                          const int64_t *bucket_base, void *out_keys, void *out_vals, void *ws,
+                          int64_t ws_bytes, dpk_stream_t stream) {
+    int rc = check_common(keys, n, P, sub_bits, ws, ws_bytes);
     if (rc) return rc;
     if (n == 0) return DPK_OK;
     if (!bucket_base || !out_keys) return fail(DPK_ERR_INVALID, "NULL pointer");
     PartFn f;
-    rc = make_partfn(P, thresholds, nthr, &f);
+    rc = make_partfn(P, thresholds, nthr, sub_bits, &f);
     if (rc) return rc;
     Plan pl = make_plan(n);
     return dispatch_scatter(keys, key_kind, vals, val_bytes, n, pl, f, (const int32_t *)ws, bucket_base,
@@ -420,17 +424,18 @@ int dpk_partition_scatter(const void *keys, int key_kind, const void *vals, int3
 }
 
 int dpk_partition(const void *keys, int key_kind, const void *vals, int32_t val_bytes, int64_t n, int32_t P,
-                  const int64_t *thresholds, int32_t nthr, void *out_keys, void *out_vals,
+                  const int64_t *thresholds, int32_t nthr, int32_t sub_bits, void *out_keys, void *out_vals,
                   int64_t *out_offsets, void *ws, int64_t ws_bytes, dpk_stream_t stream) {
-    int rc = check_common(keys, n, P, ws, ws_bytes);
+    int rc = check_common(keys, n, P, sub_bits, ws, ws_bytes);
     if (rc) return rc;
     if (!out_offsets) return fail(DPK_ERR_INVALID, "out_offsets is NULL");
-    int64_t *totals = (int64_t *)((char *)ws + ws_counts_bytes(P));
-    rc = dpk_partition_count(keys, key_kind, n, P, thresholds, nthr, totals, ws, ws_bytes, stream);
+    const int32_t F = P << sub_bits;
+    int64_t *totals = (int64_t *)((char *)ws + ws_counts_bytes(F));
+    rc = dpk_partition_count(keys, key_kind, n, P, thresholds, nthr, sub_bits, totals, ws, ws_bytes, stream);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    DPK_LAUNCH("part_offsets", st, k_part_offsets<<<1, PT_THREADS, 0, st>>>(totals, P, out_offsets));
-    return dpk_partition_scatter(keys, key_kind, vals, val_bytes, n, P, thresholds, nthr, out_offsets,
+    DPK_LAUNCH("part_offsets", st, k_part_offsets<<<1, PT_THREADS, 0, st>>>(totals, F, out_offsets));
+    return dpk_partition_scatter(keys, key_kind, vals, val_bytes, n, P, thresholds, nthr, sub_bits, out_offsets,
                                  out_keys, out_vals, ws, ws_bytes, stream);
 }
 

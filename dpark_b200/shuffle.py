@@ -7,14 +7,25 @@ Mirrors, for the hot path only:
   DiskHashMerger._merge        dpark/shuffle.py:600-608   -> reduce_side()
   MapOutputTracker             dpark/shuffle.py:809-826   -> the counts matrix
 
-Partition ownership across G ranks: reduce partition r lives on rank
-r // ceil(P/G) (contiguous blocks), so the rows a rank sends to one peer are one
-contiguous range of its bucket-major buffer.  Map splits are assigned to ranks in
-contiguous blocks too, so "source rank order" == "map_id order".
+Layout.  The map side writes ONE bucket-major buffer per rank.  Buckets are the
+reference's P reduce partitions, each refined into 2^sub_bits sub-buckets by
+other hash bits (dpk_partition, include/dpark_b200.h): partition p is the
+concatenation of its sub-buckets, so everything the reference defines (which
+keys a partition owns, row order inside a bucket) is unchanged, while the
+reduce side gets L2-sized working sets.
+
+Ownership across G ranks: reduce partition r lives on rank r // ceil(P/G)
+(contiguous blocks), so what a rank sends to one peer is one contiguous range of
+its buffer.  Map splits are assigned to ranks in contiguous blocks too, so
+"source rank order" == "map_id order".
 """
 import torch
 
 from . import _native as nv
+
+# rows per fine bucket the reduce side aims for (table region = 1.5 x 16 B x rows
+# ~ 12 MB, a small fraction of the 126 MB L2)
+TARGET_BUCKET_ROWS = 1 << 19
 
 
 def owner_blocks(P, G):
@@ -23,52 +34,66 @@ def owner_blocks(P, G):
     return [min(P, g * per) for g in range(G + 1)]
 
 
+def choose_sub_bits(total_rows, P):
+    """Sub-bucket bits so that a fine bucket holds ~TARGET_BUCKET_ROWS rows of
+    the whole job, capped by the kernel's bucket limit."""
+    sb = 0
+    while (P << (sb + 1)) <= nv.MAX_PARTITIONS and sb < 12 and total_rows / float(P << sb) > TARGET_BUCKET_ROWS:
+        sb += 1
+    # keep the map side's write runs long: at most 1024 buckets
+    while sb > 0 and (P << sb) > 1024:
+        sb -= 1
+    return sb
+
+
 class MapOutput(object):
     """Bucket-major output of the map side on one rank: the alltoallv send buffer."""
-    __slots__ = ("keys", "vals", "offsets", "P")
+    __slots__ = ("keys", "vals", "offsets", "P", "sub_bits")
 
-    def __init__(self, keys, vals, offsets, P):
-        self.keys, self.vals, self.offsets, self.P = keys, vals, offsets, P
+    def __init__(self, keys, vals, offsets, P, sub_bits):
+        self.keys, self.vals, self.offsets, self.P, self.sub_bits = keys, vals, offsets, P, sub_bits
 
 
-def map_side(key_chunks, val_chunks, P, thresholds=None, prehashed=False):
+def map_side(key_chunks, val_chunks, P, thresholds=None, prehashed=False, sub_bits=0):
     """Hash-partition all local map splits into ONE bucket-major buffer.
 
     key_chunks/val_chunks: lists of CUDA tensors (the rank's map splits in map_id
-    order).  Rows of bucket p are ordered by (map split, position) -- the order
+    order).  Rows of a bucket are ordered by (map split, position) -- the order
     OrderedGroupByDiskHashMerger produces (dpark/shuffle.py:626-646)."""
+    F = P << sub_bits
     if len(key_chunks) == 1:
-        k, v, off = nv.partition(key_chunks[0], val_chunks[0], P, thresholds, prehashed)
-        return MapOutput(k, v, off, P)
+        k, v, off = nv.partition(key_chunks[0], val_chunks[0], P, thresholds, prehashed, sub_bits)
+        return MapOutput(k, v, off, P, sub_bits)
     dev = key_chunks[0].device
     counts, wss = [], []
     for k in key_chunks:
-        c, ws = nv.partition_count(k, P, thresholds, prehashed)
+        c, ws = nv.partition_count(k, P, thresholds, prehashed, sub_bits)
         counts.append(c)
         wss.append(ws)
-    cm = torch.stack(counts)                       # [M, P]
+    cm = torch.stack(counts)                       # [M, F]
     tot = cm.sum(0)                                # rows per bucket
-    offsets = torch.zeros(P + 1, dtype=torch.int64, device=dev)
+    offsets = torch.zeros(F + 1, dtype=torch.int64, device=dev)
     torch.cumsum(tot, 0, out=offsets[1:])
-    # base[m][p] = offsets[p] + rows of bucket p in earlier splits
+    # base[m][b] = offsets[b] + rows of bucket b in earlier splits
     base = offsets[:-1].unsqueeze(0) + (torch.cumsum(cm, 0) - cm)
     n = sum(int(k.numel()) for k in key_chunks)
     out_k = torch.empty(n, dtype=key_chunks[0].dtype, device=dev)
     has_v = val_chunks[0] is not None
     out_v = torch.empty(n, dtype=val_chunks[0].dtype, device=dev) if has_v else None
     for m, (k, v) in enumerate(zip(key_chunks, val_chunks)):
-        nv.partition_scatter(k, v, P, base[m].contiguous(), out_k, out_v, wss[m], thresholds, prehashed)
-    return MapOutput(out_k, out_v, offsets, P)
+        nv.partition_scatter(k, v, P, base[m].contiguous(), out_k, out_v, wss[m], thresholds, prehashed, sub_bits)
+    return MapOutput(out_k, out_v, offsets, P, sub_bits)
 
 
 class Received(object):
     """Rows fetched for the partitions this rank owns.  keys/vals are laid out
-    source-rank-major, then bucket-major; seg[s][j] = rows from source s for
-    local partition j."""
-    __slots__ = ("keys", "vals", "seg", "part_first", "nparts")
+    source-rank-major, then bucket-major; seg[s][b] = rows from source s for
+    local fine bucket b."""
+    __slots__ = ("keys", "vals", "seg", "part_first", "nparts", "sub_bits")
 
-    def __init__(self, keys, vals, seg, part_first, nparts):
-        self.keys, self.vals, self.seg, self.part_first, self.nparts = keys, vals, seg, part_first, nparts
+    def __init__(self, keys, vals, seg, part_first, nparts, sub_bits):
+        self.keys, self.vals, self.seg = keys, vals, seg
+        self.part_first, self.nparts, self.sub_bits = part_first, nparts, sub_bits
 
 
 def exchange(mo, group=None):
@@ -77,20 +102,21 @@ def exchange(mo, group=None):
     ncclSend/ncclRecv over NVLink).  With one rank it is the identity."""
     import torch.distributed as dist
     G = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
-    P = mo.P
+    P, sb = mo.P, mo.sub_bits
     if G == 1:
         seg = (mo.offsets[1:] - mo.offsets[:-1]).unsqueeze(0)
-        return Received(mo.keys, mo.vals, seg, 0, P)
+        return Received(mo.keys, mo.vals, seg, 0, P, sb)
     rank = dist.get_rank(group)
-    blocks = owner_blocks(P, G)
-    counts = mo.offsets[1:] - mo.offsets[:-1]                       # [P] rows I hold per bucket
-    all_counts = torch.empty(G * P, dtype=torch.int64, device=counts.device)
-    dist.all_gather_into_tensor(all_counts, counts.contiguous(), group=group)   # MapOutputTracker
-    all_counts = all_counts.view(G, P)
-    host_counts = all_counts.cpu()                                  # sizes must be known on the host
+    F = P << sb
+    blocks = [b << sb for b in owner_blocks(P, G)]                  # in fine buckets
+    counts = (mo.offsets[1:] - mo.offsets[:-1]).contiguous()        # [F] rows I hold per bucket
+    all_counts = torch.empty(G * F, dtype=torch.int64, device=counts.device)
+    dist.all_gather_into_tensor(all_counts, counts, group=group)    # MapOutputTracker
+    all_counts = all_counts.view(G, F)
+    host_counts = all_counts.cpu()                                  # split sizes must be known on the host
     send_splits = [int(host_counts[rank, blocks[d]:blocks[d + 1]].sum()) for d in range(G)]
-    p0, p1 = blocks[rank], blocks[rank + 1]
-    recv_splits = [int(host_counts[s, p0:p1].sum()) for s in range(G)]
+    b0, b1 = blocks[rank], blocks[rank + 1]
+    recv_splits = [int(host_counts[s, b0:b1].sum()) for s in range(G)]
     nrecv = sum(recv_splits)
     rk = torch.empty(nrecv, dtype=mo.keys.dtype, device=mo.keys.device)
     dist.all_to_all_single(rk, mo.keys, recv_splits, send_splits, group=group)
@@ -98,8 +124,8 @@ def exchange(mo, group=None):
     if mo.vals is not None:
         rv = torch.empty(nrecv, dtype=mo.vals.dtype, device=mo.vals.device)
         dist.all_to_all_single(rv, mo.vals, recv_splits, send_splits, group=group)
-    seg = all_counts[:, p0:p1].contiguous()
-    return Received(rk, rv, seg, p0, p1 - p0)
+    seg = all_counts[:, b0:b1].contiguous()
+    return Received(rk, rv, seg, b0 >> sb, (b1 - b0) >> sb, sb)
 
 
 def reduce_side(rx, op, P, thresholds=None):
@@ -107,14 +133,11 @@ def reduce_side(rx, op, P, thresholds=None):
     (keys, vals, part_offsets[nparts+1], counts[nparts]): distinct keys of local
     partition j are keys[part_offsets[j] : part_offsets[j] + counts[j]]."""
     dev = rx.keys.device
-    rows = rx.seg.sum(0)                                            # rows per local partition
-    part_offsets = torch.zeros(rx.nparts + 1, dtype=torch.int64, device=dev)
-    if rx.nparts:
-        torch.cumsum(rows, 0, out=part_offsets[1:])
     if rx.nparts == 0:
-        return rx.keys[:0], rx.vals[:0], part_offsets, rows
-    ok, ov, cnt = nv.combine(rx.keys, rx.vals, op, P, part_offsets, rx.part_first, rx.nparts, thresholds)
-    return ok, ov, part_offsets, cnt
+        z = torch.zeros(1, dtype=torch.int64, device=dev)
+        return rx.keys[:0], (rx.vals[:0] if rx.vals is not None else None), z, z[:0]
+    bucket_rows = rx.seg.sum(0).contiguous()                        # rows per local fine bucket
+    return nv.combine(rx.keys, rx.vals, op, P, bucket_rows, rx.part_first, rx.nparts, thresholds, rx.sub_bits)
 
 
 class HostShuffle(object):
@@ -125,10 +148,11 @@ class HostShuffle(object):
     distinct (key, combined) rows.  Buffers are allocated once and reused."""
 
     def __init__(self, n_rows, key_dtype, val_dtype, P, op="sum", splits=8, thresholds=None, group=None,
-                 device=None):
+                 device=None, sub_bits=None, world=1):
         self.P, self.op, self.splits, self.thresholds, self.group = P, op, splits, thresholds, group
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         self.n = n_rows
+        self.sub_bits = choose_sub_bits(n_rows * world, P) if sub_bits is None else sub_bits
         self.h_keys = torch.empty(n_rows, dtype=key_dtype).pin_memory()
         self.h_vals = torch.empty(n_rows, dtype=val_dtype).pin_memory()
         self.d_keys = torch.empty(n_rows, dtype=key_dtype, device=self.device)
@@ -149,7 +173,7 @@ class HostShuffle(object):
             self.d_vals[a:b].copy_(self.h_vals[a:b], non_blocking=True)
             kc.append(self.d_keys[a:b])
             vc.append(self.d_vals[a:b])
-        mo = map_side(kc, vc, self.P, self.thresholds)
+        mo = map_side(kc, vc, self.P, self.thresholds, False, self.sub_bits)
         rx = exchange(mo, self.group)
         ok, ov, po, cnt = reduce_side(rx, self.op, self.P, self.thresholds)
         po_h, cnt_h = po.cpu().tolist(), cnt.cpu().tolist()      # the one host sync: result sizes
@@ -169,10 +193,14 @@ class HostShuffle(object):
         return res
 
 
-def reduce_by_key(key_chunks, val_chunks, P, op="sum", thresholds=None, group=None):
+def reduce_by_key(key_chunks, val_chunks, P, op="sum", thresholds=None, group=None, sub_bits=None):
     """Whole hot path for this rank's map splits.  Returns a list of
     (partition id, keys, vals) for the partitions this rank owns (device tensors)."""
-    mo = map_side(key_chunks, val_chunks, P, thresholds)
+    if sub_bits is None:
+        import torch.distributed as dist
+        G = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        sub_bits = choose_sub_bits(sum(int(k.numel()) for k in key_chunks) * G, P)
+    mo = map_side(key_chunks, val_chunks, P, thresholds, False, sub_bits)
     rx = exchange(mo, group)
     ok, ov, po, cnt = reduce_side(rx, op, P, thresholds)
     po_h, cnt_h = po.cpu().tolist(), cnt.cpu().tolist()

@@ -73,56 +73,67 @@ int dpk_partition_ids(const int64_t *hash, int64_t n, int32_t P, const int64_t *
                       int32_t nthr, int32_t *out_pid, dpk_stream_t stream);
 
 /* ---- a4: map side, ShuffleMapTask._run hash-partition (dpark/task.py:209-226)
- * Stable multisplit of one input chunk into P buckets: rows keep their input
+ * Stable multisplit of one input chunk into buckets: rows keep their input
  * order inside each bucket (this is what makes ordered groupByKey exact).
- * Keys may be a key column (key_kind = DPK_K_*) or, with key_kind = -1,
- * precomputed int64 hashes `hash` for variable-length keys (then `keys` is the
- * int64 payload that travels, e.g. the row index).
  *
- *   ws = dpk_partition_workspace_bytes(n, P)
- *   dpk_partition_count  : out_counts[P] (int64) = rows per bucket of this chunk;
+ * Buckets: F = P << sub_bits.  Bucket id = partition * 2^sub_bits + sub, where
+ * partition = getPartition(key) exactly as the reference and sub is taken from
+ * other bits of the key's hash.  sub_bits = 0 gives the reference's P buckets;
+ * sub_bits > 0 only refines the layout INSIDE each partition (partition p is the
+ * concatenation of its 2^sub_bits sub-buckets) so the reduce-side tables stay
+ * L2-resident.  F <= DPK_MAX_PARTITIONS.
+ *
+ * key_kind = DPK_K_* hashes the key column with portable_hash; key_kind = -1
+ * ("prehashed") takes the int64 keys AS the hash (variable-length keys: hash
+ * them with dpk_hash_bytes first and carry the row id as the value).
+ *
+ *   ws = dpk_partition_workspace_bytes(n, F)
+ *   dpk_partition_count  : out_counts[F] (int64) = rows per bucket of this chunk;
  *                          leaves per-CTA counts in ws for the scatter.
- *   dpk_partition_scatter: writes row i to out_keys/out_vals[bucket_base[p] + rank],
- *                          bucket_base[P] int64 on device (caller-computed from the
- *                          counts of all chunks, so several chunks can interleave
- *                          into one bucket-major buffer = the alltoallv send buffer).
+ *   dpk_partition_scatter: writes row i to out_keys/out_vals[bucket_base[b] + rank],
+ *                          bucket_base[F] int64 on device (caller-computed from the
+ *                          counts of all chunks, so several chunks interleave into
+ *                          one bucket-major buffer = the alltoallv send buffer).
  *                          Must follow dpk_partition_count with the same
- *                          (keys, n, P, thresholds, ws).
+ *                          (keys, n, P, thresholds, sub_bits, ws).
  *   dpk_partition        : count + exclusive scan + scatter for a single chunk;
- *                          out_offsets[P+1] int64.
- * key_bytes/val_bytes in {4, 8}.  vals may be NULL (keys only).  P <= DPK_MAX_PARTITIONS.
+ *                          out_offsets[F+1] int64.
+ * key width follows key_kind; val_bytes in {0, 4, 8} (0/NULL = keys only).
  */
 #define DPK_MAX_PARTITIONS 4096
-int64_t dpk_partition_workspace_bytes(int64_t n, int32_t P);
+int64_t dpk_partition_workspace_bytes(int64_t n, int32_t nbuckets);
 int dpk_partition_count(const void *keys, int key_kind, int64_t n, int32_t P,
-                        const int64_t *thresholds, int32_t nthr, int64_t *out_counts, void *ws,
-                        int64_t ws_bytes, dpk_stream_t stream);
+                        const int64_t *thresholds, int32_t nthr, int32_t sub_bits,
+                        int64_t *out_counts, void *ws, int64_t ws_bytes, dpk_stream_t stream);
 int dpk_partition_scatter(const void *keys, int key_kind, const void *vals, int32_t val_bytes,
                           int64_t n, int32_t P, const int64_t *thresholds, int32_t nthr,
-                          const int64_t *bucket_base, void *out_keys, void *out_vals, void *ws,
-                          int64_t ws_bytes, dpk_stream_t stream);
+                          int32_t sub_bits, const int64_t *bucket_base, void *out_keys,
+                          void *out_vals, void *ws, int64_t ws_bytes, dpk_stream_t stream);
 int dpk_partition(const void *keys, int key_kind, const void *vals, int32_t val_bytes, int64_t n,
-                  int32_t P, const int64_t *thresholds, int32_t nthr, void *out_keys,
-                  void *out_vals, int64_t *out_offsets, void *ws, int64_t ws_bytes,
-                  dpk_stream_t stream);
+                  int32_t P, const int64_t *thresholds, int32_t nthr, int32_t sub_bits,
+                  void *out_keys, void *out_vals, int64_t *out_offsets, void *ws,
+                  int64_t ws_bytes, dpk_stream_t stream);
 
 /* ---- a9: reduce side, DiskHashMerger._merge (dpark/shuffle.py:600-608) ----
- * combined[k] = op(combined[k], v) over the n rows fetched for the reduce
- * partitions this GPU owns.  Rows of several partitions may be passed at once
- * (bucket-major, part_offsets[nparts+1] on device): distinct keys of partition
- * p are written to out_keys/out_vals[part_offsets[p] ...] and their count to
- * out_counts[p] (int64).  Order inside a partition is unspecified (the
- * reference iterates a dict).  Accumulation type: I64/I32 values -> int64
- * (exact while |sum| < 2^63, like the reference's big ints); F64/F32 values ->
- * float64 (the reference adds Python floats); out_vals is 8 bytes per row.
- * part_pid_P / thresholds describe the partitioner again (needed to route each
- * distinct key to its partition's output range).
+ * combined[k] = op(combined[k], v) over the n rows fetched for the nparts reduce
+ * partitions [part_first, part_first + nparts) this GPU owns (any row order;
+ * bucket-major order keeps the tables L2-resident).  bucket_rows[nparts <<
+ * sub_bits] (device int64) = rows per local fine bucket, summed over sources:
+ * it sizes one table region per bucket.  Outputs: out_offsets[nparts+1] = start
+ * of each partition's output range (= row offsets of the partitions),
+ * out_counts[nparts] = distinct keys per partition; partition j's result is
+ * out_keys/out_vals[out_offsets[j] .. out_offsets[j] + out_counts[j]).  Order
+ * inside a partition is unspecified (the reference iterates a dict).
+ * Accumulation: I64/I32 values -> int64 (exact while |sum| < 2^63, like the
+ * reference's big ints); F64/F32 values -> float64 (the reference adds Python
+ * floats); out_vals is 8 bytes per row.  out_keys/out_vals hold n entries.
  */
-int64_t dpk_combine_workspace_bytes(int64_t n);
+int64_t dpk_combine_workspace_bytes(int64_t n, int32_t nbuckets);
 int dpk_combine(const void *keys, int key_kind, const void *vals, int val_kind, int64_t n, int op,
-                int32_t P, const int64_t *thresholds, int32_t nthr, int32_t part_first,
-                int32_t nparts, const int64_t *part_offsets, void *out_keys, void *out_vals,
-                int64_t *out_counts, void *ws, int64_t ws_bytes, dpk_stream_t stream);
+                int32_t P, const int64_t *thresholds, int32_t nthr, int32_t sub_bits,
+                int32_t part_first, int32_t nparts, const int64_t *bucket_rows, void *out_keys,
+                void *out_vals, int64_t *out_offsets, int64_t *out_counts, void *ws,
+                int64_t ws_bytes, dpk_stream_t stream);
 
 /* ---- measurement hooks (SURVEY.md §5 tracing: TaskStats -> CUDA events) -----
  * dpk_launch_count: kernels launched by this library since load.

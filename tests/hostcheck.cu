@@ -13,9 +13,16 @@ void hc_hash_bytes(const uint8_t *d, const int64_t *off, int64_t n, int mode, in
 }
 int hc_partition(const int64_t *h, int64_t n, int32_t P, const int64_t *thr, int32_t nthr, int32_t *o) {
     dpk::PartFn f;
-    int rc = dpk::make_partfn(P, thr, nthr, &f);
+    int rc = dpk::make_partfn(P, thr, nthr, 0, &f);
     if (rc) return rc;
     for (int64_t i = 0; i < n; i++) o[i] = f(h[i]);
+    return 0;
+}
+int hc_bucket(const int64_t *h, int64_t n, int32_t P, int32_t sub_bits, int32_t *o) {
+    dpk::PartFn f;
+    int rc = dpk::make_partfn(P, nullptr, 0, sub_bits, &f);
+    if (rc) return rc;
+    for (int64_t i = 0; i < n; i++) o[i] = f.bucket(h[i]);
     return 0;
 }
 }

@@ -1,0 +1,97 @@
+"""Sub-bucketed layout (sub_bits > 0): an internal refinement of each reduce
+partition.  What the reference defines must be unchanged: which keys a partition
+owns, and the (map split, position) order of rows -- now per fine bucket.  -m gpu."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def nv():
+    from dpark_b200 import _native
+    return _native
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize("P,sb", [(1, 4), (3, 2), (8, 5), (8, 7), (64, 4), (5, 9)])
+def test_partition_with_sub_buckets_refines_reference_partitions(P, sb):
+    rng = np.random.default_rng(P * 100 + sb)
+    n = 400000
+    k = rng.integers(-2 ** 63, 2 ** 63 - 1, n, dtype=np.int64)
+    k[: n // 2] = rng.integers(0, 20000, n // 2)
+    v = np.arange(n, dtype=np.int64)
+    ok, ov, off = nv().partition(dev(k), dev(v), P, sub_bits=sb)
+    ok, ov, off = ok.cpu().numpy(), ov.cpu().numpy(), off.cpu().numpy()
+    S = 1 << sb
+    assert len(off) == P * S + 1 and off[0] == 0 and off[-1] == n
+    pid = orc.partition_vec(orc.hash_vec(k), P)
+    want_off = np.zeros(P + 1, dtype=np.int64)
+    want_off[1:] = np.cumsum(np.bincount(pid, minlength=P))
+    assert np.array_equal(off[::S], want_off)                # partition boundaries == the reference's
+    bucket_of_row = np.searchsorted(off, np.arange(n), side="right") - 1
+    assert np.array_equal(bucket_of_row >> sb, orc.partition_vec(orc.hash_vec(ok), P))
+    assert np.array_equal(k[ov], ok)                         # (key, value) pairs intact
+    # stable inside every fine bucket: the row-index payload ascends
+    brk = np.zeros(n, dtype=bool)
+    brk[off[1:-1][off[1:-1] < n]] = True
+    asc = (ov[1:] > ov[:-1]) | brk[1:]
+    assert asc.all()
+    # equal keys share one fine bucket
+    order = np.argsort(ok, kind="stable")
+    same = ok[order][1:] == ok[order][:-1]
+    assert (bucket_of_row[order][1:][same] == bucket_of_row[order][:-1][same]).all()
+    # sub-buckets of a big partition are all used and roughly balanced
+    if n / (P * S) > 200:
+        cnt = np.diff(off)
+        assert cnt.min() > 0
+
+
+@pytest.mark.parametrize("sb", [0, 3, 6])
+@pytest.mark.parametrize("op", ["sum", "max"])
+def test_reduce_by_key_same_result_for_any_sub_bits(sb, op):
+    from dpark_b200 import shuffle
+    rng = np.random.default_rng(31 + sb)
+    n, P, M = 600000, 8, 3
+    k = rng.integers(-40000, 40000, n, dtype=np.int64)
+    k[:4] = [-1, -2, -2 ** 63, 2 ** 63 - 1]
+    v = rng.integers(-2 ** 20, 2 ** 20, n, dtype=np.int64)
+    ks, vs = np.array_split(k, M), np.array_split(v, M)
+    res = shuffle.reduce_by_key([dev(x) for x in ks], [dev(x) for x in vs], P, op, sub_bits=sb)
+    want = orc.reduce_by_key(ks, vs, P, op)
+    for p, gk, gv in res:
+        gk, gv = gk.cpu().numpy(), gv.cpu().numpy()
+        o1, o2 = np.argsort(gk), np.argsort(want[p][0])
+        assert np.array_equal(gk[o1], want[p][0][o2])
+        assert np.array_equal(gv[o1], want[p][1][o2])
+
+
+def test_reduce_with_thresholds_and_sub_buckets():
+    from dpark_b200 import shuffle
+    rng = np.random.default_rng(41)
+    n, P = 300000, 4
+    k = rng.integers(-1000, 1000, n, dtype=np.int64)
+    v = np.ones(n, dtype=np.int64)
+    thr = [-500, 0, 500]
+    res = shuffle.reduce_by_key([dev(k)], [dev(v)], P, "sum", thresholds=thr, sub_bits=4)
+    want = orc.reduce_by_key([k], [v], P, "sum", thr)
+    for p, gk, gv in res:
+        gk, gv = gk.cpu().numpy(), gv.cpu().numpy()
+        o1, o2 = np.argsort(gk), np.argsort(want[p][0])
+        assert np.array_equal(gk[o1], want[p][0][o2])
+        assert np.array_equal(gv[o1], want[p][1][o2])
+
+
+def test_choose_sub_bits_bounds():
+    from dpark_b200 import shuffle
+    assert shuffle.choose_sub_bits(1000, 8) == 0
+    assert shuffle.choose_sub_bits(10 ** 8, 8) == 5
+    for n in (10 ** 6, 10 ** 8, 10 ** 9, 4 * 10 ** 9):
+        for P in (1, 4, 8, 64, 1000, 4096):
+            sb = shuffle.choose_sub_bits(n, P)
+            assert (P << sb) <= max(P, 1024)
