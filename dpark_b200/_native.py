@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libdpark_b200.so")
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_WORKSPACE, ERR_CUDA = 0, -1, -2, -3, -4
 K_HASHED = -1
-K_I64, K_I32, K_F64, K_U64, K_F32 = 0, 1, 2, 3, 4
+K_I64, K_I32, K_F64, K_U64, K_F32, K_ROWID = 0, 1, 2, 3, 4, 5
 V_I64, V_F64, V_I32, V_F32 = 0, 1, 2, 3
 OPS = {"sum": 0, "min": 1, "max": 2, "prod": 3, "and": 4, "or": 5, "xor": 6}
 BYTES_SIGNED, STR_UTF8 = 0, 1
@@ -31,6 +31,7 @@ EXPORTS = [
     "dpk_partition_ids", "dpk_partition_workspace_bytes", "dpk_partition_count",
     "dpk_partition_scatter", "dpk_partition", "dpk_combine_workspace_bytes", "dpk_combine",
     "dpk_launch_count", "dpk_prof_enable", "dpk_prof_count", "dpk_prof_get",
+    "dpk_dict_encode_workspace_bytes", "dpk_dict_encode",
 ]
 
 _lib = None
@@ -64,8 +65,11 @@ def lib():
         L.dpk_partition_scatter.argtypes = [vp, ci, vp, i32, i64, i32, vp, i32, i32, vp, vp, vp, vp, i64, vp]
         L.dpk_partition.argtypes = [vp, ci, vp, i32, i64, i32, vp, i32, i32, vp, vp, vp, vp, i64, vp]
         L.dpk_combine_workspace_bytes.argtypes = [i64, i32]
-        L.dpk_combine.argtypes = [vp, ci, vp, ci, i64, ci, i32, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp,
+        L.dpk_combine.argtypes = [vp, ci, vp, vp, ci, i64, ci, i32, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp,
                                   vp, i64, vp]
+        L.dpk_dict_encode_workspace_bytes.restype = i64
+        L.dpk_dict_encode_workspace_bytes.argtypes = [i64]
+        L.dpk_dict_encode.argtypes = [vp, vp, vp, i64, vp, vp, i64, vp]
         L.dpk_prof_enable.argtypes = [ci]
         L.dpk_prof_get.argtypes = [ci, C.c_char_p, C.POINTER(C.c_float)]
         if L.dpk_abi_version() != 1:
@@ -217,13 +221,16 @@ def acc_dtype(vals_dtype):
     return torch.float64 if vals_dtype in (torch.float32, torch.float64) else torch.int64
 
 
-def combine(keys, vals, op, P, bucket_rows, part_first=0, nparts=None, thresholds=None, sub_bits=0):
+def combine(keys, vals, op, P, bucket_rows, part_first=0, nparts=None, thresholds=None, sub_bits=0,
+            row_hash=None):
     """Reduce-side merge (DiskHashMerger._merge, dpark/shuffle.py:600-608) of the
     rows of partitions [part_first, part_first+nparts).  bucket_rows: device int64
     [nparts << sub_bits] rows per local fine bucket.  Returns (out_keys, out_vals,
     out_offsets[nparts+1], out_counts[nparts]); partition j's distinct keys are
-    out[out_offsets[j] : out_offsets[j] + out_counts[j]]."""
-    _need_cuda(keys, vals, bucket_rows)
+    out[out_offsets[j] : out_offsets[j] + out_counts[j]].  With row_hash (the
+    per-row portable_hash column) the keys are representative row ids from
+    dict_encode (DPK_K_ROWID)."""
+    _need_cuda(keys, vals, bucket_rows, row_hash)
     if nparts is None:
         nparts = P
     n = keys.numel()
@@ -237,11 +244,25 @@ def combine(keys, vals, op, P, bucket_rows, part_first=0, nparts=None, threshold
     out_vals = torch.empty(n, dtype=acc_dtype(vals.dtype), device=keys.device)
     out_offsets = torch.empty(nparts + 1, dtype=torch.int64, device=keys.device)
     out_counts = torch.empty(nparts, dtype=torch.int64, device=keys.device)
-    _check(lib().dpk_combine(_ptr(keys), key_kind(keys), _ptr(vals), val_kind(vals), n, OPS[op], P,
+    kk = key_kind(keys) if row_hash is None else K_ROWID
+    _check(lib().dpk_combine(_ptr(keys), kk, _ptr(row_hash), _ptr(vals), val_kind(vals), n, OPS[op], P,
                              _ptr(thr), nthr, sub_bits, part_first, nparts, _ptr(bucket_rows), _ptr(out_keys),
                              _ptr(out_vals), _ptr(out_offsets), _ptr(out_counts), _ptr(ws), ws_bytes,
                              _stream()))
     return out_keys, out_vals, out_offsets, out_counts
+
+
+# ---- variable-length keys ----------------------------------------------------------
+def dict_encode(data, offsets, hashes):
+    """Representative row id per row: rep[i] == rep[j] <=> the byte strings are equal."""
+    _need_cuda(data, offsets, hashes)
+    n = offsets.numel() - 1
+    ws_bytes = lib().dpk_dict_encode_workspace_bytes(n)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=offsets.device)
+    rep = torch.empty(n, dtype=torch.int64, device=offsets.device)
+    _check(lib().dpk_dict_encode(_ptr(data), _ptr(offsets), _ptr(hashes), n, _ptr(rep), _ptr(ws), ws_bytes,
+                                 _stream()))
+    return rep
 
 
 # ---- measurement hooks ---------------------------------------------------------

@@ -50,6 +50,15 @@ template <> __device__ __forceinline__ uint64_t key_from_bits<uint64_t>(int64_t 
 template <> __device__ __forceinline__ double key_from_bits<double>(int64_t b) { return __longlong_as_double(b); }
 template <> __device__ __forceinline__ float key_from_bits<float>(int64_t b) { return __int_as_float((int)b); }
 
+// Row-id keys (DPK_K_ROWID): the key column holds the index of a representative
+// row of a variable-length key (dpk_dict_encode); its portable_hash is looked up
+// in `aux` (the per-row hash column) instead of being computed from the id.
+struct RowId { int64_t v; };
+template <> __device__ __forceinline__ int64_t key_bits<RowId>(RowId k) { return k.v; }
+template <> __device__ __forceinline__ RowId key_from_bits<RowId>(int64_t b) { RowId r; r.v = b; return r; }
+template <typename KeyT> __device__ __forceinline__ int64_t hash_of(KeyT k, const int64_t *) { return KeyHash<KeyT>::of(k); }
+template <> __device__ __forceinline__ int64_t hash_of<RowId>(RowId k, const int64_t *aux) { return __ldg(&aux[k.v]); }
+
 // ---- accumulator ops (op is kernel-uniform, so the switch costs nothing) ------
 template <typename AccT> struct Acc;
 
@@ -162,8 +171,8 @@ k_tbl_init(Slot *__restrict__ table, const int64_t *__restrict__ tbl_total, int6
 
 template <typename KeyT, typename ValT, typename AccT>
 __global__ void __launch_bounds__(CB_THREADS)
-k_tbl_insert(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, int64_t n, int op, PartFn f,
-             int32_t bucket_first, int32_t F, const int64_t *__restrict__ tbl_off, Slot *__restrict__ table,
+k_tbl_insert(const KeyT *__restrict__ keys, const int64_t *__restrict__ aux, const ValT *__restrict__ vals,
+             int64_t n, int op, PartFn f, int32_t bucket_first, int32_t F, const int64_t *__restrict__ tbl_off, Slot *__restrict__ table,
              Slot *__restrict__ side, int32_t *__restrict__ side_used) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -176,7 +185,7 @@ k_tbl_insert(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, int64
             s = side;
             *side_used = 1;
         } else {
-            int b = f.bucket(KeyHash<KeyT>::of(key)) - bucket_first;
+            int b = f.bucket(hash_of<KeyT>(key, aux)) - bucket_first;
             b = min(max(b, 0), F - 1);  // rows of foreign partitions cannot occur; stay in bounds regardless
             const int64_t base = __ldg(&tbl_off[b]);
             const uint32_t size = (uint32_t)(__ldg(&tbl_off[b + 1]) - base);
@@ -202,7 +211,8 @@ k_tbl_insert(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, int64
 template <typename KeyT>
 __global__ void __launch_bounds__(CB_THREADS)
 k_tbl_compact(const Slot *__restrict__ table, const int64_t *__restrict__ tbl_total, int64_t max_slots,
-              const int32_t *__restrict__ side_used, PartFn f, int32_t part_first, int32_t nparts,
+              const int32_t *__restrict__ side_used, const int64_t *__restrict__ aux, PartFn f,
+              int32_t part_first, int32_t nparts,
               const int64_t *__restrict__ part_offsets, KeyT *__restrict__ out_keys,
               int64_t *__restrict__ out_vals, unsigned long long *__restrict__ out_counts) {
     extern __shared__ __align__(16) int32_t s_mem[];  // [nparts] counts, [nparts] 64-bit bases after
@@ -228,7 +238,7 @@ k_tbl_compact(const Slot *__restrict__ table, const int64_t *__restrict__ tbl_to
                 acc[j] = (int64_t)(((uint64_t)(uint32_t)raw.w << 32) | (uint32_t)raw.z);
                 bool occ = (i < nslots) ? (kb[j] != kEmpty) : (*side_used != 0);
                 if (i == nslots) kb[j] = kEmpty;
-                if (occ) lp[j] = f(KeyHash<KeyT>::of(key_from_bits<KeyT>(kb[j]))) - part_first;
+                if (occ) lp[j] = f(hash_of<KeyT>(key_from_bits<KeyT>(kb[j]), aux)) - part_first;
             }
         }
 #pragma unroll
@@ -271,6 +281,7 @@ static inline int grid_cap(int64_t items, int per_cta, int waves) {
 
 struct Ctx {
     const void *keys, *vals;
+    const int64_t *aux;
     int64_t n;
     int op;
     PartFn f;
@@ -289,7 +300,7 @@ static int dispatch_op(const Ctx &c) {
         c.table, c.tbl_off + c.F, c.max_slots, Acc<AccT>::identity(c.op)));
     if (c.n > 0) {
         DPK_LAUNCH("tbl_insert", c.st, k_tbl_insert<KeyT, ValT, AccT><<<grid_cap(c.n, CB_THREADS, 16), CB_THREADS, 0, c.st>>>(
-            (const KeyT *)c.keys, (const ValT *)c.vals, c.n, c.op, c.f, c.part_first << c.f.sub_bits, c.F,
+            (const KeyT *)c.keys, c.aux, (const ValT *)c.vals, c.n, c.op, c.f, c.part_first << c.f.sub_bits, c.F,
             c.tbl_off, c.table, c.side, c.side_used));
     }
     return DPK_OK;
@@ -323,7 +334,7 @@ static int run_combine(Ctx &c, int val_kind, const int64_t *bucket_rows, void *o
     if (rc) return rc;
     size_t sh = (size_t)((c.nparts + 1) & ~1) * 4 + (size_t)c.nparts * 8;
     DPK_LAUNCH("tbl_compact", c.st, k_tbl_compact<KeyT><<<grid_cap(c.max_slots, CB_THREADS * 4, 8), CB_THREADS, sh, c.st>>>(
-        c.table, tbl_off + c.F, c.max_slots, c.side_used, c.f, c.part_first, c.nparts, out_offsets,
+        c.table, tbl_off + c.F, c.max_slots, c.side_used, c.aux, c.f, c.part_first, c.nparts, out_offsets,
         (KeyT *)out_keys, (int64_t *)out_vals, (unsigned long long *)out_counts));
     return DPK_OK;
 }
@@ -340,7 +351,8 @@ int64_t dpk_combine_workspace_bytes(int64_t n, int32_t nbuckets) {
     return (max_slots_for(n, nbuckets) + 2) * (int64_t)sizeof(Slot) + ((int64_t)nbuckets + 2) * 8 + 64;
 }
 
-int dpk_combine(const void *keys, int key_kind, const void *vals, int val_kind, int64_t n, int op, int32_t P,
+int dpk_combine(const void *keys, int key_kind, const int64_t *key_aux, const void *vals, int val_kind, int64_t n,
+                int op, int32_t P,
                 const int64_t *thresholds, int32_t nthr, int32_t sub_bits, int32_t part_first, int32_t nparts,
                 const int64_t *bucket_rows, void *out_keys, void *out_vals, int64_t *out_offsets,
                 int64_t *out_counts, void *ws, int64_t ws_bytes, dpk_stream_t stream) {
@@ -353,9 +365,12 @@ int dpk_combine(const void *keys, int key_kind, const void *vals, int val_kind, 
     int rc = make_partfn(P, thresholds, nthr, sub_bits, &c.f);
     if (rc) return rc;
     c.F = nparts << sub_bits;
+    if (c.F > DPK_MAX_PARTITIONS)
+        return fail(DPK_ERR_UNSUPPORTED, "%d local buckets exceed %d", c.F, DPK_MAX_PARTITIONS);
     if (ws_bytes < dpk_combine_workspace_bytes(n, c.F))
         return fail(DPK_ERR_WORKSPACE, "workspace needs %lld B, got %lld", (long long)dpk_combine_workspace_bytes(n, c.F), (long long)ws_bytes);
-    c.keys = keys; c.vals = vals; c.n = n; c.op = op;
+    c.keys = keys; c.vals = vals; c.n = n; c.op = op; c.aux = key_aux;
+    if (key_kind == DPK_K_ROWID && n > 0 && !key_aux) return fail(DPK_ERR_INVALID, "DPK_K_ROWID needs key_aux (the per-row hash column)");
     c.part_first = part_first; c.nparts = nparts;
     c.max_slots = max_slots_for(n, c.F);
     c.st = (cudaStream_t)stream;
@@ -365,6 +380,7 @@ int dpk_combine(const void *keys, int key_kind, const void *vals, int val_kind, 
     case DPK_K_F64: return run_combine<double>(c, val_kind, bucket_rows, out_keys, out_vals, out_offsets, out_counts, ws);
     case DPK_K_U64: return run_combine<uint64_t>(c, val_kind, bucket_rows, out_keys, out_vals, out_offsets, out_counts, ws);
     case DPK_K_F32: return run_combine<float>(c, val_kind, bucket_rows, out_keys, out_vals, out_offsets, out_counts, ws);
+    case DPK_K_ROWID: return run_combine<RowId>(c, val_kind, bucket_rows, out_keys, out_vals, out_offsets, out_counts, ws);
     }
     return fail(DPK_ERR_UNSUPPORTED, "key kind %d is unhashable by portable_hash", key_kind);
 }

@@ -55,7 +55,9 @@ ProfScope::~ProfScope() {
 
 int make_partfn(int32_t P, const int64_t *thresholds, int32_t nthr, int32_t sub_bits, PartFn *out) {
     if (P < 1) return fail(DPK_ERR_INVALID, "P must be >= 1, got %d", P);
-    if (sub_bits < 0 || sub_bits > 12 || ((int64_t)P << sub_bits) > DPK_MAX_PARTITIONS)
+    // the bucket limit belongs to the multisplit kernels (their shared-memory
+    // histograms); plain getPartition (sub_bits == 0) works for any P
+    if (sub_bits < 0 || sub_bits > 12 || (sub_bits > 0 && ((int64_t)P << sub_bits) > DPK_MAX_PARTITIONS))
         return fail(DPK_ERR_UNSUPPORTED, "P=%d with sub_bits=%d exceeds %d buckets", P, sub_bits, DPK_MAX_PARTITIONS);
     PartFn f;
     f.P = P; f.magic = 0; f.shift = 0; f.nthr = 0; f.thresholds = nullptr; f.sub_bits = sub_bits;

@@ -1,0 +1,467 @@
+"""RDD operator surface for the shuffle hot path -- the reference's names,
+signatures and result semantics (dpark/rdd.py) over the B200 shuffle engine.
+
+Only what a user of reduceByKey / groupByKey / combineByKey touches is here
+(SURVEY.md §8b seam 1): sources (ParallelCollection, TextFileRDD, ColumnarRDD),
+narrow Python-side operators that feed or consume a shuffle (map, flatMap,
+filter, mapValue, glom, union ...), the shuffle itself (ShuffledRDD) and the
+actions (collect, collectAsMap, count, saveAsTextFile ...).  The narrow
+operators are plain Python generators, as in the reference; every shuffle runs
+on the GPU through dpark_b200.shuffle -- there is no CPU shuffle.
+"""
+import itertools
+import os
+import shutil
+
+import numpy as np
+
+from . import columnar, conf, trace
+from .dependency import Aggregator, GroupByAggregator, HashPartitioner, Partitioner, ShuffleDependency
+from .errors import DparkUserFatalError  # noqa: F401
+
+
+class Split(object):
+    def __init__(self, index):
+        self.index = index
+
+
+class RDD(object):
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self.id = ctx.newRddId()
+        self._splits = []
+        self._dependencies = []
+        self.partitioner = None
+        self.mem = None
+        self.rddconf = None
+        self._cache = None
+        self.should_cache = False
+
+    # ------------------------------------------------------------------ plumbing
+    @property
+    def splits(self):
+        return self._splits
+
+    def __len__(self):
+        return len(self.splits)
+
+    def __repr__(self):
+        return "<%s>" % self.__class__.__name__
+
+    def compute(self, split):
+        raise NotImplementedError
+
+    def iterator(self, split):
+        if self.should_cache:
+            if self._cache is None:
+                self._cache = {}
+            if split.index not in self._cache:
+                self._cache[split.index] = list(self.compute(split))
+            return iter(self._cache[split.index])
+        return self.compute(split)
+
+    def cache(self):
+        self.should_cache = True
+        return self
+
+    def set_rddconf(self, rddconf):
+        self.rddconf = conf.default_rddconf.dup() if rddconf is None else rddconf
+
+    # -------------------------------------------------------------- narrow ops
+    def map(self, f):
+        return MappedRDD(self, f)
+
+    def flatMap(self, f):
+        return FlatMappedRDD(self, f)
+
+    def filter(self, f):
+        return FilteredRDD(self, f)
+
+    def glom(self):
+        return GlommedRDD(self)
+
+    def mapPartitions(self, f):
+        return MapPartitionsRDD(self, f)
+
+    mapPartition = mapPartitions
+
+    def mapPartitionWithIndex(self, f):
+        return MapPartitionsRDD(self, f, with_index=True)
+
+    def mapValue(self, f):
+        return MappedValuesRDD(self, f)
+
+    mapValues = mapValue
+
+    def flatMapValue(self, f):
+        return FlatMappedValuesRDD(self, f)
+
+    def keyBy(self, f):
+        return self.map(lambda x: (f(x), x))
+
+    def union(self, *others):
+        return UnionRDD(self.ctx, [self] + list(others))
+
+    def __add__(self, other):
+        return self.union(other)
+
+    # ----------------------------------------------------------------- actions
+    def collect(self):
+        """Concatenation of the partitions in index order (dpark/schedule.py:669-672)."""
+        return list(itertools.chain.from_iterable(self.ctx.runJob(self, list)))
+
+    def __iter__(self):
+        return iter(self.collect())
+
+    def collectAsMap(self):
+        d = {}
+        for part in self.ctx.runJob(self, list):
+            d.update(part)
+        return d
+
+    def count(self):
+        return sum(self.ctx.runJob(self, lambda it: sum(1 for _ in it)))
+
+    def reduce(self, f):
+        def part(it):
+            it = iter(it)
+            try:
+                acc = next(it)
+            except StopIteration:
+                return []
+            for x in it:
+                acc = f(acc, x)
+            return [acc]
+        vals = list(itertools.chain.from_iterable(self.ctx.runJob(self, part)))
+        if not vals:
+            return None
+        acc = vals[0]
+        for x in vals[1:]:
+            acc = f(acc, x)
+        return acc
+
+    def foreach(self, f):
+        def run(it):
+            for x in it:
+                f(x)
+        list(self.ctx.runJob(self, run))
+
+    def take(self, n):
+        out = []
+        for part in self.ctx.runJob(self, list):
+            out.extend(part[:n - len(out)])
+            if len(out) >= n:
+                break
+        return out
+
+    def first(self):
+        r = self.take(1)
+        return r[0] if r else None
+
+    def saveAsTextFile(self, path, ext="", overwrite=True, compress=False):
+        return OutputTextFileRDD(self, path, ext, overwrite, compress).collect()
+
+    def lookup(self, key):
+        """dpark/rdd.py lookup: with a partitioner only the key's partition is
+        scanned; a (k, v) RDD answers the value, None when absent."""
+        if self.partitioner is not None:
+            idx = self.partitioner.getPartition(key)
+            for k, v in self.iterator(self.splits[idx]):
+                if k == key:
+                    return v
+            return None
+        for k, v in self.collect():
+            if k == key:
+                return v
+        return None
+
+    # ------------------------------------------------------------- the shuffle
+    def combineByKey(self, aggregator, splits=None, taskMemory=None, fixSkew=-1, rddconf=None):
+        """dpark/rdd.py:511-541.  `splits` is a partition count or a Partitioner.
+        fixSkew (t-digest thresholds) is not implemented: the
+        flag is accepted and ignored, explicit HashPartitioner(thresholds=...) works."""
+        if splits is None:
+            splits = min(self.ctx.defaultMinSplits, len(self))
+        if type(splits) is int:
+            splits = HashPartitioner(splits)
+        return ShuffledRDD(self, aggregator, splits, taskMemory, rddconf=rddconf)
+
+    def reduceByKey(self, func, numSplits=None, taskMemory=None, fixSkew=-1, rddconf=None):
+        """dpark/rdd.py:543-545."""
+        aggregator = Aggregator(lambda x: x, func, func)
+        return self.combineByKey(aggregator, numSplits, taskMemory, fixSkew=fixSkew, rddconf=rddconf)
+
+    def groupByKey(self, numSplits=None, taskMemory=None, fixSkew=-1, rddconf=None):
+        """dpark/rdd.py:547-550."""
+        return self.combineByKey(GroupByAggregator(), numSplits, taskMemory, fixSkew=fixSkew, rddconf=rddconf)
+
+    def partitionByKey(self, numSplits=None, taskMemory=None, rddconf=None):
+        return self.groupByKey(numSplits, taskMemory, rddconf=rddconf).flatMapValue(lambda x: x)
+
+    def reduceByKeyToDriver(self, func):
+        """dpark/rdd.py:503-509 (driver-side merge of per-row dicts); here simply
+        the shuffle followed by collectAsMap."""
+        return self.reduceByKey(func).collectAsMap()
+
+
+class DerivedRDD(RDD):
+    def __init__(self, prev):
+        RDD.__init__(self, prev.ctx)
+        self.prev = prev
+        self._splits = prev.splits
+
+    @property
+    def splits(self):
+        return self.prev.splits
+
+
+class MappedRDD(DerivedRDD):
+    def __init__(self, prev, f):
+        DerivedRDD.__init__(self, prev)
+        self.func = f
+
+    def compute(self, split):
+        return map(self.func, self.prev.iterator(split))
+
+
+class FlatMappedRDD(MappedRDD):
+    def compute(self, split):
+        return itertools.chain.from_iterable(map(self.func, self.prev.iterator(split)))
+
+
+class FilteredRDD(MappedRDD):
+    def compute(self, split):
+        return filter(self.func, self.prev.iterator(split))
+
+
+class GlommedRDD(DerivedRDD):
+    def compute(self, split):
+        yield list(self.prev.iterator(split))
+
+
+class MapPartitionsRDD(DerivedRDD):
+    def __init__(self, prev, f, with_index=False):
+        DerivedRDD.__init__(self, prev)
+        self.func, self.with_index = f, with_index
+
+    def compute(self, split):
+        it = self.prev.iterator(split)
+        return self.func(split.index, it) if self.with_index else self.func(it)
+
+
+class MappedValuesRDD(MappedRDD):
+    """Keeps the parent's partitioner: keys are untouched (dpark/rdd.py MappedValuesRDD)."""
+
+    def __init__(self, prev, f):
+        MappedRDD.__init__(self, prev, f)
+        self.partitioner = prev.partitioner
+
+    def compute(self, split):
+        f = self.func
+        return ((k, f(v)) for k, v in self.prev.iterator(split))
+
+
+class FlatMappedValuesRDD(MappedValuesRDD):
+    def compute(self, split):
+        f = self.func
+        return ((k, x) for k, v in self.prev.iterator(split) for x in f(v))
+
+
+class UnionRDD(RDD):
+    def __init__(self, ctx, rdds):
+        RDD.__init__(self, ctx)
+        self.rdds = rdds
+        self._splits = []
+        for r in rdds:
+            for s in r.splits:
+                sp = Split(len(self._splits))
+                sp.rdd, sp.split = r, s
+                self._splits.append(sp)
+
+    def compute(self, split):
+        return split.rdd.iterator(split.split)
+
+
+class ParallelCollection(RDD):
+    """dpark/rdd.py:1556-1598: a list cut into numSlices contiguous chunks of
+    ceil(len/numSlices) (numSlices capped to len; trailing chunks may be empty)."""
+
+    def __init__(self, ctx, data, numSlices, taskMemory=None):
+        RDD.__init__(self, ctx)
+        data = data if isinstance(data, (list, range)) else list(data)
+        self.size = len(data)
+        k = max(1, min(self.size, numSlices))
+        if k <= 0:
+            raise ValueError("invalid numSlices %d" % numSlices)
+        if self.size == 0:
+            chunks = [[]]
+        else:
+            per = -(-self.size // k)
+            chunks = [data[i * per:i * per + per] for i in range(k)]
+        self._splits = []
+        for i, c in enumerate(chunks):
+            sp = Split(i)
+            sp.values = c
+            self._splits.append(sp)
+
+    def compute(self, split):
+        return iter(split.values)
+
+
+class ColumnarRDD(RDD):
+    """Extension: a (k, v) RDD whose partitions are already columns -- numpy
+    arrays or torch tensors (host or cuda).  This is how 1e8..1e9-row inputs
+    enter without ever becoming Python tuples; a ShuffledRDD on top of it takes
+    the columns as they are."""
+
+    def __init__(self, ctx, keys, vals, numSlices):
+        RDD.__init__(self, ctx)
+        import torch
+        self.keys = keys if torch.is_tensor(keys) else torch.from_numpy(np.ascontiguousarray(keys))
+        self.vals = vals if torch.is_tensor(vals) else torch.from_numpy(np.ascontiguousarray(vals))
+        if self.keys.numel() != self.vals.numel():
+            raise DparkUserFatalError("ragged pair columns: %d keys, %d values"
+                                      % (self.keys.numel(), self.vals.numel()))
+        n = int(self.keys.numel())
+        k = max(1, min(n, numSlices)) if n else 1
+        per = -(-n // k) if n else 0
+        self._splits = []
+        for i in range(k):
+            sp = Split(i)
+            sp.begin, sp.end = min(n, i * per), min(n, i * per + per)
+            self._splits.append(sp)
+
+    def columns(self, split):
+        return self.keys[split.begin:split.end], self.vals[split.begin:split.end]
+
+    def compute(self, split):
+        k, v = self.columns(split)
+        return zip(k.cpu().tolist(), v.cpu().tolist())
+
+
+class TextFileRDD(RDD):
+    """dpark/rdd.py:1633-1711: byte-range splits; a split owns the lines that
+    START inside its range (a line straddling the end belongs to the split it
+    starts in)."""
+    DEFAULT_SPLIT_SIZE = 64 * 1024 * 1024
+
+    def __init__(self, ctx, path, numSplits=None, splitSize=None):
+        RDD.__init__(self, ctx)
+        self.path = path
+        size = os.path.getsize(path)
+        if splitSize is None:
+            splitSize = self.DEFAULT_SPLIT_SIZE if numSplits is None else (size // numSplits or self.DEFAULT_SPLIT_SIZE)
+        n = size // splitSize + (1 if size % splitSize > 0 else 0)
+        self.splitSize = splitSize
+        self._splits = []
+        for i in range(n):
+            sp = Split(i)
+            sp.begin, sp.end = i * splitSize, min(size, (i + 1) * splitSize)
+            self._splits.append(sp)
+
+    def compute(self, split):
+        with open(self.path, "rb") as f:
+            start, end = split.begin, split.end
+            if start > 0:
+                f.seek(start - 1)
+                byte = f.read(1)
+                while byte != b"\n":
+                    byte = f.read(1)
+                    if not byte:
+                        return
+                    start += 1
+            if start >= end:
+                return
+            for line in f:
+                size = len(line)
+                text = line.decode("utf-8")
+                yield text[:-1] if text.endswith("\n") else text
+                start += size
+                if start >= end:
+                    break
+
+
+class OutputTextFileRDD(DerivedRDD):
+    """dpark/rdd.py:2097-2161: one file `%04d<ext>` per partition, empty
+    partitions write nothing; yields the paths written."""
+
+    def __init__(self, rdd, path, ext="", overwrite=False, compress=False):
+        if os.path.exists(path):
+            if not os.path.isdir(path):
+                raise Exception("output must be dir")
+            if overwrite:
+                for n in os.listdir(path):
+                    p = os.path.join(path, n)
+                    if os.path.isdir(p):
+                        shutil.rmtree(p)
+                    else:
+                        os.remove(p)
+        else:
+            os.makedirs(path)
+        DerivedRDD.__init__(self, rdd)
+        self.path = os.path.abspath(path)
+        if ext and not ext.startswith("."):
+            ext = "." + ext
+        if compress and not ext.endswith("gz"):
+            ext += ".gz"
+        self.ext, self.overwrite, self.compress = ext, overwrite, compress
+
+    def compute(self, split):
+        path = os.path.join(self.path, "%04d%s" % (split.index, self.ext))
+        if os.path.exists(path) and not self.overwrite:
+            return
+        lines = list(self.prev.iterator(split))
+        if not lines:
+            return
+        tmp = path + ".tmp%d" % os.getpid()
+        if self.compress:
+            import gzip
+            opener = lambda p: gzip.open(p, "wt", encoding="utf-8")  # noqa: E731
+        else:
+            opener = lambda p: open(p, "w", encoding="utf-8")        # noqa: E731
+        with opener(tmp) as f:
+            for line in lines:
+                f.write(line if line.endswith("\n") else line + "\n")
+        os.rename(tmp, path)
+        yield path
+
+
+class ShuffledRDD(RDD):
+    """dpark/rdd.py:1101-1134.  The plan node is built eagerly (aggregator is
+    recognised at construction, so unsupported combiners fail when the job is
+    declared, not in the middle of it); the shuffle itself runs once, on the
+    GPU, the first time any partition is asked for, and is reused afterwards
+    (the reference caches map outputs per shuffleId the same way)."""
+
+    def __init__(self, parent, aggregator, part, taskMemory=None, rddconf=None):
+        RDD.__init__(self, parent.ctx)
+        if not isinstance(part, Partitioner):
+            raise TypeError("splits must be an int or a Partitioner")
+        if not isinstance(part, HashPartitioner):
+            raise NotImplementedError("only HashPartitioner is supported on the B200 shuffle path")
+        self.parent = parent
+        self.aggregator = aggregator
+        self.partitioner = part
+        if taskMemory:
+            self.mem = taskMemory
+        self._splits = [Split(i) for i in range(part.numPartitions)]
+        self.shuffleId = self.ctx.newShuffleId()
+        self.set_rddconf(rddconf)
+        self._dependencies = [ShuffleDependency(self.shuffleId, parent, aggregator, part, self.rddconf)]
+        self.kind, self.op = trace.recognize_aggregator(aggregator)
+        if self.kind == "group":
+            self.rddconf.op = conf.OP_GROUPBY
+        self._result = None
+
+    def _materialize(self):
+        if self._result is None:
+            from . import engine
+            self._result = engine.run_shuffle(self)
+        return self._result
+
+    def compute(self, split):
+        return iter(self._materialize().rows(split.index))
+
+    def columns(self, split):
+        """Extension: the partition as columns (numpy) instead of Python rows."""
+        return self._materialize().columns(split.index)

@@ -1,0 +1,73 @@
+"""reduceByKey over str / bytes keys (examples/wc.py's shape).
+
+Columnar form of the keys: one uint8 buffer + int64 offsets.  On the device:
+
+    hash_bytes     portable_hash per row (string_hash over signed chars for bytes,
+                   unicode_hash over code points for str; dpark/portable_hash.pyx:17-48)
+    dict_encode    representative row id per row (key identity by VALUE, like the
+                   reference's dicts -- the 64-bit hash is never trusted as identity)
+    partition_count + combine(DPK_K_ROWID)
+                   rows are routed by their hash to the reference's partitions and
+                   merged per representative id (map-side combine and reduce-side
+                   merge collapse into one pass on a single GPU, because every row
+                   of a key is local).
+
+Only (representative id, combined value) pairs come back; the host decodes each
+distinct key once from the byte buffer it already holds.
+
+Multi-GPU exchange of variable-length keys is a later row:
+this module raises if torch.distributed is initialised with more than one rank.
+"""
+import numpy as np
+import torch
+
+from . import _native as nv
+from . import columnar
+
+
+def _concat(splits):
+    datas, offs, vals, base, rows = [], [np.zeros(1, np.int64)], [], 0, 0
+    for c in splits:
+        if c.n == 0:
+            continue
+        datas.append(c.keys)
+        offs.append(c.key_offsets[1:] + base)
+        base += int(c.key_offsets[-1])
+        vals.append(c.vals)
+        rows += c.n
+    data = np.concatenate(datas) if datas else np.zeros(0, np.uint8)
+    offsets = np.concatenate(offs)
+    v = np.concatenate(vals) if vals else np.zeros(0, np.int64)
+    return data, offsets, v, rows
+
+
+def reduce_by_key_bytes(splits, key_kind, P, thresholds, op, dev, res):
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        raise NotImplementedError("str/bytes keys across several GPUs are not implemented yet")
+    data, offsets, vals, n = _concat(splits)
+    if n == 0:
+        for p in range(P):
+            res.parts[p] = ([], [])
+        return res
+    mode = nv.STR_UTF8 if key_kind == columnar.KEY_STR else nv.BYTES_SIGNED
+    d_data = torch.from_numpy(data if data.size else np.zeros(1, np.uint8)).to(dev)
+    d_off = torch.from_numpy(offsets).to(dev)
+    d_vals = torch.from_numpy(vals).to(dev)
+    h = nv.hash_bytes(d_data, d_off, mode)
+    rep = nv.dict_encode(d_data, d_off, h)
+    bucket_rows, _ = nv.partition_count(h, P, thresholds, prehashed=True)
+    ok, ov, off, cnt = nv.combine(rep, d_vals, op, P, bucket_rows, 0, P, thresholds, 0, row_hash=h)
+    off_h, cnt_h = off.cpu().tolist(), cnt.cpu().tolist()
+    ok_h, ov_h = ok.cpu().numpy(), ov.cpu().numpy()
+    raw = data.tobytes()
+    offs_l = offsets
+    is_str = key_kind == columnar.KEY_STR
+    for p in range(P):
+        ids = ok_h[off_h[p]:off_h[p] + cnt_h[p]]
+        keys = []
+        for r in ids.tolist():
+            b = raw[offs_l[r]:offs_l[r + 1]]
+            keys.append(b.decode("utf-8", "surrogatepass") if is_str else b)
+        res.parts[p] = (keys, ov_h[off_h[p]:off_h[p] + cnt_h[p]].tolist())
+    return res

@@ -41,7 +41,8 @@ enum {
 
 /* key column kinds.  The hash of each follows dpark/portable_hash.pyx:51-70:
  * ints and floats -> Python's builtin hash(); see dpk_hash_keys. */
-enum { DPK_K_I64 = 0, DPK_K_I32 = 1, DPK_K_F64 = 2, DPK_K_U64 = 3, DPK_K_F32 = 4 };
+enum { DPK_K_I64 = 0, DPK_K_I32 = 1, DPK_K_F64 = 2, DPK_K_U64 = 3, DPK_K_F32 = 4,
+       DPK_K_ROWID = 5 /* dpk_combine only: int64 ids of representative rows, hash looked up in key_aux */ };
 /* value column kinds */
 enum { DPK_V_I64 = 0, DPK_V_F64 = 1, DPK_V_I32 = 2, DPK_V_F32 = 3 };
 /* combiner ops a reduceByKey(func) lowers to (dpark/rdd.py:543-545 builds
@@ -129,11 +130,23 @@ int dpk_partition(const void *keys, int key_kind, const void *vals, int32_t val_
  * floats); out_vals is 8 bytes per row.  out_keys/out_vals hold n entries.
  */
 int64_t dpk_combine_workspace_bytes(int64_t n, int32_t nbuckets);
-int dpk_combine(const void *keys, int key_kind, const void *vals, int val_kind, int64_t n, int op,
-                int32_t P, const int64_t *thresholds, int32_t nthr, int32_t sub_bits,
+int dpk_combine(const void *keys, int key_kind, const int64_t *key_aux, const void *vals,
+                int val_kind, int64_t n, int op, int32_t P, const int64_t *thresholds, int32_t nthr, int32_t sub_bits,
                 int32_t part_first, int32_t nparts, const int64_t *bucket_rows, void *out_keys,
                 void *out_vals, int64_t *out_offsets, int64_t *out_counts, void *ws,
                 int64_t ws_bytes, dpk_stream_t stream);
+
+/* ---- variable-length keys (str / bytes): key identity on the device ---------
+ * The reference's dicts compare keys by value; two different strings may share
+ * a portable_hash, so the hash alone cannot be the key.  dpk_dict_encode gives
+ * every row the index of a representative row holding an equal byte string
+ * (out_rep[i] == out_rep[j]  <=>  key i == key j): an open-addressing table of
+ * row indices, probed by hash, verified byte-wise.  The representative ids then
+ * go through dpk_combine as DPK_K_ROWID keys with key_aux = hash.
+ * hash: the column dpk_hash_bytes produced for the same (data, offsets). */
+int64_t dpk_dict_encode_workspace_bytes(int64_t n);
+int dpk_dict_encode(const uint8_t *data, const int64_t *offsets, const int64_t *hash, int64_t n,
+                    int64_t *out_rep, void *ws, int64_t ws_bytes, dpk_stream_t stream);
 
 /* ---- measurement hooks (SURVEY.md §5 tracing: TaskStats -> CUDA events) -----
  * dpk_launch_count: kernels launched by this library since load.

@@ -1,0 +1,256 @@
+"""CPU-only tests of the host side: combiner recognition, columnar ingest, the
+operator surface's split semantics, the C-ABI library's exports, and the
+__host__ __device__ hash/partition arithmetic run on the CPU (hostcheck)."""
+import ctypes as C
+import operator
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from tests.golden_util import dec, load
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ----------------------------------------------------------------- trace
+def test_recognize_binary_ops():
+    from dpark_b200 import trace
+    cases = [
+        (lambda x, y: x + y, "sum"), (lambda a, b: b + a, "sum"), (operator.add, "sum"),
+        (lambda x, y: x * y, "prod"), (min, "min"), (max, "max"),
+        (lambda x, y: min(x, y), "min"), (lambda x, y: max(y, x), "max"),
+        (lambda x, y: x if x < y else y, "min"), (lambda x, y: y if y >= x else x, "max"),
+        (lambda x, y: x | y, "or"), (lambda x, y: x & y, "and"), (lambda x, y: x ^ y, "xor"),
+    ]
+    for f, want in cases:
+        assert trace.recognize_binary(f) == want
+
+
+@pytest.mark.parametrize("bad", [
+    lambda x, y: x - y, lambda x, y: x + y + 1, lambda x, y: x, lambda x, y: y,
+    lambda x, y: (x[0] + y[0], x[1] + y[1]), lambda x, y: x + 2 * y, lambda x, y: str(x) + str(y),
+    lambda x, y: x if x < y else x,
+])
+def test_unrecognised_combiners_raise_no_cpu_fallback(bad):
+    from dpark_b200 import trace
+    with pytest.raises(NotImplementedError):
+        trace.recognize_binary(bad)
+
+
+def test_recognize_aggregator_kinds():
+    from dpark_b200 import trace
+    from dpark_b200.dependency import AddAggregator, Aggregator, GroupByAggregator, MergeAggregator
+    assert trace.recognize_aggregator(GroupByAggregator()) == ("group", None)
+    assert trace.recognize_aggregator(MergeAggregator()) == ("group", None)
+    assert trace.recognize_aggregator(AddAggregator()) == ("reduce", "sum")
+    f = lambda a, b: a + b  # noqa: E731
+    assert trace.recognize_aggregator(Aggregator(lambda x: x, f, f)) == ("reduce", "sum")
+    with pytest.raises(NotImplementedError):
+        trace.recognize_aggregator(Aggregator(lambda x: [x], f, f))
+    with pytest.raises(NotImplementedError):
+        trace.recognize_aggregator(Aggregator(lambda x: x, f, lambda a, b: a * b))
+
+
+# -------------------------------------------------------------- columnar
+def test_ingest_pairs_kinds_and_errors():
+    from dpark_b200 import columnar
+    from dpark_b200.errors import DparkUserFatalError
+    c = columnar.ingest_pairs([(1, 2), (-5, 7)])
+    assert c.key_kind == "i64" and c.val_kind == "i64" and c.keys.tolist() == [1, -5]
+    c = columnar.ingest_pairs([("ab", 1.5), ("你好", 2.0), ("", 0.0)])
+    assert c.key_kind == "str" and c.val_kind == "f64"
+    assert columnar.decode_keys("str", c.keys, c.key_offsets) == ["ab", "你好", ""]
+    c = columnar.ingest_pairs([(b"\xff\x00", 1)])
+    assert c.key_kind == "bytes" and columnar.decode_keys("bytes", c.keys, c.key_offsets) == [b"\xff\x00"]
+    c = columnar.ingest_pairs([(1, object()), (2, "x")], numeric_values=False)
+    assert c.val_kind == "obj" and c.vals.tolist() == [0, 1] and len(c.objs) == 2
+    with pytest.raises(DparkUserFatalError):
+        columnar.ingest_pairs([(1, 2), 3])                    # dpark/task.py:216-219
+    with pytest.raises(DparkUserFatalError):
+        columnar.ingest_pairs([(1, 2, 3)])
+    with pytest.raises(TypeError, match="unhashable by portable_hash"):
+        columnar.ingest_pairs([(True, 1)])                    # bool is not int for the reference
+    with pytest.raises(TypeError, match="unhashable by portable_hash"):
+        columnar.ingest_pairs([([1], 1)])
+    with pytest.raises(TypeError):
+        columnar.ingest_pairs([(1, 1), ("a", 1)])
+    with pytest.raises(TypeError):
+        columnar.ingest_pairs([(2 ** 70, 1)])
+    with pytest.raises(TypeError):
+        columnar.ingest_pairs([(1, 1), (2, 2.5)])
+
+
+# ------------------------------------------------------------ rdd surface
+def _ctx():
+    sys.argv = [sys.argv[0]]
+    from dpark_b200 import DparkContext
+    return DparkContext("local")
+
+
+def test_parallelize_split_sizes_match_reference():
+    dc = _ctx()
+    for case in load("shuffle_cases.json")["cases"]:
+        rows = case["rows"]
+        got = [len(x) for x in dc.parallelize(rows, case["M"]).glom().collect()]
+        assert got == case["split_sizes"], case["name"]
+
+
+def test_narrow_ops_and_actions():
+    dc = _ctx()
+    r = dc.parallelize(range(10), 3)
+    assert r.map(lambda x: x * 2).filter(lambda x: x % 3 == 0).collect() == [0, 6, 12, 18]
+    assert r.flatMap(lambda x: [x] * (x % 3)).count() == sum(x % 3 for x in range(10))
+    assert r.reduce(lambda a, b: a + b) == 45
+    assert r.take(4) == [0, 1, 2, 3] and r.first() == 0
+    kv = dc.makeRDD([(1, 2), (3, 4)], 2)
+    assert kv.mapValue(lambda v: v + 1).collectAsMap() == {1: 3, 3: 5}
+    assert kv.flatMapValue(lambda v: range(v)).count() == 6
+    assert dc.union([r, r]).count() == 20 and len(dc.union([r, r])) == 6
+    assert dc.defaultParallelism == 2 and dc.defaultMinSplits == 2
+
+
+def test_text_file_rdd_splits_own_the_lines_that_start_in_them(tmp_path):
+    dc = _ctx()
+    from dpark_b200.rdd import TextFileRDD
+    lines = ["line %d %s" % (i, "x" * (i % 17)) for i in range(500)] + ["", "你好 world", "last-without-newline"]
+    p = tmp_path / "in.txt"
+    p.write_bytes("\n".join(lines).encode("utf-8"))
+    for split_size in (7, 64, 1000, 10 ** 6):
+        rdd = TextFileRDD(dc, str(p), splitSize=split_size)
+        assert rdd.collect() == lines, split_size
+    assert dc.textFile(str(p), numSplits=4).collect() == lines
+
+
+def test_save_as_text_file_layout(tmp_path):
+    dc = _ctx()
+    out = tmp_path / "out"
+    paths = dc.parallelize(["a", "b", "c"], 3).filter(lambda x: x != "b").saveAsTextFile(str(out))
+    assert sorted(os.path.basename(p) for p in paths) == ["0000", "0002"]   # empty partition: no file
+    assert (out / "0000").read_text() == "a\n"
+
+
+def test_shuffled_rdd_plan_is_checked_at_declaration():
+    dc = _ctx()
+    kv = dc.parallelize([(1, 1)], 1)
+    with pytest.raises(NotImplementedError):
+        kv.reduceByKey(lambda x, y: x - y)
+    sh = kv.reduceByKey(lambda x, y: x + y, 6)
+    assert len(sh) == 6 and sh.partitioner.numPartitions == 6 and sh.op == "sum"
+    assert kv.groupByKey(3).rddconf.is_groupby
+    assert len(kv.reduceByKey(lambda x, y: x + y)) == 1      # min(defaultMinSplits, len(self))
+
+
+def test_hash_partitioner_record():
+    from dpark_b200 import HashPartitioner
+    assert HashPartitioner(4) == HashPartitioner(4) and HashPartitioner(4) != HashPartitioner(5)
+    assert HashPartitioner(3, [10, 100]) != HashPartitioner(3)
+    with pytest.raises(AssertionError):
+        HashPartitioner(3, [1])
+    assert HashPartitioner(0).numPartitions == 1
+
+
+def test_shuffle_without_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    dc = _ctx()
+    from dpark_b200 import _native
+    with pytest.raises(_native.NativeError):
+        dc.parallelize([(1, 1), (2, 2)], 2).reduceByKey(lambda x, y: x + y).collect()
+
+
+# ------------------------------------------------------------- C ABI library
+def test_library_exports_every_symbol_the_header_declares():
+    from dpark_b200 import _native
+    hdr = open(os.path.join(ROOT, "include", "dpark_b200.h")).read()
+    declared = set(re.findall(r"\b(dpk_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations found"
+    L = _native.lib()
+    missing = [n for n in sorted(declared) if not hasattr(L, n)]
+    assert not missing, missing
+    assert declared == set(_native.EXPORTS)
+    assert L.dpk_abi_version() == 1
+    assert L.dpk_partition_workspace_bytes(0, 8) > 0
+
+
+def test_product_never_imports_the_oracle():
+    bad = []
+    for dirpath, _, names in os.walk(os.path.join(ROOT, "dpark_b200")):
+        for n in names:
+            if n.endswith((".py", ".cu", ".cuh", ".h")):
+                if re.search(r"^\s*(from|import)\s+oracle|dpk_oracle|orc_", open(os.path.join(dirpath, n)).read(), re.M):
+                    bad.append(n)
+    assert not bad, bad
+
+
+# --------------------------------------------------- hostcheck (HD functions)
+def _hostcheck():
+    path = os.path.join(ROOT, "tests", "_hostcheck.so")
+    if not os.path.exists(path):
+        subprocess.call([sys.executable, "-c", "import __graft_entry__ as g; g.build()"], cwd=ROOT)
+    if not os.path.exists(path):
+        pytest.skip("hostcheck not built")
+    return C.CDLL(path)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def test_device_hash_functions_on_cpu_match_oracle():
+    L = _hostcheck()
+    rng = np.random.default_rng(1)
+    xs = rng.integers(-2 ** 63, 2 ** 63 - 1, 200000, dtype=np.int64, endpoint=True)
+    xs[:8] = [0, -1, 2 ** 61 - 1, 2 ** 61, -(2 ** 61 - 1), 2 ** 63 - 1, -2 ** 63, 4 * (2 ** 61 - 1)]
+    o = np.empty_like(xs)
+    L.hc_hash_i64(_p(xs), C.c_int64(len(xs)), _p(o))
+    assert np.array_equal(o, orc.hash_vec(xs))
+    fs = np.concatenate([rng.standard_normal(50000) * 10.0 ** rng.integers(-300, 300, 50000),
+                         np.array([0.0, -0.0, np.inf, -np.inf, 5e-324, 1.5, 2.0 ** 61, 2.0 ** 61 - 1])])
+    o = np.empty(len(fs), dtype=np.int64)
+    L.hc_hash_f64(_p(fs), C.c_int64(len(fs)), _p(o))
+    assert np.array_equal(o, orc.hash_vec(fs))
+    hv = load("hash_vectors.json")
+    for tag, mode, encf in (("b", 0, lambda b: b), ("s", 1, lambda s: s.encode("utf-8", "surrogatepass"))):
+        ks = [(dec(r["key"]), r["hash"]) for r in hv["rows"] if isinstance(r["key"], dict) and tag in r["key"]]
+        blobs = [encf(k) for k, _ in ks]
+        offs = np.zeros(len(blobs) + 1, dtype=np.int64)
+        offs[1:] = np.cumsum([len(b) for b in blobs])
+        data = np.frombuffer(b"".join(blobs), dtype=np.uint8).copy()
+        o = np.empty(len(blobs), dtype=np.int64)
+        L.hc_hash_bytes(_p(data), _p(offs), C.c_int64(len(blobs)), mode, _p(o))
+        assert o.tolist() == [h for _, h in ks]
+
+
+@pytest.mark.parametrize("P", [1, 2, 3, 5, 6, 7, 8, 12, 63, 64, 65, 100, 1000, 1023, 1025, 4095, 4096,
+                               2 ** 31 - 1, 2 ** 30 + 3])
+def test_device_floor_mod_on_cpu_matches_oracle(P):
+    L = _hostcheck()
+    rng = np.random.default_rng(P)
+    h = rng.integers(-2 ** 63, 2 ** 63 - 1, 100000, dtype=np.int64, endpoint=True)
+    h[:6] = [0, -1, -2, 2 ** 61 - 2, -(2 ** 61 - 2), 2 ** 63 - 1]
+    pid = np.empty(len(h), dtype=np.int32)
+    assert L.hc_partition(_p(h), C.c_int64(len(h)), C.c_int32(P), None, 0, _p(pid)) == 0
+    assert np.array_equal(pid, orc.partition_vec(h, P))
+
+
+def test_device_bisect_and_sub_buckets_on_cpu():
+    L = _hostcheck()
+    rng = np.random.default_rng(5)
+    h = rng.integers(-2 ** 63, 2 ** 63 - 1, 50000, dtype=np.int64, endpoint=True)
+    thr = np.sort(rng.integers(-2 ** 62, 2 ** 62, 15, dtype=np.int64))
+    pid = np.empty(len(h), dtype=np.int32)
+    assert L.hc_partition(_p(h), C.c_int64(len(h)), C.c_int32(16), _p(thr), 15, _p(pid)) == 0
+    assert np.array_equal(pid, orc.partition_vec(h, 16, thr))
+    for P, sb in ((8, 5), (3, 2), (1, 7)):
+        b = np.empty(len(h), dtype=np.int32)
+        assert L.hc_bucket(_p(h), C.c_int64(len(h)), C.c_int32(P), C.c_int32(sb), _p(b)) == 0
+        assert np.array_equal(b >> sb, orc.partition_vec(h, P))     # refinement of the reference partition
+        assert b.min() >= 0 and b.max() < (P << sb)
+        cnt = np.bincount(b & ((1 << sb) - 1), minlength=1 << sb)
+        assert cnt.min() > 0.5 * len(h) / (1 << sb)                 # sub-bucket bits are well mixed
