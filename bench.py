@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-sample-rows", type=int, default=4_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--reduce-impl", type=int, default=1, help="A/B switch of the reduce-side kernel (dpk_set_option)")
+    ap.add_argument("--sub-bits", type=int, default=-1, help="override the sub-bucket bits (default: auto)")
     return ap.parse_args()
 
 
@@ -254,7 +256,8 @@ def run_ours(args):
     kc = [keys[i * per:min(n, (i + 1) * per)] for i in range(M)]
     vc = [vals[i * per:min(n, (i + 1) * per)] for i in range(M)]
 
-    sub_bits = shuffle.choose_sub_bits(n * world, P)
+    sub_bits = shuffle.choose_sub_bits(n * world, P) if args.sub_bits < 0 else args.sub_bits
+    nv.set_option("reduce_impl", args.reduce_impl)
 
     def step():
         mo = shuffle.map_side(kc, vc, P, None, False, sub_bits)
@@ -314,6 +317,7 @@ def run_ours(args):
         "tbl_init": 0,
         "tbl_insert": kv * nrecv,                     # read every received pair once
         "tbl_compact": kv * int(tot[2]) // world,     # write one pair per distinct key
+        "bucket_reduce": kv * (nrecv + int(tot[2]) // world),   # fused init+insert+compact per bucket
     }
     kernels = []
     ktotal = sum(a[0] for a in agg.values()) or 1.0
@@ -333,10 +337,11 @@ def run_ours(args):
                 "traffic": None, "peak_source": peak_src,
                 "alg_bytes_per_launch": dom_bytes_launch, "ms_per_launch": dom_launch_ms,
                 "share_of_step": dom_ms / ktotal}
-    red_ms = sum(agg.get(k, [0.0, 0])[0] for k in ("tbl_init", "tbl_insert", "tbl_compact")) / args.steps
+    red_names = ("tbl_plan", "side_init", "side_flush", "tbl_init", "tbl_insert", "tbl_compact", "bucket_reduce")
+    red_ms = sum(agg.get(k, [0.0, 0])[0] for k in red_names) / args.steps
     if red_ms > 0:
         red_bytes = alg["tbl_insert"] + alg["tbl_compact"]
-        roofline_reduce = {"bound": "hbm", "kernel": "reduce side (tbl_init+tbl_insert+tbl_compact)",
+        roofline_reduce = {"bound": "hbm", "kernel": "reduce side (DiskHashMerger._merge: plan + bucket_reduce)",
                            "achieved": red_bytes / (red_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                            "frac": red_bytes / (red_ms * 1e-3) / 1e9 / peak, "ms_per_step": red_ms}
     else:

@@ -31,7 +31,7 @@ EXPORTS = [
     "dpk_partition_ids", "dpk_partition_workspace_bytes", "dpk_partition_count",
     "dpk_partition_scatter", "dpk_partition", "dpk_combine_workspace_bytes", "dpk_combine",
     "dpk_launch_count", "dpk_prof_enable", "dpk_prof_count", "dpk_prof_get",
-    "dpk_dict_encode_workspace_bytes", "dpk_dict_encode",
+    "dpk_dict_encode_workspace_bytes", "dpk_dict_encode", "dpk_set_option",
 ]
 
 _lib = None
@@ -64,9 +64,10 @@ def lib():
         L.dpk_partition_count.argtypes = [vp, ci, i64, i32, vp, i32, i32, vp, vp, i64, vp]
         L.dpk_partition_scatter.argtypes = [vp, ci, vp, i32, i64, i32, vp, i32, i32, vp, vp, vp, vp, i64, vp]
         L.dpk_partition.argtypes = [vp, ci, vp, i32, i64, i32, vp, i32, i32, vp, vp, vp, vp, i64, vp]
-        L.dpk_combine_workspace_bytes.argtypes = [i64, i32]
-        L.dpk_combine.argtypes = [vp, ci, vp, vp, ci, i64, ci, i32, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp,
-                                  vp, i64, vp]
+        L.dpk_combine_workspace_bytes.argtypes = [i64, i32, i32]
+        L.dpk_combine.argtypes = [vp, ci, vp, vp, ci, i64, ci, i32, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp,
+                                  vp, vp, i64, vp]
+        L.dpk_set_option.argtypes = [C.c_char_p, i64]
         L.dpk_dict_encode_workspace_bytes.restype = i64
         L.dpk_dict_encode_workspace_bytes.argtypes = [i64]
         L.dpk_dict_encode.argtypes = [vp, vp, vp, i64, vp, vp, i64, vp]
@@ -221,24 +222,29 @@ def acc_dtype(vals_dtype):
     return torch.float64 if vals_dtype in (torch.float32, torch.float64) else torch.int64
 
 
-def combine(keys, vals, op, P, bucket_rows, part_first=0, nparts=None, thresholds=None, sub_bits=0,
+def combine(keys, vals, op, P, seg_rows, part_first=0, nparts=None, thresholds=None, sub_bits=0,
             row_hash=None):
     """Reduce-side merge (DiskHashMerger._merge, dpark/shuffle.py:600-608) of the
-    rows of partitions [part_first, part_first+nparts).  bucket_rows: device int64
-    [nparts << sub_bits] rows per local fine bucket.  Returns (out_keys, out_vals,
-    out_offsets[nparts+1], out_counts[nparts]); partition j's distinct keys are
-    out[out_offsets[j] : out_offsets[j] + out_counts[j]].  With row_hash (the
-    per-row portable_hash column) the keys are representative row ids from
+    rows of partitions [part_first, part_first+nparts).  Rows are laid out
+    source-major, bucket-major inside; seg_rows: device int64 [nsrc, nparts <<
+    sub_bits] rows of local fine bucket b from source s.  Returns (out_keys,
+    out_vals, out_offsets[nparts+1], out_counts[nparts]); partition j's distinct
+    keys are out[out_offsets[j] : out_offsets[j] + out_counts[j]].  With row_hash
+    (the per-row portable_hash column) the keys are representative row ids from
     dict_encode (DPK_K_ROWID)."""
-    _need_cuda(keys, vals, bucket_rows, row_hash)
+    _need_cuda(keys, vals, seg_rows, row_hash)
     if nparts is None:
         nparts = P
     n = keys.numel()
     F = nparts << sub_bits
-    if bucket_rows.numel() != F or bucket_rows.dtype != torch.int64:
-        raise ValueError("bucket_rows must be int64[%d]" % F)
+    if seg_rows.dim() == 1:
+        seg_rows = seg_rows.unsqueeze(0)
+    nsrc = int(seg_rows.shape[0])
+    if seg_rows.shape[1] != F or seg_rows.dtype != torch.int64:
+        raise ValueError("seg_rows must be int64[nsrc, %d]" % F)
+    bucket_rows = seg_rows
     thr, nthr = _thr(thresholds, keys.device)
-    ws_bytes = lib().dpk_combine_workspace_bytes(n, F)
+    ws_bytes = lib().dpk_combine_workspace_bytes(n, F, nsrc)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=keys.device)
     out_keys = torch.empty_like(keys)
     out_vals = torch.empty(n, dtype=acc_dtype(vals.dtype), device=keys.device)
@@ -246,7 +252,7 @@ def combine(keys, vals, op, P, bucket_rows, part_first=0, nparts=None, threshold
     out_counts = torch.empty(nparts, dtype=torch.int64, device=keys.device)
     kk = key_kind(keys) if row_hash is None else K_ROWID
     _check(lib().dpk_combine(_ptr(keys), kk, _ptr(row_hash), _ptr(vals), val_kind(vals), n, OPS[op], P,
-                             _ptr(thr), nthr, sub_bits, part_first, nparts, _ptr(bucket_rows), _ptr(out_keys),
+                             _ptr(thr), nthr, sub_bits, part_first, nparts, nsrc, _ptr(bucket_rows), _ptr(out_keys),
                              _ptr(out_vals), _ptr(out_offsets), _ptr(out_counts), _ptr(ws), ws_bytes,
                              _stream()))
     return out_keys, out_vals, out_offsets, out_counts
@@ -263,6 +269,10 @@ def dict_encode(data, offsets, hashes):
     _check(lib().dpk_dict_encode(_ptr(data), _ptr(offsets), _ptr(hashes), n, _ptr(rep), _ptr(ws), ws_bytes,
                                  _stream()))
     return rep
+
+
+def set_option(name, value):
+    _check(lib().dpk_set_option(name.encode(), int(value)))
 
 
 # ---- measurement hooks ---------------------------------------------------------

@@ -19,7 +19,10 @@
 // reference's big ints), float64 for float values (the reference adds Python
 // floats).  Algorithmic bytes: (K+V) * (rows + distinct).
 #include "dpk_common.cuh"
+#include <cooperative_groups.h>
 #include <type_traits>
+
+namespace cg = cooperative_groups;
 
 namespace dpk {
 
@@ -125,18 +128,21 @@ template <> struct Acc<double> {
 };
 
 // ---- kernels ---------------------------------------------------------------
-// plan (single CTA): bucket_rows[F] -> tbl_off[F+1] (slot offsets, region b holds
-// 1.5*rows_b + 32 slots rounded to 8) and part_off[nparts+1] (row offsets of the
-// partitions = upper bound of their output ranges).
+// plan (single CTA).  seg_rows[nsrc][F]: rows of local fine bucket b that came
+// from source s (the received buffer is source-major, bucket-major inside).
+//   tbl_off[F+1]   slot offsets: region b holds 1.5*rows_b + 32 slots, rounded to 8
+//   part_off[nparts+1] row offsets of the partitions (= start of their output ranges)
+//   seg_start[nsrc][F] first row of segment (s, b) in the received buffer
 __global__ void __launch_bounds__(CB_THREADS)
-k_tbl_plan(const int64_t *__restrict__ bucket_rows, int32_t F, int32_t sub_bits, int32_t nparts,
-           int64_t *__restrict__ tbl_off, int64_t *__restrict__ part_off) {
-    __shared__ long long s_slots[CB_THREADS], s_rows[CB_THREADS];
+k_tbl_plan(const int64_t *__restrict__ seg_rows, int32_t nsrc, int32_t F, int32_t sub_bits, int32_t nparts,
+           int64_t *__restrict__ tbl_off, int64_t *__restrict__ part_off, int64_t *__restrict__ seg_start) {
+    __shared__ long long s_slots[CB_THREADS], s_rows[CB_THREADS], s_carry;
     const int E = (F + CB_THREADS - 1) / CB_THREADS;
     const int b0 = threadIdx.x * E, b1 = min(b0 + E, F);
     long long slots = 0, rows = 0;
     for (int b = b0; b < b1; b++) {
-        long long r = bucket_rows[b];
+        long long r = 0;
+        for (int s = 0; s < nsrc; s++) r += seg_rows[(int64_t)s * F + b];
         slots += ((r + (r >> 1) + 32 + 7) >> 3) << 3;
         rows += r;
     }
@@ -147,33 +153,72 @@ k_tbl_plan(const int64_t *__restrict__ bucket_rows, int32_t F, int32_t sub_bits,
     for (int t = 0; t < (int)threadIdx.x; t++) { sbase += s_slots[t]; rbase += s_rows[t]; }
     const int S = 1 << sub_bits;
     for (int b = b0; b < b1; b++) {
+        long long r = 0;
+        for (int s = 0; s < nsrc; s++) r += seg_rows[(int64_t)s * F + b];
         tbl_off[b] = sbase;
         if ((b & (S - 1)) == 0) part_off[b >> sub_bits] = rbase;
-        long long r = bucket_rows[b];
         sbase += ((r + (r >> 1) + 32 + 7) >> 3) << 3;
         rbase += r;
     }
     if (b0 < F && b1 == F) { tbl_off[F] = sbase; part_off[nparts] = rbase; }
     if (F == 0 && threadIdx.x == 0) { tbl_off[0] = 0; part_off[0] = 0; }
+    // seg_start: running row offset, source by source
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int s = 0; s < nsrc; s++) {
+        long long mine = 0;
+        for (int b = b0; b < b1; b++) mine += seg_rows[(int64_t)s * F + b];
+        s_rows[threadIdx.x] = mine;
+        __syncthreads();
+        long long base = s_carry;
+        for (int t = 0; t < (int)threadIdx.x; t++) base += s_rows[t];
+        for (int b = b0; b < b1; b++) {
+            seg_start[(int64_t)s * F + b] = base;
+            base += seg_rows[(int64_t)s * F + b];
+        }
+        __syncthreads();
+        if (threadIdx.x == CB_THREADS - 1) s_carry = base;   // last thread saw every earlier bucket
+        __syncthreads();
+    }
 }
 
-// slots [0, tbl_off[F]) plus the side slot at index max_slots
+__device__ __forceinline__ int4 slot_fill(int64_t ident) {
+    return make_int4((int)(uint32_t)((uint64_t)kEmpty & 0xffffffffu), (int)(uint32_t)((uint64_t)kEmpty >> 32),
+                     (int)(uint32_t)((uint64_t)ident & 0xffffffffu), (int)(uint32_t)((uint64_t)ident >> 32));
+}
+
+// claim-or-find the slot of key bits `kb` inside `region` (size slots), linear probing
+__device__ __forceinline__ Slot *probe_slot(Slot *region, uint32_t size, int64_t kb) {
+    uint32_t h = (uint32_t)(((mix64((uint64_t)kb) & 0xffffffffull) * (uint64_t)size) >> 32);
+    for (;;) {
+        int64_t cur = __ldcg(&region[h].key);
+        if (cur == kb) break;
+        if (cur == kEmpty) {
+            unsigned long long prev = atomicCAS((unsigned long long *)&region[h].key, (unsigned long long)kEmpty,
+                                                (unsigned long long)kb);
+            if (prev == (unsigned long long)kEmpty || prev == (unsigned long long)kb) break;
+        }
+        h = h + 1 == size ? 0 : h + 1;
+    }
+    return &region[h];
+}
+
+// ===== implementation 0: three grid-wide passes over all regions ================
 __global__ void __launch_bounds__(CB_THREADS)
-k_tbl_init(Slot *__restrict__ table, const int64_t *__restrict__ tbl_total, int64_t max_slots, int64_t ident) {
+k_tbl_init(Slot *__restrict__ table, const int64_t *__restrict__ tbl_total, int64_t ident) {
     const int64_t slots = *tbl_total;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const int4 fill = make_int4((int)(uint32_t)((uint64_t)kEmpty & 0xffffffffu), (int)(uint32_t)((uint64_t)kEmpty >> 32),
-                                (int)(uint32_t)((uint64_t)ident & 0xffffffffu), (int)(uint32_t)((uint64_t)ident >> 32));
-    if (i == 0) reinterpret_cast<int4 *>(table)[max_slots] = fill;
+    const int4 fill = slot_fill(ident);
     for (; i < slots; i += stride) reinterpret_cast<int4 *>(table)[i] = fill;
 }
 
 template <typename KeyT, typename ValT, typename AccT>
 __global__ void __launch_bounds__(CB_THREADS)
 k_tbl_insert(const KeyT *__restrict__ keys, const int64_t *__restrict__ aux, const ValT *__restrict__ vals,
-             int64_t n, int op, PartFn f, int32_t bucket_first, int32_t F, const int64_t *__restrict__ tbl_off, Slot *__restrict__ table,
-             Slot *__restrict__ side, int32_t *__restrict__ side_used) {
+             int64_t n, int op, PartFn f, int32_t bucket_first, int32_t F,
+             const int64_t *__restrict__ tbl_off, Slot *__restrict__ table, Slot *__restrict__ side,
+             int32_t *__restrict__ side_used) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
@@ -186,33 +231,18 @@ k_tbl_insert(const KeyT *__restrict__ keys, const int64_t *__restrict__ aux, con
             *side_used = 1;
         } else {
             int b = f.bucket(hash_of<KeyT>(key, aux)) - bucket_first;
-            b = min(max(b, 0), F - 1);  // rows of foreign partitions cannot occur; stay in bounds regardless
+            b = min(max(b, 0), F - 1);
             const int64_t base = __ldg(&tbl_off[b]);
-            const uint32_t size = (uint32_t)(__ldg(&tbl_off[b + 1]) - base);
-            uint32_t h = (uint32_t)(((mix64((uint64_t)kb) & 0xffffffffull) * (uint64_t)size) >> 32);
-            Slot *region = table + base;
-            for (;;) {
-                int64_t cur = __ldcg(&region[h].key);
-                if (cur == kb) break;
-                if (cur == kEmpty) {
-                    unsigned long long prev = atomicCAS((unsigned long long *)&region[h].key,
-                                                        (unsigned long long)kEmpty, (unsigned long long)kb);
-                    if (prev == (unsigned long long)kEmpty || prev == (unsigned long long)kb) break;
-                }
-                h = h + 1 == size ? 0 : h + 1;
-            }
-            s = &region[h];
+            s = probe_slot(table + base, (uint32_t)(__ldg(&tbl_off[b + 1]) - base), kb);
         }
         Acc<AccT>::apply(op, &s->acc, v);
     }
 }
 
-// slots [0, *tbl_total) are the tables; slot max_slots is the side slot (valid iff *side_used)
 template <typename KeyT>
 __global__ void __launch_bounds__(CB_THREADS)
-k_tbl_compact(const Slot *__restrict__ table, const int64_t *__restrict__ tbl_total, int64_t max_slots,
-              const int32_t *__restrict__ side_used, const int64_t *__restrict__ aux, PartFn f,
-              int32_t part_first, int32_t nparts,
+k_tbl_compact(const Slot *__restrict__ table, const int64_t *__restrict__ tbl_total,
+              const int64_t *__restrict__ aux, PartFn f, int32_t part_first, int32_t nparts,
               const int64_t *__restrict__ part_offsets, KeyT *__restrict__ out_keys,
               int64_t *__restrict__ out_vals, unsigned long long *__restrict__ out_counts) {
     extern __shared__ __align__(16) int32_t s_mem[];  // [nparts] counts, [nparts] 64-bit bases after
@@ -220,8 +250,7 @@ k_tbl_compact(const Slot *__restrict__ table, const int64_t *__restrict__ tbl_to
     long long *s_base = reinterpret_cast<long long *>(s_mem + ((nparts + 1) & ~1));
     const int lane = threadIdx.x & 31;
     constexpr int ITEMS = 4;
-    const int64_t nslots = *tbl_total;
-    const int64_t total = nslots + 1;
+    const int64_t total = *tbl_total;
     const int64_t tile = (int64_t)CB_THREADS * ITEMS;
     for (int64_t t0 = (int64_t)blockIdx.x * tile; t0 < total; t0 += (int64_t)gridDim.x * tile) {
         for (int p = threadIdx.x; p < nparts; p += CB_THREADS) s_cnt[p] = 0;
@@ -233,12 +262,10 @@ k_tbl_compact(const Slot *__restrict__ table, const int64_t *__restrict__ tbl_to
             int64_t i = t0 + (int64_t)j * CB_THREADS + threadIdx.x;
             lp[j] = -1;
             if (i < total) {
-                int4 raw = __ldcs(reinterpret_cast<const int4 *>(table) + (i < nslots ? i : max_slots));
+                int4 raw = __ldcs(reinterpret_cast<const int4 *>(table) + i);
                 kb[j] = (int64_t)(((uint64_t)(uint32_t)raw.y << 32) | (uint32_t)raw.x);
                 acc[j] = (int64_t)(((uint64_t)(uint32_t)raw.w << 32) | (uint32_t)raw.z);
-                bool occ = (i < nslots) ? (kb[j] != kEmpty) : (*side_used != 0);
-                if (i == nslots) kb[j] = kEmpty;
-                if (occ) lp[j] = f(hash_of<KeyT>(key_from_bits<KeyT>(kb[j]), aux)) - part_first;
+                if (kb[j] != kEmpty) lp[j] = f(hash_of<KeyT>(key_from_bits<KeyT>(kb[j]), aux)) - part_first;
             }
         }
 #pragma unroll
@@ -268,6 +295,133 @@ k_tbl_compact(const Slot *__restrict__ table, const int64_t *__restrict__ tbl_to
     }
 }
 
+// ===== implementation 1: one thread-block cluster per fine bucket ===============
+// A cluster of 8 CTAs (8 SMs, hardware cluster barrier) takes a bucket and runs its
+// whole life cycle back to back -- init the region, insert the bucket's rows, compact
+// the region into the partition's output range -- so the region is written, probed
+// and read while it sits in L2: HBM sees the rows once (read) and the distinct pairs
+// once (write), plus the write-back of dirty table lines.  ~16 clusters run at once,
+// each on a different bucket (16 x ~5 MB of live tables in the 126 MB L2).
+constexpr int BR_THREADS = 1024;
+constexpr int BR_CLUSTER = 8;
+
+template <typename KeyT, typename ValT, typename AccT>
+__global__ void __cluster_dims__(BR_CLUSTER, 1, 1) __launch_bounds__(BR_THREADS, 1)
+k_bucket_reduce(const KeyT *__restrict__ keys, const int64_t *__restrict__ aux, const ValT *__restrict__ vals,
+                int op, int64_t ident, int32_t sub_bits, int32_t F, int32_t nsrc,
+                const int64_t *__restrict__ seg_start, const int64_t *__restrict__ seg_rows,
+                const int64_t *__restrict__ tbl_off, Slot *__restrict__ table, Slot *__restrict__ side,
+                int32_t *__restrict__ side_used, const int64_t *__restrict__ part_offsets,
+                KeyT *__restrict__ out_keys, int64_t *__restrict__ out_vals,
+                unsigned long long *__restrict__ out_counts, int *__restrict__ bucket_counter) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned crank = cluster.block_rank();
+    __shared__ int s_bucket;
+    __shared__ int s_wsum[BR_THREADS / 32];
+    __shared__ long long s_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t tid_c = (int64_t)crank * BR_THREADS + threadIdx.x;
+    const int64_t nth_c = (int64_t)BR_CLUSTER * BR_THREADS;
+    const int4 fill = slot_fill(ident);
+    for (;;) {
+        if (crank == 0 && threadIdx.x == 0) s_bucket = atomicAdd(bucket_counter, 1);
+        cluster.sync();
+        const int b = *cluster.map_shared_rank(&s_bucket, 0);
+        cluster.sync();  // every CTA has read rank 0's shared memory before anyone may exit or overwrite
+        if (b >= F) break;
+        const int64_t base = tbl_off[b];
+        const uint32_t size = (uint32_t)(tbl_off[b + 1] - base);
+        Slot *region = table + base;
+        // ---- 1. init (full 16 B stores: write-allocate in L2, nothing is fetched from HBM)
+        for (int64_t i = tid_c; i < size; i += nth_c) reinterpret_cast<int4 *>(region)[i] = fill;
+        cluster.sync();
+        // ---- 2. insert the bucket's rows (one segment per source rank)
+        for (int s = 0; s < nsrc; s++) {
+            const int64_t r0 = seg_start[(int64_t)s * F + b];
+            const int64_t rn = seg_rows[(int64_t)s * F + b];
+            for (int64_t i = tid_c; i < rn; i += nth_c) {
+                const int64_t kb = key_bits<KeyT>(keys[r0 + i]);
+                const AccT v = (AccT)vals[r0 + i];
+                Slot *sl;
+                if (kb == kEmpty) {
+                    sl = side;
+                    *side_used = 1;
+                } else {
+                    sl = probe_slot(region, size, kb);
+                }
+                Acc<AccT>::apply(op, &sl->acc, v);
+            }
+        }
+        cluster.sync();
+        // ---- 3. compact the region into the partition's output range
+        const int p = b >> sub_bits;
+        const int64_t pbase = part_offsets[p];
+        constexpr int ITEMS = 4;
+        const int64_t tile = (int64_t)BR_THREADS * ITEMS;
+        for (int64_t t0 = (int64_t)crank * tile; t0 < size; t0 += (int64_t)BR_CLUSTER * tile) {
+            int64_t kb[ITEMS], acc[ITEMS];
+            int c = 0;
+#pragma unroll
+            for (int j = 0; j < ITEMS; j++) {
+                const int64_t i = t0 + (int64_t)threadIdx.x * ITEMS + j;
+                kb[j] = kEmpty;
+                if (i < size) {
+                    int4 raw = __ldcg(reinterpret_cast<const int4 *>(region) + i);
+                    kb[j] = (int64_t)(((uint64_t)(uint32_t)raw.y << 32) | (uint32_t)raw.x);
+                    acc[j] = (int64_t)(((uint64_t)(uint32_t)raw.w << 32) | (uint32_t)raw.z);
+                }
+                c += kb[j] != kEmpty;
+            }
+            // block exclusive scan of c
+            int inc = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += t;
+            }
+            if (lane == 31) s_wsum[warp] = inc;
+            __syncthreads();
+            if (warp == 0) {
+                int w = s_wsum[lane];
+                int winc = w;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    int t = __shfl_up_sync(0xffffffffu, winc, d);
+                    if (lane >= d) winc += t;
+                }
+                s_wsum[lane] = winc - w;  // exclusive
+                if (lane == 31) s_base = winc ? (long long)atomicAdd(&out_counts[p], (unsigned long long)winc) : 0;
+            }
+            __syncthreads();
+            int64_t dst = pbase + s_base + s_wsum[warp] + (inc - c);
+#pragma unroll
+            for (int j = 0; j < ITEMS; j++) {
+                if (kb[j] != kEmpty) {
+                    out_keys[dst] = key_from_bits<KeyT>(kb[j]);
+                    out_vals[dst] = acc[j];
+                    dst++;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// the key whose bits equal the free-slot marker lives in the side slot: append it
+template <typename KeyT>
+__global__ void k_side_flush(const Slot *__restrict__ side, const int32_t *__restrict__ side_used,
+                             const int64_t *__restrict__ aux, PartFn f, int32_t part_first, int32_t nparts,
+                             const int64_t *__restrict__ part_offsets, KeyT *__restrict__ out_keys,
+                             int64_t *__restrict__ out_vals, unsigned long long *__restrict__ out_counts) {
+    if (threadIdx.x != 0 || blockIdx.x != 0 || *side_used == 0) return;
+    const KeyT key = key_from_bits<KeyT>(kEmpty);
+    const int p = f(hash_of<KeyT>(key, aux)) - part_first;
+    if (p < 0 || p >= nparts) return;
+    const int64_t dst = part_offsets[p] + (int64_t)atomicAdd(&out_counts[p], 1ull);
+    out_keys[dst] = key;
+    out_vals[dst] = side->acc;
+}
+
 // host-side upper bound of the slot count for n rows in F buckets
 static inline int64_t max_slots_for(int64_t n, int32_t F) { return n + (n >> 1) + (int64_t)F * 40 + 64; }
 
@@ -279,30 +433,55 @@ static inline int grid_cap(int64_t items, int per_cta, int waves) {
     return (int)g;
 }
 
+int g_reduce_impl = 1;  // dpk_set_option("reduce_impl", 0|1)
+
 struct Ctx {
     const void *keys, *vals;
     const int64_t *aux;
     int64_t n;
     int op;
     PartFn f;
-    int32_t part_first, nparts, F;
-    const int64_t *tbl_off;
+    int32_t part_first, nparts, F, nsrc;
+    const int64_t *seg_rows, *seg_start, *tbl_off, *part_off;
     Slot *table, *side;
     int64_t max_slots;
     int32_t *side_used;
+    int *bucket_counter;
+    void *out_keys;
+    int64_t *out_vals;
+    unsigned long long *out_counts;
     cudaStream_t st;
 };
 
 template <typename KeyT, typename ValT, typename AccT>
 static int dispatch_op(const Ctx &c) {
     if (!Acc<AccT>::supports(c.op)) return fail(DPK_ERR_UNSUPPORTED, "op %d unsupported for this value kind", c.op);
-    DPK_LAUNCH("tbl_init", c.st, k_tbl_init<<<grid_cap(c.max_slots, CB_THREADS, 16), CB_THREADS, 0, c.st>>>(
-        c.table, c.tbl_off + c.F, c.max_slots, Acc<AccT>::identity(c.op)));
-    if (c.n > 0) {
-        DPK_LAUNCH("tbl_insert", c.st, k_tbl_insert<KeyT, ValT, AccT><<<grid_cap(c.n, CB_THREADS, 16), CB_THREADS, 0, c.st>>>(
-            (const KeyT *)c.keys, c.aux, (const ValT *)c.vals, c.n, c.op, c.f, c.part_first << c.f.sub_bits, c.F,
-            c.tbl_off, c.table, c.side, c.side_used));
+    const int64_t ident = Acc<AccT>::identity(c.op);
+    if (g_reduce_impl == 1) {
+        auto kern = k_bucket_reduce<KeyT, ValT, AccT>;
+        int nclusters = sm_count() / BR_CLUSTER;
+        if (nclusters > c.F) nclusters = c.F;
+        if (nclusters < 1) nclusters = 1;
+        DPK_LAUNCH("bucket_reduce", c.st, kern<<<nclusters * BR_CLUSTER, BR_THREADS, 0, c.st>>>(
+            (const KeyT *)c.keys, c.aux, (const ValT *)c.vals, c.op, ident, c.f.sub_bits, c.F, c.nsrc,
+            c.seg_start, c.seg_rows, c.tbl_off, c.table, c.side, c.side_used, c.part_off, (KeyT *)c.out_keys,
+            c.out_vals, c.out_counts, c.bucket_counter));
+    } else {
+        DPK_LAUNCH("tbl_init", c.st, k_tbl_init<<<grid_cap(c.max_slots, CB_THREADS, 16), CB_THREADS, 0, c.st>>>(
+            c.table, c.tbl_off + c.F, ident));
+        if (c.n > 0) {
+            DPK_LAUNCH("tbl_insert", c.st, k_tbl_insert<KeyT, ValT, AccT><<<grid_cap(c.n, CB_THREADS, 16), CB_THREADS, 0, c.st>>>(
+                (const KeyT *)c.keys, c.aux, (const ValT *)c.vals, c.n, c.op, c.f, c.part_first << c.f.sub_bits,
+                c.F, c.tbl_off, c.table, c.side, c.side_used));
+        }
+        size_t sh = (size_t)((c.nparts + 1) & ~1) * 4 + (size_t)c.nparts * 8;
+        DPK_LAUNCH("tbl_compact", c.st, k_tbl_compact<KeyT><<<grid_cap(c.max_slots, CB_THREADS * 4, 8), CB_THREADS, sh, c.st>>>(
+            c.table, c.tbl_off + c.F, c.aux, c.f, c.part_first, c.nparts, c.part_off, (KeyT *)c.out_keys,
+            c.out_vals, c.out_counts));
     }
+    DPK_LAUNCH("side_flush", c.st, k_side_flush<KeyT><<<1, 32, 0, c.st>>>(
+        c.side, c.side_used, c.aux, c.f, c.part_first, c.nparts, c.part_off, (KeyT *)c.out_keys, c.out_vals,
+        c.out_counts));
     return DPK_OK;
 }
 
@@ -318,25 +497,27 @@ static int dispatch_valkind(int val_kind, const Ctx &c) {
 }
 
 template <typename KeyT>
-static int run_combine(Ctx &c, int val_kind, const int64_t *bucket_rows, void *out_keys, void *out_vals,
-                       int64_t *out_offsets, int64_t *out_counts, void *ws) {
-    // workspace: Slot table[max_slots] | Slot side | int32 side_used[4] | int64 tbl_off[F+1]
+static int run_combine(Ctx &c, int val_kind, int64_t *out_offsets, void *ws) {
+    // workspace: Slot table[max_slots] | Slot side | int32 side_used[4] | int64 tbl_off[F+1] | int64 seg_start[nsrc*F]
     c.table = (Slot *)ws;
     c.side = c.table + c.max_slots;
     c.side_used = (int32_t *)(c.side + 1);
+    c.bucket_counter = (int *)(c.side_used + 2);
     int64_t *tbl_off = (int64_t *)(c.side_used + 4);
+    int64_t *seg_start = tbl_off + c.F + 2;
     c.tbl_off = tbl_off;
+    c.seg_start = seg_start;
+    c.part_off = out_offsets;
+    // side slot: free marker + identity are written by the init below; flags cleared here
     DPK_CUDA_TRY(cudaMemsetAsync(c.side_used, 0, 16, c.st));
-    DPK_CUDA_TRY(cudaMemsetAsync(out_counts, 0, (size_t)c.nparts * 8, c.st));
-    DPK_LAUNCH("tbl_plan", c.st, k_tbl_plan<<<1, CB_THREADS, 0, c.st>>>(bucket_rows, c.F, c.f.sub_bits, c.nparts,
-                                                                       tbl_off, out_offsets));
-    int rc = dispatch_valkind<KeyT>(val_kind, c);
-    if (rc) return rc;
-    size_t sh = (size_t)((c.nparts + 1) & ~1) * 4 + (size_t)c.nparts * 8;
-    DPK_LAUNCH("tbl_compact", c.st, k_tbl_compact<KeyT><<<grid_cap(c.max_slots, CB_THREADS * 4, 8), CB_THREADS, sh, c.st>>>(
-        c.table, tbl_off + c.F, c.max_slots, c.side_used, c.aux, c.f, c.part_first, c.nparts, out_offsets,
-        (KeyT *)out_keys, (int64_t *)out_vals, (unsigned long long *)out_counts));
-    return DPK_OK;
+    DPK_CUDA_TRY(cudaMemsetAsync(c.out_counts, 0, (size_t)c.nparts * 8, c.st));
+    DPK_LAUNCH("tbl_plan", c.st, k_tbl_plan<<<1, CB_THREADS, 0, c.st>>>(c.seg_rows, c.nsrc, c.F, c.f.sub_bits, c.nparts,
+                                                                       tbl_off, out_offsets, seg_start));
+    return dispatch_valkind<KeyT>(val_kind, c);
+}
+
+__global__ void k_side_init(Slot *side, int64_t ident) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) { side->key = kEmpty; side->acc = ident; }
 }
 
 }  // namespace dpk
@@ -345,21 +526,33 @@ using namespace dpk;
 
 extern "C" {
 
-int64_t dpk_combine_workspace_bytes(int64_t n, int32_t nbuckets) {
+int dpk_set_option(const char *name, int64_t value) {
+    if (!name) return fail(DPK_ERR_INVALID, "name is NULL");
+    if (strcmp(name, "reduce_impl") == 0) {
+        if (value != 0 && value != 1) return fail(DPK_ERR_INVALID, "reduce_impl must be 0 or 1");
+        g_reduce_impl = (int)value;
+        return DPK_OK;
+    }
+    return fail(DPK_ERR_INVALID, "unknown option %s", name);
+}
+
+int64_t dpk_combine_workspace_bytes(int64_t n, int32_t nbuckets, int32_t nsrc) {
     if (n < 0) n = 0;
     if (nbuckets < 1) nbuckets = 1;
-    return (max_slots_for(n, nbuckets) + 2) * (int64_t)sizeof(Slot) + ((int64_t)nbuckets + 2) * 8 + 64;
+    if (nsrc < 1) nsrc = 1;
+    return (max_slots_for(n, nbuckets) + 2) * (int64_t)sizeof(Slot) +
+           ((int64_t)nbuckets + 4 + (int64_t)nbuckets * nsrc) * 8 + 64;
 }
 
 int dpk_combine(const void *keys, int key_kind, const int64_t *key_aux, const void *vals, int val_kind, int64_t n,
-                int op, int32_t P,
-                const int64_t *thresholds, int32_t nthr, int32_t sub_bits, int32_t part_first, int32_t nparts,
-                const int64_t *bucket_rows, void *out_keys, void *out_vals, int64_t *out_offsets,
-                int64_t *out_counts, void *ws, int64_t ws_bytes, dpk_stream_t stream) {
+                int op, int32_t P, const int64_t *thresholds, int32_t nthr, int32_t sub_bits, int32_t part_first,
+                int32_t nparts, int32_t nsrc, const int64_t *seg_rows, void *out_keys, void *out_vals,
+                int64_t *out_offsets, int64_t *out_counts, void *ws, int64_t ws_bytes, dpk_stream_t stream) {
     if (n < 0 || n >= ((int64_t)1 << 31)) return fail(DPK_ERR_INVALID, "n=%lld out of range [0, 2^31)", (long long)n);
     if (nparts < 1 || part_first < 0 || part_first + nparts > P)
         return fail(DPK_ERR_INVALID, "bad partition range first=%d n=%d P=%d", part_first, nparts, P);
-    if (!bucket_rows || !out_counts || !out_offsets || !ws) return fail(DPK_ERR_INVALID, "NULL pointer");
+    if (nsrc < 1) return fail(DPK_ERR_INVALID, "nsrc must be >= 1");
+    if (!seg_rows || !out_counts || !out_offsets || !ws) return fail(DPK_ERR_INVALID, "NULL pointer");
     if (n > 0 && (!keys || !vals || !out_keys || !out_vals)) return fail(DPK_ERR_INVALID, "NULL pointer");
     Ctx c;
     int rc = make_partfn(P, thresholds, nthr, sub_bits, &c.f);
@@ -367,20 +560,27 @@ int dpk_combine(const void *keys, int key_kind, const int64_t *key_aux, const vo
     c.F = nparts << sub_bits;
     if (c.F > DPK_MAX_PARTITIONS)
         return fail(DPK_ERR_UNSUPPORTED, "%d local buckets exceed %d", c.F, DPK_MAX_PARTITIONS);
-    if (ws_bytes < dpk_combine_workspace_bytes(n, c.F))
-        return fail(DPK_ERR_WORKSPACE, "workspace needs %lld B, got %lld", (long long)dpk_combine_workspace_bytes(n, c.F), (long long)ws_bytes);
+    if (ws_bytes < dpk_combine_workspace_bytes(n, c.F, nsrc))
+        return fail(DPK_ERR_WORKSPACE, "workspace needs %lld B, got %lld", (long long)dpk_combine_workspace_bytes(n, c.F, nsrc), (long long)ws_bytes);
     c.keys = keys; c.vals = vals; c.n = n; c.op = op; c.aux = key_aux;
     if (key_kind == DPK_K_ROWID && n > 0 && !key_aux) return fail(DPK_ERR_INVALID, "DPK_K_ROWID needs key_aux (the per-row hash column)");
-    c.part_first = part_first; c.nparts = nparts;
+    c.part_first = part_first; c.nparts = nparts; c.nsrc = nsrc; c.seg_rows = seg_rows;
     c.max_slots = max_slots_for(n, c.F);
+    c.out_keys = out_keys; c.out_vals = (int64_t *)out_vals; c.out_counts = (unsigned long long *)out_counts;
     c.st = (cudaStream_t)stream;
+    // the side slot must hold {free marker, identity} before any insert
+    {
+        int64_t ident = (val_kind == DPK_V_F64 || val_kind == DPK_V_F32) ? Acc<double>::identity(op) : Acc<int64_t>::identity(op);
+        Slot *side = (Slot *)ws + c.max_slots;
+        DPK_LAUNCH("side_init", c.st, k_side_init<<<1, 32, 0, c.st>>>(side, ident));
+    }
     switch (key_kind) {
-    case DPK_K_I64: return run_combine<int64_t>(c, val_kind, bucket_rows, out_keys, out_vals, out_offsets, out_counts, ws);
-    case DPK_K_I32: return run_combine<int32_t>(c, val_kind, bucket_rows, out_keys, out_vals, out_offsets, out_counts, ws);
-    case DPK_K_F64: return run_combine<double>(c, val_kind, bucket_rows, out_keys, out_vals, out_offsets, out_counts, ws);
-    case DPK_K_U64: return run_combine<uint64_t>(c, val_kind, bucket_rows, out_keys, out_vals, out_offsets, out_counts, ws);
-    case DPK_K_F32: return run_combine<float>(c, val_kind, bucket_rows, out_keys, out_vals, out_offsets, out_counts, ws);
-    case DPK_K_ROWID: return run_combine<RowId>(c, val_kind, bucket_rows, out_keys, out_vals, out_offsets, out_counts, ws);
+    case DPK_K_I64: return run_combine<int64_t>(c, val_kind, out_offsets, ws);
+    case DPK_K_I32: return run_combine<int32_t>(c, val_kind, out_offsets, ws);
+    case DPK_K_F64: return run_combine<double>(c, val_kind, out_offsets, ws);
+    case DPK_K_U64: return run_combine<uint64_t>(c, val_kind, out_offsets, ws);
+    case DPK_K_F32: return run_combine<float>(c, val_kind, out_offsets, ws);
+    case DPK_K_ROWID: return run_combine<RowId>(c, val_kind, out_offsets, ws);
     }
     return fail(DPK_ERR_UNSUPPORTED, "key kind %d is unhashable by portable_hash", key_kind);
 }

@@ -7,6 +7,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <string.h>
 #include <math.h>
 
 #include "dpark_b200.h"
@@ -148,6 +149,8 @@ struct PartFn {
     // bucket id = partition * 2^sub_bits + sub, sub a function of the hash only
     // (equal keys -> equal hash -> same bucket)
     DPK_HD int32_t bucket(int64_t h) const {
+        // mode 4 (radix pass of the group-by sort): digit `shift` of the raw key bits, P = 2^bits
+        if (mode == 4) return (int32_t)(((uint64_t)h >> shift) & (uint64_t)(P - 1));
         int32_t p = (*this)(h);
         if (sub_bits == 0) return p;
         uint64_t m = (uint64_t)h * 0x9E3779B97F4A7C15ull;

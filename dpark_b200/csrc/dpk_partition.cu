@@ -439,4 +439,31 @@ int dpk_partition(const void *keys, int key_kind, const void *vals, int32_t val_
                                  out_keys, out_vals, ws, ws_bytes, stream);
 }
 
+// One stable LSD radix pass over int64 key bits: the same multisplit with the
+// bucket = digit `shift` (bits wide) of the raw key.  groupByKey's reduce side is
+// a stable sort by key built from these passes (dpk_group.cu).
+int dpk_radix_pass(const int64_t *keys, const void *vals, int32_t val_bytes, int64_t n, int32_t shift,
+                   int32_t bits, int64_t *out_keys, void *out_vals, void *ws, int64_t ws_bytes,
+                   dpk_stream_t stream) {
+    if (bits < 1 || bits > 12 || shift < 0 || shift > 63)
+        return fail(DPK_ERR_INVALID, "bad radix digit shift=%d bits=%d", shift, bits);
+    const int32_t F = 1 << bits;
+    int rc = check_common(keys, n, F, 0, ws, ws_bytes);
+    if (rc) return rc;
+    if (n == 0) return DPK_OK;
+    if (!out_keys) return fail(DPK_ERR_INVALID, "NULL pointer");
+    PartFn f;
+    f.P = F; f.mode = 4; f.magic = 0; f.shift = shift; f.nthr = 0; f.thresholds = nullptr; f.sub_bits = 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    int32_t *tile_counts = (int32_t *)ws;
+    int64_t *totals = (int64_t *)((char *)ws + ws_counts_bytes(F));
+    int64_t *offsets = (int64_t *)((char *)totals + align_up((int64_t)F * 8, 256));
+    Plan pl = make_plan(n);
+    rc = dispatch_count(keys, -1, n, pl, f, tile_counts, st);
+    if (rc) return rc;
+    DPK_LAUNCH("part_scan", st, k_part_scan<<<F, PT_THREADS, 0, st>>>(tile_counts, pl.T, totals));
+    DPK_LAUNCH("part_offsets", st, k_part_offsets<<<1, PT_THREADS, 0, st>>>(totals, F, offsets));
+    return dispatch_scatter(keys, -1, vals, val_bytes, n, pl, f, tile_counts, offsets, out_keys, out_vals, st);
+}
+
 }  // extern "C"

@@ -37,10 +37,11 @@ def _device():
 
 def _gather_parent(srdd, numeric_values):
     """Stage-1 input: one Columns (host) or a (keys, vals) tensor pair per parent split."""
+    from .rdd import ColumnarRDD
     parent = srdd.parent
     out = []
     for sp in parent.splits:
-        if hasattr(parent, "columns"):
+        if isinstance(parent, ColumnarRDD):
             out.append(parent.columns(sp))
         else:
             out.append(columnar.ingest_pairs(parent.iterator(sp), repr(parent), numeric_values))

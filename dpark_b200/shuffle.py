@@ -23,9 +23,10 @@ import torch
 
 from . import _native as nv
 
-# rows per fine bucket the reduce side aims for (table region = 1.5 x 16 B x rows
-# ~ 12 MB, a small fraction of the 126 MB L2)
-TARGET_BUCKET_ROWS = 1 << 19
+# rows per fine bucket the reduce side aims for: ~16 thread-block clusters work on
+# 16 buckets at once, each with a table region of 1.5 x 16 B x rows (~5 MB at
+# 2^17.6 rows), so the live tables take ~80 MB of the 126 MB L2
+TARGET_BUCKET_ROWS = 200_000
 
 
 def owner_blocks(P, G):
@@ -136,8 +137,8 @@ def reduce_side(rx, op, P, thresholds=None):
     if rx.nparts == 0:
         z = torch.zeros(1, dtype=torch.int64, device=dev)
         return rx.keys[:0], (rx.vals[:0] if rx.vals is not None else None), z, z[:0]
-    bucket_rows = rx.seg.sum(0).contiguous()                        # rows per local fine bucket
-    return nv.combine(rx.keys, rx.vals, op, P, bucket_rows, rx.part_first, rx.nparts, thresholds, rx.sub_bits)
+    return nv.combine(rx.keys, rx.vals, op, P, rx.seg.contiguous(), rx.part_first, rx.nparts, thresholds,
+                      rx.sub_bits)
 
 
 class HostShuffle(object):

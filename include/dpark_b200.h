@@ -117,10 +117,12 @@ int dpk_partition(const void *keys, int key_kind, const void *vals, int32_t val_
 
 /* ---- a9: reduce side, DiskHashMerger._merge (dpark/shuffle.py:600-608) ----
  * combined[k] = op(combined[k], v) over the n rows fetched for the nparts reduce
- * partitions [part_first, part_first + nparts) this GPU owns (any row order;
- * bucket-major order keeps the tables L2-resident).  bucket_rows[nparts <<
- * sub_bits] (device int64) = rows per local fine bucket, summed over sources:
- * it sizes one table region per bucket.  Outputs: out_offsets[nparts+1] = start
+ * partitions [part_first, part_first + nparts) this GPU owns.  Row layout = what
+ * the exchange delivers: source-rank-major, and bucket-major inside each source
+ * (nsrc = 1 is a plain bucket-major buffer).  seg_rows[nsrc][nparts << sub_bits]
+ * (device int64, row-major) = rows of local fine bucket b that came from source
+ * s; it locates every segment and sizes one table region per bucket.
+ * Outputs: out_offsets[nparts+1] = start
  * of each partition's output range (= row offsets of the partitions),
  * out_counts[nparts] = distinct keys per partition; partition j's result is
  * out_keys/out_vals[out_offsets[j] .. out_offsets[j] + out_counts[j]).  Order
@@ -129,12 +131,15 @@ int dpk_partition(const void *keys, int key_kind, const void *vals, int32_t val_
  * reference's big ints); F64/F32 values -> float64 (the reference adds Python
  * floats); out_vals is 8 bytes per row.  out_keys/out_vals hold n entries.
  */
-int64_t dpk_combine_workspace_bytes(int64_t n, int32_t nbuckets);
+int64_t dpk_combine_workspace_bytes(int64_t n, int32_t nbuckets, int32_t nsrc);
 int dpk_combine(const void *keys, int key_kind, const int64_t *key_aux, const void *vals,
-                int val_kind, int64_t n, int op, int32_t P, const int64_t *thresholds, int32_t nthr, int32_t sub_bits,
-                int32_t part_first, int32_t nparts, const int64_t *bucket_rows, void *out_keys,
-                void *out_vals, int64_t *out_offsets, int64_t *out_counts, void *ws,
-                int64_t ws_bytes, dpk_stream_t stream);
+                int val_kind, int64_t n, int op, int32_t P, const int64_t *thresholds, int32_t nthr,
+                int32_t sub_bits, int32_t part_first, int32_t nparts, int32_t nsrc,
+                const int64_t *seg_rows, void *out_keys, void *out_vals, int64_t *out_offsets,
+                int64_t *out_counts, void *ws, int64_t ws_bytes, dpk_stream_t stream);
+/* options: "reduce_impl" = 1 (default: one thread-block cluster per fine bucket,
+ * table life cycle L2-resident) or 0 (three grid-wide passes; kept for A/B runs) */
+int dpk_set_option(const char *name, int64_t value);
 
 /* ---- variable-length keys (str / bytes): key identity on the device ---------
  * The reference's dicts compare keys by value; two different strings may share

@@ -1,0 +1,119 @@
+"""The reference's operator surface on the GPU shuffle, checked against the golden
+vectors captured from the real reference (tests/golden/make_golden.py) and the
+reference's own shuffle tests (tests/test_rdd.py:246-272).  -m gpu."""
+import json
+import os
+import sys
+
+import pytest
+
+from tests.golden_util import dec, load
+
+pytestmark = pytest.mark.gpu
+
+SC = load("shuffle_cases.json")
+FUNCS = {"add": lambda x, y: x + y, "min": lambda x, y: min(x, y), "max": lambda x, y: max(x, y),
+         "mul": lambda x, y: x * y, "or": lambda x, y: x | y, "and": lambda x, y: x & y,
+         "xor": lambda x, y: x ^ y}
+
+
+def ctx():
+    sys.argv = [sys.argv[0]]
+    from dpark_b200 import DparkContext
+    return DparkContext("local")
+
+
+def _canon(parts):
+    from tests.golden.make_golden import enc
+    return [sorted(([enc(k), enc(v)] for k, v in part), key=json.dumps) for part in parts]
+
+
+REDUCE_CASES = [c for c in SC["cases"] if c["op"] == "reduceByKey" and c["name"] != "mul_small"]
+
+
+@pytest.mark.parametrize("case", REDUCE_CASES, ids=[c["name"] for c in REDUCE_CASES])
+def test_reduce_by_key_matches_reference_per_partition(case):
+    """Per-partition multisets equal the reference's glom() output: same keys in
+    the same partitions, same combined values (ints bit-exact; float sums within
+    1e-9 relative -- the reference's own merge order is nondeterministic)."""
+    from dpark_b200 import Aggregator, HashPartitioner
+    dc = ctx()
+    rows = [(dec(k), dec(v)) for k, v in case["rows"]]
+    rdd = dc.parallelize(rows, case["M"])
+    f = FUNCS[case["func"]]
+    if case["thresholds"] is None:
+        got = rdd.reduceByKey(f, case["P"]).glom().collect()
+    else:
+        got = rdd.combineByKey(Aggregator(lambda x: x, f, f),
+                               HashPartitioner(case["P"], thresholds=case["thresholds"])).glom().collect()
+    isfloat_sum = rows and isinstance(rows[0][1], float) and case["func"] == "add"
+    if not isfloat_sum:
+        assert _canon(got) == case["parts"]
+    else:
+        assert len(got) == len(case["parts"])
+        for gp, wp in zip(got, case["parts"]):
+            want = {json.dumps(k): dec(v) for k, v in wp}
+            from tests.golden.make_golden import enc
+            assert len(gp) == len(want)
+            for k, v in gp:
+                w = want[json.dumps(enc(k))]
+                assert abs(v - w) <= 1e-9 * max(1.0, abs(w))
+
+
+def test_reference_test_basic_reduce():
+    """tests/test_rdd.py:246-257 of the reference."""
+    dc = ctx()
+    d = list(zip([1, 2, 3, 3], list(range(4, 8))))
+    nums = dc.makeRDD(d, 2)
+    assert nums.reduceByKey(lambda x, y: x + y).collectAsMap() == {1: 4, 2: 5, 3: 13}
+    assert nums.reduceByKeyToDriver(lambda x, y: x + y) == {1: 4, 2: 5, 3: 13}
+    assert nums.reduceByKey(lambda x, y: x + y).lookup(3) == 13
+
+
+def test_wc_pipeline_writes_the_files_the_reference_writes(tmp_path):
+    """examples/wc.py shape: textFile -> flatMap -> reduceByKey(+, 6) -> map ->
+    saveAsTextFile.  The golden fixture holds the reference's output files for
+    the same input; file names (= partition ids of str keys) and line sets must match."""
+    dc = ctx()
+    wc = SC["wc"]
+    inp = tmp_path / "in.txt"
+    inp.write_text("\n".join(wc["lines"]) + "\n", encoding="utf-8")
+    out = tmp_path / "out"
+
+    def fm(x):
+        for w in x.strip().split():
+            yield (w, 1)
+
+    (dc.textFile(str(inp)).flatMap(fm).reduceByKey(lambda x, y: x + y, numSplits=6)
+       .map(lambda x: " ".join(list(map(str, x)))).saveAsTextFile(str(out), overwrite=False))
+    got = {fn: sorted(open(os.path.join(str(out), fn), encoding="utf-8").read().splitlines())
+           for fn in sorted(os.listdir(str(out)))}
+    assert got == wc["files"]
+
+
+def test_columnar_rdd_reduce_large():
+    import numpy as np
+    from oracle import oracle as orc
+    dc = ctx()
+    rng = np.random.default_rng(5)
+    n, P = 3_000_000, 8
+    k = rng.integers(0, 2 ** 20, n, dtype=np.int64)
+    v = rng.integers(0, 2 ** 16, n, dtype=np.int64)
+    sh = dc.parallelizeColumns(k, v, 8).reduceByKey(lambda a, b: a + b, P)
+    want = orc.reduce_by_key(np.array_split(k, 8), np.array_split(v, 8), P, "sum")
+    for p in range(P):
+        gk, gv = sh.columns(sh.splits[p])
+        gk, gv = np.array(gk), np.array(gv)
+        o1, o2 = np.argsort(gk), np.argsort(want[p][0])
+        assert np.array_equal(gk[o1], want[p][0][o2]) and np.array_equal(gv[o1], want[p][1][o2])
+
+
+def test_unsupported_things_fail_loudly():
+    dc = ctx()
+    with pytest.raises(NotImplementedError):
+        dc.parallelize([(1, 1)], 1).reduceByKey(lambda x, y: x - y)
+    from dpark_b200 import DparkUserFatalError
+    with pytest.raises(DparkUserFatalError):
+        dc.parallelize([(1, 1), 5], 1).reduceByKey(lambda x, y: x + y).collect()
+    with pytest.raises(TypeError):
+        dc.parallelize([(True, 1)], 1).reduceByKey(lambda x, y: x + y).collect()

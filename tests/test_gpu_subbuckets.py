@@ -90,7 +90,7 @@ def test_reduce_with_thresholds_and_sub_buckets():
 def test_choose_sub_bits_bounds():
     from dpark_b200 import shuffle
     assert shuffle.choose_sub_bits(1000, 8) == 0
-    assert shuffle.choose_sub_bits(10 ** 8, 8) == 5
+    assert shuffle.choose_sub_bits(10 ** 8, 8) == 6
     for n in (10 ** 6, 10 ** 8, 10 ** 9, 4 * 10 ** 9):
         for P in (1, 4, 8, 64, 1000, 4096):
             sb = shuffle.choose_sub_bits(n, P)
