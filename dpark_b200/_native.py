@@ -32,6 +32,7 @@ EXPORTS = [
     "dpk_partition_scatter", "dpk_partition", "dpk_combine_workspace_bytes", "dpk_combine",
     "dpk_launch_count", "dpk_prof_enable", "dpk_prof_count", "dpk_prof_get",
     "dpk_dict_encode_workspace_bytes", "dpk_dict_encode", "dpk_set_option",
+    "dpk_key_or", "dpk_radix_pass", "dpk_group_heads_workspace_bytes", "dpk_group_heads", "dpk_gather_i64",
 ]
 
 _lib = None
@@ -61,13 +62,19 @@ def lib():
         L.dpk_hash_bytes.argtypes = [vp, vp, i64, ci, vp, vp]
         L.dpk_partition_ids.argtypes = [vp, i64, i32, vp, i32, vp, vp]
         L.dpk_partition_workspace_bytes.argtypes = [i64, i32]
-        L.dpk_partition_count.argtypes = [vp, ci, i64, i32, vp, i32, i32, vp, vp, i64, vp]
-        L.dpk_partition_scatter.argtypes = [vp, ci, vp, i32, i64, i32, vp, i32, i32, vp, vp, vp, vp, i64, vp]
-        L.dpk_partition.argtypes = [vp, ci, vp, i32, i64, i32, vp, i32, i32, vp, vp, vp, vp, i64, vp]
+        L.dpk_partition_count.argtypes = [vp, ci, vp, i64, i32, vp, i32, i32, vp, vp, i64, vp]
+        L.dpk_partition_scatter.argtypes = [vp, ci, vp, vp, i32, i64, i32, vp, i32, i32, vp, vp, vp, vp, i64, vp]
+        L.dpk_partition.argtypes = [vp, ci, vp, vp, i32, i64, i32, vp, i32, i32, vp, vp, vp, vp, i64, vp]
         L.dpk_combine_workspace_bytes.argtypes = [i64, i32, i32]
         L.dpk_combine.argtypes = [vp, ci, vp, vp, ci, i64, ci, i32, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp,
                                   vp, vp, i64, vp]
         L.dpk_set_option.argtypes = [C.c_char_p, i64]
+        L.dpk_key_or.argtypes = [vp, i64, vp, vp]
+        L.dpk_gather_i64.argtypes = [vp, vp, i64, vp, vp]
+        L.dpk_radix_pass.argtypes = [vp, vp, i32, i64, i32, i32, vp, vp, vp, i64, vp]
+        L.dpk_group_heads_workspace_bytes.restype = i64
+        L.dpk_group_heads_workspace_bytes.argtypes = [i64]
+        L.dpk_group_heads.argtypes = [vp, i64, vp, vp, vp, vp, i64, vp]
         L.dpk_dict_encode_workspace_bytes.restype = i64
         L.dpk_dict_encode_workspace_bytes.argtypes = [i64]
         L.dpk_dict_encode.argtypes = [vp, vp, vp, i64, vp, vp, i64, vp]
@@ -172,33 +179,39 @@ def partition_workspace(nbuckets, device):
     return torch.empty(nbytes, dtype=torch.uint8, device=device)
 
 
-def partition_count(keys, P, thresholds=None, prehashed=False, sub_bits=0, ws=None):
+def _kk(keys, prehashed, row_hash):
+    return K_ROWID if row_hash is not None else key_kind(keys, prehashed)
+
+
+def partition_count(keys, P, thresholds=None, prehashed=False, sub_bits=0, ws=None, row_hash=None):
     """Rows per bucket of one chunk; returns (counts[P << sub_bits] int64 device, ws)."""
-    _need_cuda(keys)
+    _need_cuda(keys, row_hash)
     F = P << sub_bits
     thr, nthr = _thr(thresholds, keys.device)
     if ws is None:
         ws = partition_workspace(F, keys.device)
     counts = torch.empty(F, dtype=torch.int64, device=keys.device)
-    _check(lib().dpk_partition_count(_ptr(keys), key_kind(keys, prehashed), keys.numel(), P, _ptr(thr), nthr,
+    _check(lib().dpk_partition_count(_ptr(keys), _kk(keys, prehashed, row_hash), _ptr(row_hash), keys.numel(), P,
+                                     _ptr(thr), nthr,
                                      sub_bits, _ptr(counts), _ptr(ws), ws.numel(), _stream()))
     return counts, ws
 
 
 def partition_scatter(keys, vals, P, bucket_base, out_keys, out_vals, ws, thresholds=None, prehashed=False,
-                      sub_bits=0):
-    _need_cuda(keys, vals, bucket_base, out_keys, out_vals, ws)
+                      sub_bits=0, row_hash=None):
+    _need_cuda(keys, vals, bucket_base, out_keys, out_vals, ws, row_hash)
     thr, nthr = _thr(thresholds, keys.device)
     vb = 0 if vals is None else vals.element_size()
-    _check(lib().dpk_partition_scatter(_ptr(keys), key_kind(keys, prehashed), _ptr(vals), vb, keys.numel(), P,
+    _check(lib().dpk_partition_scatter(_ptr(keys), _kk(keys, prehashed, row_hash), _ptr(row_hash), _ptr(vals), vb,
+                                       keys.numel(), P,
                                        _ptr(thr), nthr, sub_bits, _ptr(bucket_base), _ptr(out_keys),
                                        _ptr(out_vals), _ptr(ws), ws.numel(), _stream()))
 
 
-def partition(keys, vals, P, thresholds=None, prehashed=False, sub_bits=0):
+def partition(keys, vals, P, thresholds=None, prehashed=False, sub_bits=0, row_hash=None):
     """Stable hash-partition of one chunk (ShuffleMapTask._run, dpark/task.py:209-226).
     Returns (out_keys, out_vals, offsets[(P << sub_bits) + 1] int64 device)."""
-    _need_cuda(keys, vals)
+    _need_cuda(keys, vals, row_hash)
     if vals is not None and vals.numel() != keys.numel():
         from .errors import DparkUserFatalError
         raise DparkUserFatalError("ragged pair columns: %d keys, %d values" % (keys.numel(), vals.numel()))
@@ -209,7 +222,8 @@ def partition(keys, vals, P, thresholds=None, prehashed=False, sub_bits=0):
     out_vals = None if vals is None else torch.empty_like(vals)
     offsets = torch.empty(F + 1, dtype=torch.int64, device=keys.device)
     vb = 0 if vals is None else vals.element_size()
-    _check(lib().dpk_partition(_ptr(keys), key_kind(keys, prehashed), _ptr(vals), vb, keys.numel(), P,
+    _check(lib().dpk_partition(_ptr(keys), _kk(keys, prehashed, row_hash), _ptr(row_hash), _ptr(vals), vb,
+                               keys.numel(), P,
                                _ptr(thr), nthr, sub_bits, _ptr(out_keys), _ptr(out_vals), _ptr(offsets),
                                _ptr(ws), ws.numel(), _stream()))
     return out_keys, out_vals, offsets
@@ -269,6 +283,54 @@ def dict_encode(data, offsets, hashes):
     _check(lib().dpk_dict_encode(_ptr(data), _ptr(offsets), _ptr(hashes), n, _ptr(rep), _ptr(ws), ws_bytes,
                                  _stream()))
     return rep
+
+
+# ---- a10: groupByKey reduce side ---------------------------------------------------
+def key_or(keys):
+    """Device uint64 (as int64 tensor[1]): OR over i of keys[i] ^ keys[0]."""
+    _need_cuda(keys)
+    out = torch.empty(1, dtype=torch.int64, device=keys.device)
+    _check(lib().dpk_key_or(_ptr(keys), keys.numel(), _ptr(out), _stream()))
+    return out
+
+
+def gather_i64(src, idx):
+    _need_cuda(src, idx)
+    out = torch.empty(idx.numel(), dtype=torch.int64, device=idx.device)
+    _check(lib().dpk_gather_i64(_ptr(src), _ptr(idx), idx.numel(), _ptr(out), _stream()))
+    return out
+
+
+def radix_pass(keys, vals, shift, bits, out_keys=None, out_vals=None, ws=None):
+    """One stable LSD radix pass over int64 key bits (the multisplit with digit buckets)."""
+    _need_cuda(keys, vals)
+    if keys.dtype != torch.int64:
+        raise TypeError("radix_pass sorts int64 key bits")
+    if out_keys is None:
+        out_keys = torch.empty_like(keys)
+    if out_vals is None and vals is not None:
+        out_vals = torch.empty_like(vals)
+    if ws is None:
+        ws = partition_workspace(1 << bits, keys.device)
+    vb = 0 if vals is None else vals.element_size()
+    _check(lib().dpk_radix_pass(_ptr(keys), _ptr(vals), vb, keys.numel(), shift, bits, _ptr(out_keys),
+                                _ptr(out_vals), _ptr(ws), ws.numel(), _stream()))
+    return out_keys, out_vals
+
+
+def group_heads(sorted_keys):
+    """CSR heads of a key-sorted column: (group_keys[n], starts[n+1], ngroups[1]) device tensors;
+    only the first ngroups (+1) entries are meaningful."""
+    _need_cuda(sorted_keys)
+    n = sorted_keys.numel()
+    ws_bytes = lib().dpk_group_heads_workspace_bytes(n)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=sorted_keys.device)
+    out_keys = torch.empty(n, dtype=torch.int64, device=sorted_keys.device)
+    out_starts = torch.empty(n + 1, dtype=torch.int64, device=sorted_keys.device)
+    ng = torch.empty(1, dtype=torch.int64, device=sorted_keys.device)
+    _check(lib().dpk_group_heads(_ptr(sorted_keys), n, _ptr(out_keys), _ptr(out_starts), _ptr(ng), _ptr(ws),
+                                 ws_bytes, _stream()))
+    return out_keys, out_starts, ng
 
 
 def set_option(name, value):

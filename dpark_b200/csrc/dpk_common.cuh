@@ -144,6 +144,8 @@ struct PartFn {
     // of its sub-buckets).  Sub-buckets bound the reduce-side table working set so
     // it stays resident in the 126 MB L2.
     int32_t sub_bits;
+    // DPK_K_ROWID keys: per-row portable_hash column the multisplit looks the hash up in
+    const int64_t *row_hash;
 
     DPK_HD int32_t nbuckets() const { return P << sub_bits; }
     // bucket id = partition * 2^sub_bits + sub, sub a function of the hash only

@@ -61,6 +61,7 @@ int make_partfn(int32_t P, const int64_t *thresholds, int32_t nthr, int32_t sub_
         return fail(DPK_ERR_UNSUPPORTED, "P=%d with sub_bits=%d exceeds %d buckets", P, sub_bits, DPK_MAX_PARTITIONS);
     PartFn f;
     f.P = P; f.magic = 0; f.shift = 0; f.nthr = 0; f.thresholds = nullptr; f.sub_bits = sub_bits;
+    f.row_hash = nullptr;
     if (thresholds != nullptr) {
         if (nthr != P - 1) return fail(DPK_ERR_INVALID, "thresholds need P-1=%d entries, got %d", P - 1, nthr);
         f.mode = 3; f.nthr = nthr; f.thresholds = thresholds;

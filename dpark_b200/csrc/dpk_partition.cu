@@ -53,9 +53,13 @@ static int64_t ws_total_bytes(int32_t P) {
     return ws_counts_bytes(P) + align_up((int64_t)P * 8, 256) + align_up((int64_t)(P + 1) * 8, 256);
 }
 
-template <typename KeyT, bool PRE>
-__device__ __forceinline__ int64_t key_hash(KeyT k) {
-    if constexpr (PRE) return (int64_t)k;
+// PRE: 0 = portable_hash of the key column, 1 = the int64 key IS the hash
+// (prehashed / radix digits), 2 = the key is a row id and its hash is looked up
+// in f.row_hash (DPK_K_ROWID, variable-length keys)
+template <typename KeyT, int PRE>
+__device__ __forceinline__ int64_t key_hash(KeyT k, const PartFn &f) {
+    if constexpr (PRE == 1) return (int64_t)k;
+    else if constexpr (PRE == 2) return __ldg(&f.row_hash[(int64_t)k]);
     else return KeyHash<KeyT>::of(k);
 }
 
@@ -84,7 +88,7 @@ __device__ __forceinline__ int block_excl_scan(int v, int *s_warp, int *total) {
 }
 
 // ------------------------------------------------------------------ count
-template <typename KeyT, bool PRE>
+template <typename KeyT, int PRE>
 __global__ void __launch_bounds__(PT_THREADS)
 k_part_count(const KeyT *__restrict__ keys, int64_t n, int64_t L, PartFn f,
              int32_t *__restrict__ tile_counts, int32_t T) {
@@ -107,7 +111,7 @@ k_part_count(const KeyT *__restrict__ keys, int64_t n, int64_t L, PartFn f,
         }
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            int pid = ok[u] ? f.bucket(key_hash<KeyT, PRE>(k[u])) : -1;
+            int pid = ok[u] ? f.bucket(key_hash<KeyT, PRE>(k[u], f)) : -1;
             unsigned m = __match_any_sync(0xffffffffu, pid);
             if (ok[u] && lane == __ffs(m) - 1) atomicAdd(&s_cnt[pid], __popc(m));
         }
@@ -174,7 +178,7 @@ static ScatterSmem scatter_smem(int kb, int vb, int32_t P) {
     return s;
 }
 
-template <typename KeyT, typename ValT, bool PRE>
+template <typename KeyT, typename ValT, int PRE>
 __global__ void __launch_bounds__(PT_THREADS, 2)
 k_part_scatter(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, int64_t n, int64_t L,
                PartFn f, const int32_t *__restrict__ tile_off, int32_t T,
@@ -230,7 +234,7 @@ k_part_scatter(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, int
 #pragma unroll
         for (int j = 0; j < PT_ITEMS; j++) {
             const bool ok = (wbase + j * 32) < end;
-            const int p = ok ? f.bucket(key_hash<KeyT, PRE>(k[j])) : P;  // P = "no row"
+            const int p = ok ? f.bucket(key_hash<KeyT, PRE>(k[j], f)) : P;  // P = "no row"
             const unsigned m = __match_any_sync(0xffffffffu, p);
             int base = 0;
             if (ok) base = wh[p];
@@ -295,7 +299,7 @@ k_part_scatter(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, int
 }
 
 // ------------------------------------------------------------ host dispatch
-template <typename KeyT, bool PRE>
+template <typename KeyT, int PRE>
 static int launch_count(const void *keys, int64_t n, const Plan &pl, const PartFn &f,
                         int32_t *tile_counts, cudaStream_t st) {
     size_t sh = (size_t)f.nbuckets() * sizeof(int32_t);
@@ -312,11 +316,14 @@ static int dispatch_count(const void *keys, int key_kind, int64_t n, const Plan 
     case DPK_K_F64: return launch_count<double, false>(keys, n, pl, f, tile_counts, st);
     case DPK_K_U64: return launch_count<uint64_t, false>(keys, n, pl, f, tile_counts, st);
     case DPK_K_F32: return launch_count<float, false>(keys, n, pl, f, tile_counts, st);
+    case DPK_K_ROWID:
+        if (!f.row_hash) return fail(DPK_ERR_INVALID, "DPK_K_ROWID needs key_aux (the per-row hash column)");
+        return launch_count<int64_t, 2>(keys, n, pl, f, tile_counts, st);
     }
     return fail(DPK_ERR_UNSUPPORTED, "key kind %d is unhashable by portable_hash", key_kind);
 }
 
-template <typename KeyT, typename ValT, bool PRE>
+template <typename KeyT, typename ValT, int PRE>
 static int launch_scatter(const void *keys, const void *vals, int64_t n, const Plan &pl, const PartFn &f,
                           const int32_t *tile_off, const int64_t *bucket_base, void *out_keys,
                           void *out_vals, cudaStream_t st) {
@@ -333,7 +340,7 @@ static int launch_scatter(const void *keys, const void *vals, int64_t n, const P
     return DPK_OK;
 }
 
-template <typename KeyT, bool PRE>
+template <typename KeyT, int PRE>
 static int dispatch_val(const void *keys, const void *vals, int32_t val_bytes, int64_t n, const Plan &pl,
                         const PartFn &f, const int32_t *tile_off, const int64_t *bucket_base,
                         void *out_keys, void *out_vals, cudaStream_t st) {
@@ -358,6 +365,9 @@ static int dispatch_scatter(const void *keys, int key_kind, const void *vals, in
     case DPK_K_F64: return dispatch_val<double, false>(keys, vals, val_bytes, n, pl, f, tile_off, bucket_base, out_keys, out_vals, st);
     case DPK_K_U64: return dispatch_val<uint64_t, false>(keys, vals, val_bytes, n, pl, f, tile_off, bucket_base, out_keys, out_vals, st);
     case DPK_K_F32: return dispatch_val<float, false>(keys, vals, val_bytes, n, pl, f, tile_off, bucket_base, out_keys, out_vals, st);
+    case DPK_K_ROWID:
+        if (!f.row_hash) return fail(DPK_ERR_INVALID, "DPK_K_ROWID needs key_aux (the per-row hash column)");
+        return dispatch_val<int64_t, 2>(keys, vals, val_bytes, n, pl, f, tile_off, bucket_base, out_keys, out_vals, st);
     }
     return fail(DPK_ERR_UNSUPPORTED, "key kind %d is unhashable by portable_hash", key_kind);
 }
@@ -384,15 +394,16 @@ int64_t dpk_partition_workspace_bytes(int64_t n, int32_t nbuckets) {
     return ws_total_bytes(nbuckets);
 }
 
-int dpk_partition_count(const void *keys, int key_kind, int64_t n, int32_t P, const int64_t *thresholds,
-                        int32_t nthr, int32_t sub_bits, int64_t *out_counts, void *ws, int64_t ws_bytes,
-                        dpk_stream_t stream) {
+int dpk_partition_count(const void *keys, int key_kind, const int64_t *key_aux, int64_t n, int32_t P,
+                        const int64_t *thresholds, int32_t nthr, int32_t sub_bits, int64_t *out_counts,
+                        void *ws, int64_t ws_bytes, dpk_stream_t stream) {
     int rc = check_common(keys, n, P, sub_bits, ws, ws_bytes);
     if (rc) return rc;
     if (!out_counts) return fail(DPK_ERR_INVALID, "out_counts is NULL");
     PartFn f;
     rc = make_partfn(P, thresholds, nthr, sub_bits, &f);
     if (rc) return rc;
+    f.row_hash = key_aux;
     const int32_t F = f.nbuckets();
     cudaStream_t st = (cudaStream_t)stream;
     int32_t *tile_counts = (int32_t *)ws;
@@ -407,8 +418,9 @@ int dpk_partition_count(const void *keys, int key_kind, int64_t n, int32_t P, co
     return DPK_OK;
 }
 
-int dpk_partition_scatter(const void *keys, int key_kind, const void *vals, int32_t val_bytes, int64_t n,
-                          int32_t P, const int64_t *thresholds, int32_t nthr, int32_t sub_bits,
+int dpk_partition_scatter(const void *keys, int key_kind, const int64_t *key_aux, const void *vals,
+                          int32_t val_bytes, int64_t n, int32_t P, const int64_t *thresholds, int32_t nthr,
+                          int32_t sub_bits,
                           const int64_t *bucket_base, void *out_keys, void *out_vals, void *ws,
                           int64_t ws_bytes, dpk_stream_t stream) {
     int rc = check_common(keys, n, P, sub_bits, ws, ws_bytes);
@@ -418,24 +430,25 @@ int dpk_partition_scatter(const void *keys, int key_kind, const void *vals, int3
     PartFn f;
     rc = make_partfn(P, thresholds, nthr, sub_bits, &f);
     if (rc) return rc;
+    f.row_hash = key_aux;
     Plan pl = make_plan(n);
     return dispatch_scatter(keys, key_kind, vals, val_bytes, n, pl, f, (const int32_t *)ws, bucket_base,
                             out_keys, out_vals, (cudaStream_t)stream);
 }
 
-int dpk_partition(const void *keys, int key_kind, const void *vals, int32_t val_bytes, int64_t n, int32_t P,
-                  const int64_t *thresholds, int32_t nthr, int32_t sub_bits, void *out_keys, void *out_vals,
+int dpk_partition(const void *keys, int key_kind, const int64_t *key_aux, const void *vals, int32_t val_bytes,
+                  int64_t n, int32_t P, const int64_t *thresholds, int32_t nthr, int32_t sub_bits, void *out_keys, void *out_vals,
                   int64_t *out_offsets, void *ws, int64_t ws_bytes, dpk_stream_t stream) {
     int rc = check_common(keys, n, P, sub_bits, ws, ws_bytes);
     if (rc) return rc;
     if (!out_offsets) return fail(DPK_ERR_INVALID, "out_offsets is NULL");
     const int32_t F = P << sub_bits;
     int64_t *totals = (int64_t *)((char *)ws + ws_counts_bytes(F));
-    rc = dpk_partition_count(keys, key_kind, n, P, thresholds, nthr, sub_bits, totals, ws, ws_bytes, stream);
+    rc = dpk_partition_count(keys, key_kind, key_aux, n, P, thresholds, nthr, sub_bits, totals, ws, ws_bytes, stream);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     DPK_LAUNCH("part_offsets", st, k_part_offsets<<<1, PT_THREADS, 0, st>>>(totals, F, out_offsets));
-    return dpk_partition_scatter(keys, key_kind, vals, val_bytes, n, P, thresholds, nthr, sub_bits, out_offsets,
+    return dpk_partition_scatter(keys, key_kind, key_aux, vals, val_bytes, n, P, thresholds, nthr, sub_bits, out_offsets,
                                  out_keys, out_vals, ws, ws_bytes, stream);
 }
 
@@ -454,6 +467,7 @@ int dpk_radix_pass(const int64_t *keys, const void *vals, int32_t val_bytes, int
     if (!out_keys) return fail(DPK_ERR_INVALID, "NULL pointer");
     PartFn f;
     f.P = F; f.mode = 4; f.magic = 0; f.shift = shift; f.nthr = 0; f.thresholds = nullptr; f.sub_bits = 0;
+    f.row_hash = nullptr;
     cudaStream_t st = (cudaStream_t)stream;
     int32_t *tile_counts = (int32_t *)ws;
     int64_t *totals = (int64_t *)((char *)ws + ws_counts_bytes(F));

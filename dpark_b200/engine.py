@@ -41,7 +41,7 @@ def _gather_parent(srdd, numeric_values):
     parent = srdd.parent
     out = []
     for sp in parent.splits:
-        if isinstance(parent, ColumnarRDD):
+        if isinstance(parent, ColumnarRDD) and numeric_values:
             out.append(parent.columns(sp))
         else:
             out.append(columnar.ingest_pairs(parent.iterator(sp), repr(parent), numeric_values))

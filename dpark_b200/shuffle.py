@@ -55,7 +55,7 @@ class MapOutput(object):
         self.keys, self.vals, self.offsets, self.P, self.sub_bits = keys, vals, offsets, P, sub_bits
 
 
-def map_side(key_chunks, val_chunks, P, thresholds=None, prehashed=False, sub_bits=0):
+def map_side(key_chunks, val_chunks, P, thresholds=None, prehashed=False, sub_bits=0, row_hash=None):
     """Hash-partition all local map splits into ONE bucket-major buffer.
 
     key_chunks/val_chunks: lists of CUDA tensors (the rank's map splits in map_id
@@ -63,12 +63,12 @@ def map_side(key_chunks, val_chunks, P, thresholds=None, prehashed=False, sub_bi
     OrderedGroupByDiskHashMerger produces (dpark/shuffle.py:626-646)."""
     F = P << sub_bits
     if len(key_chunks) == 1:
-        k, v, off = nv.partition(key_chunks[0], val_chunks[0], P, thresholds, prehashed, sub_bits)
+        k, v, off = nv.partition(key_chunks[0], val_chunks[0], P, thresholds, prehashed, sub_bits, row_hash)
         return MapOutput(k, v, off, P, sub_bits)
     dev = key_chunks[0].device
     counts, wss = [], []
     for k in key_chunks:
-        c, ws = nv.partition_count(k, P, thresholds, prehashed, sub_bits)
+        c, ws = nv.partition_count(k, P, thresholds, prehashed, sub_bits, None, row_hash)
         counts.append(c)
         wss.append(ws)
     cm = torch.stack(counts)                       # [M, F]
@@ -82,7 +82,8 @@ def map_side(key_chunks, val_chunks, P, thresholds=None, prehashed=False, sub_bi
     has_v = val_chunks[0] is not None
     out_v = torch.empty(n, dtype=val_chunks[0].dtype, device=dev) if has_v else None
     for m, (k, v) in enumerate(zip(key_chunks, val_chunks)):
-        nv.partition_scatter(k, v, P, base[m].contiguous(), out_k, out_v, wss[m], thresholds, prehashed, sub_bits)
+        nv.partition_scatter(k, v, P, base[m].contiguous(), out_k, out_v, wss[m], thresholds, prehashed, sub_bits,
+                             row_hash)
     return MapOutput(out_k, out_v, offsets, P, sub_bits)
 
 
@@ -139,6 +140,55 @@ def reduce_side(rx, op, P, thresholds=None):
         return rx.keys[:0], (rx.vals[:0] if rx.vals is not None else None), z, z[:0]
     return nv.combine(rx.keys, rx.vals, op, P, rx.seg.contiguous(), rx.part_first, rx.nparts, thresholds,
                       rx.sub_bits)
+
+
+RADIX_BITS = 8
+
+
+def sort_by_key_bits(keys, vals, bits=None):
+    """Stable LSD radix sort of (int64 key bits, 8-byte payload) with the multisplit
+    passes; digit windows in which all keys agree are skipped."""
+    bits = bits or RADIX_BITS
+    n = int(keys.numel())
+    if n <= 1:
+        return keys, vals
+    ormask = int(nv.key_or(keys).item()) & 0xFFFFFFFFFFFFFFFF      # tiny host read: which digits differ
+    ws = nv.partition_workspace(1 << bits, keys.device)
+    src_k, src_v = keys, vals
+    dst_k, dst_v = torch.empty_like(keys), (None if vals is None else torch.empty_like(vals))
+    spare_k = spare_v = None
+    shift = 0
+    while shift < 64:
+        width = min(bits, 64 - shift)
+        if (ormask >> shift) & ((1 << width) - 1):
+            nv.radix_pass(src_k, src_v, shift, width, dst_k, dst_v, ws)
+            if src_k is keys:      # never write into the caller's buffers
+                spare_k, spare_v = torch.empty_like(keys), (None if vals is None else torch.empty_like(vals))
+                src_k, src_v, dst_k, dst_v = dst_k, dst_v, spare_k, spare_v
+            else:
+                src_k, src_v, dst_k, dst_v = dst_k, dst_v, src_k, src_v
+        shift += width
+    return src_k, src_v
+
+
+def group_side(rx, P, thresholds=None, key_view=None, row_hash=None):
+    """Reduce side of groupByKey (OrderedGroupByDiskHashMerger,
+    dpark/shuffle.py:626-646): stable sort of the received rows by key, then
+    partition-major, then CSR.  rx.keys: int64 key bits (for float keys pass
+    key_view=torch.float64 so that the partition step hashes them as floats; for
+    row-id keys pass row_hash so that the partition step uses the looked-up hash).
+    Returns (group_keys, group_starts, ngroups, values, part_offsets[P+1]); group g
+    holds values[group_starts[g] : group_starts[g+1]], groups are partition-major."""
+    k, v = sort_by_key_bits(rx.keys, rx.vals)
+    if row_hash is not None:
+        # keys are representative row ids: partition by the hash of the key they stand for,
+        # carrying the id as payload next to the value is not possible in a (k, v) pair, so
+        # partition (hash, value) and re-derive the ids afterwards from the values (row ids)
+        raise NotImplementedError("row-id keys are handled by dpark_b200.grouping")
+    pk = k if key_view is None else k.view(key_view)
+    ok, ov, off = nv.partition(pk, v, P, thresholds)
+    gk, gs, ng = nv.group_heads(ok.view(torch.int64))
+    return gk, gs, ng, ov, off
 
 
 class HostShuffle(object):

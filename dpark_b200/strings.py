@@ -22,7 +22,7 @@ import numpy as np
 import torch
 
 from . import _native as nv
-from . import columnar
+from . import columnar, shuffle
 
 
 def _concat(splits):
@@ -56,8 +56,12 @@ def reduce_by_key_bytes(splits, key_kind, P, thresholds, op, dev, res):
     d_vals = torch.from_numpy(vals).to(dev)
     h = nv.hash_bytes(d_data, d_off, mode)
     rep = nv.dict_encode(d_data, d_off, h)
-    bucket_rows, _ = nv.partition_count(h, P, thresholds, prehashed=True)
-    ok, ov, off, cnt = nv.combine(rep, d_vals, op, P, bucket_rows, 0, P, thresholds, 0, row_hash=h)
+    # map side: bucket-major by the hash of the string each id stands for; reduce side: merge per id
+    sb = shuffle.choose_sub_bits(n, P)
+    mo = shuffle.map_side([rep], [d_vals], P, thresholds, False, sb, row_hash=h)
+    rx = shuffle.exchange(mo)
+    ok, ov, off, cnt = nv.combine(rx.keys, rx.vals, op, P, rx.seg.contiguous(), rx.part_first, rx.nparts,
+                                  thresholds, sb, row_hash=h)
     off_h, cnt_h = off.cpu().tolist(), cnt.cpu().tolist()
     ok_h, ov_h = ok.cpu().numpy(), ov.cpu().numpy()
     raw = data.tobytes()

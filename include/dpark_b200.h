@@ -42,7 +42,7 @@ enum {
 /* key column kinds.  The hash of each follows dpark/portable_hash.pyx:51-70:
  * ints and floats -> Python's builtin hash(); see dpk_hash_keys. */
 enum { DPK_K_I64 = 0, DPK_K_I32 = 1, DPK_K_F64 = 2, DPK_K_U64 = 3, DPK_K_F32 = 4,
-       DPK_K_ROWID = 5 /* dpk_combine only: int64 ids of representative rows, hash looked up in key_aux */ };
+       DPK_K_ROWID = 5 /* int64 ids of representative rows; their hash is looked up in key_aux */ };
 /* value column kinds */
 enum { DPK_V_I64 = 0, DPK_V_F64 = 1, DPK_V_I32 = 2, DPK_V_F32 = 3 };
 /* combiner ops a reduceByKey(func) lowers to (dpark/rdd.py:543-545 builds
@@ -85,8 +85,10 @@ int dpk_partition_ids(const int64_t *hash, int64_t n, int32_t P, const int64_t *
  * L2-resident.  F <= DPK_MAX_PARTITIONS.
  *
  * key_kind = DPK_K_* hashes the key column with portable_hash; key_kind = -1
- * ("prehashed") takes the int64 keys AS the hash (variable-length keys: hash
- * them with dpk_hash_bytes first and carry the row id as the value).
+ * ("prehashed") takes the int64 keys AS the hash; key_kind = DPK_K_ROWID takes
+ * int64 row ids (representatives of variable-length keys, dpk_dict_encode) and
+ * looks their hash up in key_aux (the column dpk_hash_bytes produced).  key_aux
+ * is NULL for every other kind.
  *
  *   ws = dpk_partition_workspace_bytes(n, F)
  *   dpk_partition_count  : out_counts[F] (int64) = rows per bucket of this chunk;
@@ -103,16 +105,17 @@ int dpk_partition_ids(const int64_t *hash, int64_t n, int32_t P, const int64_t *
  */
 #define DPK_MAX_PARTITIONS 4096
 int64_t dpk_partition_workspace_bytes(int64_t n, int32_t nbuckets);
-int dpk_partition_count(const void *keys, int key_kind, int64_t n, int32_t P,
+int dpk_partition_count(const void *keys, int key_kind, const int64_t *key_aux, int64_t n, int32_t P,
                         const int64_t *thresholds, int32_t nthr, int32_t sub_bits,
                         int64_t *out_counts, void *ws, int64_t ws_bytes, dpk_stream_t stream);
-int dpk_partition_scatter(const void *keys, int key_kind, const void *vals, int32_t val_bytes,
-                          int64_t n, int32_t P, const int64_t *thresholds, int32_t nthr,
-                          int32_t sub_bits, const int64_t *bucket_base, void *out_keys,
-                          void *out_vals, void *ws, int64_t ws_bytes, dpk_stream_t stream);
-int dpk_partition(const void *keys, int key_kind, const void *vals, int32_t val_bytes, int64_t n,
-                  int32_t P, const int64_t *thresholds, int32_t nthr, int32_t sub_bits,
-                  void *out_keys, void *out_vals, int64_t *out_offsets, void *ws,
+int dpk_partition_scatter(const void *keys, int key_kind, const int64_t *key_aux, const void *vals,
+                          int32_t val_bytes, int64_t n, int32_t P, const int64_t *thresholds,
+                          int32_t nthr, int32_t sub_bits, const int64_t *bucket_base,
+                          void *out_keys, void *out_vals, void *ws, int64_t ws_bytes,
+                          dpk_stream_t stream);
+int dpk_partition(const void *keys, int key_kind, const int64_t *key_aux, const void *vals,
+                  int32_t val_bytes, int64_t n, int32_t P, const int64_t *thresholds, int32_t nthr,
+                  int32_t sub_bits, void *out_keys, void *out_vals, int64_t *out_offsets, void *ws,
                   int64_t ws_bytes, dpk_stream_t stream);
 
 /* ---- a9: reduce side, DiskHashMerger._merge (dpark/shuffle.py:600-608) ----
@@ -140,6 +143,30 @@ int dpk_combine(const void *keys, int key_kind, const int64_t *key_aux, const vo
 /* options: "reduce_impl" = 1 (default: one thread-block cluster per fine bucket,
  * table life cycle L2-resident) or 0 (three grid-wide passes; kept for A/B runs) */
 int dpk_set_option(const char *name, int64_t value);
+
+/* ---- a10: reduce side of groupByKey (dpark/dependency.py:107-118 merged by
+ * OrderedGroupByDiskHashMerger, dpark/shuffle.py:626-646): per key the list of
+ * its values ordered by (map_id, arrival).  On the device: a STABLE sort of the
+ * received rows by key -- LSD radix, each pass the stable multisplit of a4 with
+ * bucket = one digit of the raw int64 key bits -- then CSR extraction.
+ *   dpk_key_or      : *out_or (device uint64) = OR_i(keys[i] ^ keys[0]); digits where
+ *                     it is zero need no pass.
+ *   dpk_radix_pass  : one pass, digit = (key >> shift) & (2^bits - 1), bits <= 12;
+ *                     ws = dpk_partition_workspace_bytes(n, 1 << bits).
+ *   dpk_group_heads : over keys sorted so that equal keys are adjacent: out_keys[g],
+ *                     out_starts[g] = first row of group g, out_starts[G] = n,
+ *                     *out_ngroups = G (device int64).  out_starts holds n+1 entries.
+ */
+int dpk_key_or(const int64_t *keys, int64_t n, uint64_t *out_or, dpk_stream_t stream);
+/* out[i] = src[idx[i]] (row-id keys: fetch the hash / representative of a moved row) */
+int dpk_gather_i64(const int64_t *src, const int64_t *idx, int64_t n, int64_t *out,
+                   dpk_stream_t stream);
+int dpk_radix_pass(const int64_t *keys, const void *vals, int32_t val_bytes, int64_t n, int32_t shift,
+                   int32_t bits, int64_t *out_keys, void *out_vals, void *ws, int64_t ws_bytes,
+                   dpk_stream_t stream);
+int64_t dpk_group_heads_workspace_bytes(int64_t n);
+int dpk_group_heads(const int64_t *sorted_keys, int64_t n, int64_t *out_keys, int64_t *out_starts,
+                    int64_t *out_ngroups, void *ws, int64_t ws_bytes, dpk_stream_t stream);
 
 /* ---- variable-length keys (str / bytes): key identity on the device ---------
  * The reference's dicts compare keys by value; two different strings may share

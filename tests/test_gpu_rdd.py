@@ -60,6 +60,60 @@ def test_reduce_by_key_matches_reference_per_partition(case):
                 assert abs(v - w) <= 1e-9 * max(1.0, abs(w))
 
 
+GROUP_CASES = [c for c in SC["cases"] if c["op"] == "groupByKey"]
+
+
+@pytest.mark.parametrize("case", GROUP_CASES, ids=[c["name"] for c in GROUP_CASES])
+def test_group_by_key_matches_reference_ordered_group(case):
+    """Per partition: same keys, and for every key the SAME LIST (order included)
+    as the reference run with ordered_group=True."""
+    dc = ctx()
+    rows = [(dec(k), dec(v)) for k, v in case["rows"]]
+    got = dc.parallelize(rows, case["M"]).groupByKey(case["P"]).glom().collect()
+    assert _canon([[(k, list(v)) for k, v in part] for part in got]) == case["parts"]
+
+
+def test_reference_test_basic_group_and_lookup():
+    """tests/test_rdd.py:246-272 of the reference (groupByKey / lookup / partitionByKey)."""
+    dc = ctx()
+    d = list(zip([1, 2, 3, 3], list(range(4, 8))))
+    nums = dc.makeRDD(d, 2)
+    assert nums.groupByKey().mapValue(list).collectAsMap() == {1: [4], 2: [5], 3: [6, 7]}
+    assert nums.groupByKey().mapValue(list).lookup(3) == [6, 7]
+    assert nums.partitionByKey().lookup(2) == 5
+    assert nums.partitionByKey().lookup(4) is None
+    assert nums.flatMapValue(lambda x: list(range(x))).count() == 22
+
+
+def test_radix_sort_is_a_stable_sort_of_key_bits():
+    import numpy as np
+    import torch
+    from dpark_b200 import shuffle
+    rng = np.random.default_rng(9)
+    for n, lo, hi in ((1, 0, 10), (1000, -50, 50), (300000, 0, 2 ** 31), (300000, -2 ** 63, 2 ** 63 - 1),
+                      (200000, 7, 8)):
+        k = rng.integers(lo, hi, n, dtype=np.int64)
+        v = np.arange(n, dtype=np.int64)
+        sk, sv = shuffle.sort_by_key_bits(torch.from_numpy(k).cuda(), torch.from_numpy(v).cuda())
+        order = np.argsort(k.view(np.uint64), kind="stable")          # bit order == unsigned order
+        assert np.array_equal(sk.cpu().numpy(), k[order])
+        assert np.array_equal(sv.cpu().numpy(), v[order])
+
+
+def test_group_heads_csr():
+    import numpy as np
+    import torch
+    from dpark_b200 import _native as nv
+    rng = np.random.default_rng(10)
+    k = np.sort(rng.integers(0, 5000, 100003, dtype=np.int64))
+    gk, gs, ng = nv.group_heads(torch.from_numpy(k).cuda())
+    G = int(ng.item())
+    uk, first = np.unique(k, return_index=True)
+    assert G == len(uk)
+    assert np.array_equal(gk[:G].cpu().numpy(), uk)
+    assert np.array_equal(gs[:G + 1].cpu().numpy(), np.concatenate([first, [len(k)]]))
+
+
 def test_reference_test_basic_reduce():
     """tests/test_rdd.py:246-257 of the reference."""
     dc = ctx()
