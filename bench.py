@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-sample-rows", type=int, default=4_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--reduce-impl", type=int, default=1, help="A/B switch of the reduce-side kernel (dpk_set_option)")
+    ap.add_argument("--reduce-impl", type=int, default=2, help="A/B switch of the reduce-side kernel (dpk_set_option)")
     ap.add_argument("--sub-bits", type=int, default=-1, help="override the sub-bucket bits (default: auto)")
     return ap.parse_args()
 
@@ -259,9 +259,18 @@ def run_ours(args):
     sub_bits = shuffle.choose_sub_bits(n * world, P) if args.sub_bits < 0 else args.sub_bits
     nv.set_option("reduce_impl", args.reduce_impl)
 
+    ex_events = []
+
     def step():
         mo = shuffle.map_side(kc, vc, P, None, False, sub_bits)
-        rx = shuffle.exchange(mo)
+        if world > 1:      # bracket the one collective (alltoallv) for the NVLink roofline
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            rx = shuffle.exchange(mo)
+            b.record()
+            ex_events.append((a, b))
+        else:
+            rx = shuffle.exchange(mo)
         return shuffle.reduce_side(rx, "sum", P)
 
     def barrier():
@@ -288,12 +297,24 @@ def run_ours(args):
     nv.prof_enable(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    del ex_events[:]
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
     barrier()
     nv.prof_enable(False)
+    roofline_exchange = None
+    if world > 1 and ex_events:
+        ex_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in ex_events) / len(ex_events)],
+                             dtype=torch.float64, device=dev)
+        dist.all_reduce(ex_ms, op=dist.ReduceOp.MAX)
+        sent = (KEY_BYTES + VAL_BYTES) * n * (world - 1) / world       # bytes each GPU sends per step
+        gbs = sent / (float(ex_ms) * 1e-3) / 1e9
+        roofline_exchange = {"bound": "nvlink", "kernel": "alltoallv (counts all-gather + 2 x all_to_all_single)",
+                             "achieved": gbs, "peak": 770.0, "unit": "GB/s per GPU per direction",
+                             "frac": gbs / 770.0, "ms_per_step": float(ex_ms),
+                             "peak_source": "measured peer copy on this pool (B200_PROFILING.md); nominal 900"}
     launches = nv.launch_count() - launches0
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -318,6 +339,9 @@ def run_ours(args):
         "tbl_insert": kv * nrecv,                     # read every received pair once
         "tbl_compact": kv * int(tot[2]) // world,     # write one pair per distinct key
         "bucket_reduce": kv * (nrecv + int(tot[2]) // world),   # fused init+insert+compact per bucket
+        "seg_count": KEY_BYTES * nrecv,               # second-level split: histogram re-read (not credited)
+        "seg_scatter": 2 * kv * nrecv,                # second-level split: read + write every received pair
+        "smem_aggregate": kv * (nrecv + int(tot[2]) // world),  # read every pair once, write one per distinct key
     }
     kernels = []
     ktotal = sum(a[0] for a in agg.values()) or 1.0
@@ -337,7 +361,8 @@ def run_ours(args):
                 "traffic": None, "peak_source": peak_src,
                 "alg_bytes_per_launch": dom_bytes_launch, "ms_per_launch": dom_launch_ms,
                 "share_of_step": dom_ms / ktotal}
-    red_names = ("tbl_plan", "side_init", "side_flush", "tbl_init", "tbl_insert", "tbl_compact", "bucket_reduce")
+    red_names = ("tbl_plan", "side_init", "side_flush", "tbl_init", "tbl_insert", "tbl_compact", "bucket_reduce",
+                 "seg_plan", "seg_count", "seg_scan", "seg_scatter", "smem_aggregate")
     red_ms = sum(agg.get(k, [0.0, 0])[0] for k in red_names) / args.steps
     if red_ms > 0:
         red_bytes = alg["tbl_insert"] + alg["tbl_compact"]
@@ -386,7 +411,8 @@ def run_ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
             "config": workload_config(args, world), "gpu_launches": launches, "e2e": e2e,
-            "roofline": roofline, "roofline_reduce": roofline_reduce, "kernels": kernels,
+            "roofline": roofline, "roofline_reduce": roofline_reduce, "roofline_exchange": roofline_exchange,
+            "kernels": kernels,
             "cpu_baseline": cpu_baseline, "clocks": clk,
             "distinct_keys": int(tot[2]),
         }

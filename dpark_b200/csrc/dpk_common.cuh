@@ -153,12 +153,18 @@ struct PartFn {
     DPK_HD int32_t bucket(int64_t h) const {
         // mode 4 (radix pass of the group-by sort): digit `shift` of the raw key bits, P = 2^bits
         if (mode == 4) return (int32_t)(((uint64_t)h >> shift) & (uint64_t)(P - 1));
+        // mode 5 (second-level split on the reduce side): the P = 2^k bits of the same mixed
+        // hash that follow the first-level sub-bucket bits (shift = 64 - sub_bits_1 - k)
+        if (mode == 5) return P == 1 ? 0 : (int32_t)((mixed(h) >> shift) & (uint64_t)(P - 1));
         int32_t p = (*this)(h);
         if (sub_bits == 0) return p;
+        return (p << sub_bits) | (int32_t)(mixed(h) >> (64 - sub_bits));
+    }
+    static DPK_HD uint64_t mixed(int64_t h) {
         uint64_t m = (uint64_t)h * 0x9E3779B97F4A7C15ull;
         m ^= m >> 29;
         m *= 0xBF58476D1CE4E5B9ull;
-        return (p << sub_bits) | (int32_t)(m >> (64 - sub_bits));
+        return m;
     }
 
     DPK_HD int32_t operator()(int64_t h) const {
@@ -188,6 +194,16 @@ struct PartFn {
 };
 // host: build the functor (thresholds is a device pointer, only stored)
 int make_partfn(int32_t P, const int64_t *thresholds, int32_t nthr, int32_t sub_bits, PartFn *out);
+
+// Segmented multisplit (dpk_partition.cu), used by the reduce side: every first-level
+// bucket b (rows in nsrc segments seg_start/seg_rows[s][b] of the input) is split into
+// fine.nbuckets() fine buckets; output rows are bucket-major then fine-bucket-major and
+// fine_off[F1 * S2 + 1] delimits the fine buckets.  keys/vals: device; st-ordered.
+int64_t seg_multisplit_ws_bytes(int64_t n, int32_t F1, int32_t S2, int32_t nsrc);
+int seg_multisplit(const void *keys, int key_kind, const void *vals, int32_t val_bytes, int64_t n,
+                   const PartFn &fine, int32_t F1, int32_t nsrc, const int64_t *seg_start,
+                   const int64_t *seg_rows, void *out_keys, void *out_vals, int64_t *fine_off, void *ws,
+                   int64_t ws_bytes, cudaStream_t st);
 
 // murmur3 fmix64 -- slot hash for the reduce-side tables (not part of the
 // reference semantics; only spreads keys over table slots)

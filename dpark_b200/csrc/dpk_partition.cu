@@ -27,13 +27,27 @@ constexpr int PT_TILE = PT_THREADS * PT_ITEMS;  // 4096 rows per tile
 
 struct NoVal {};
 
+// Segmented mode (second-level split on the reduce side): the grid runs over a
+// device-resident chunk table instead of equal row ranges; every chunk lies inside
+// one first-level bucket and is split by OTHER hash bits into f.nbuckets() fine
+// buckets.  Counts / offsets are chunk-major [chunk][bucket].  All pointers null =
+// plain mode.
+struct SegTab {
+    const int64_t *cbeg, *cend;     // row range of chunk c
+    const int32_t *ctotal;          // number of chunks (device)
+    int32_t *chunk_counts;          // [chunk][F]   (count kernel writes)
+    const int64_t *chunk_off;       // [chunk][F]   absolute output position (scatter kernel reads)
+};
+
 struct Plan {
-    int32_t T;  // CTAs (row ranges)
+    int32_t T;  // CTAs (row ranges, or the chunk-table upper bound in segmented mode)
     int64_t L;  // rows per CTA, multiple of PT_TILE
+    SegTab seg;
 };
 
 static Plan make_plan(int64_t n) {
     Plan pl;
+    pl.seg = SegTab{nullptr, nullptr, nullptr, nullptr, nullptr};
     int64_t tiles = (n + PT_TILE - 1) / PT_TILE;
     if (tiles < 1) tiles = 1;
     int64_t maxT = (int64_t)sm_count() * 4;
@@ -91,13 +105,14 @@ __device__ __forceinline__ int block_excl_scan(int v, int *s_warp, int *total) {
 template <typename KeyT, int PRE>
 __global__ void __launch_bounds__(PT_THREADS)
 k_part_count(const KeyT *__restrict__ keys, int64_t n, int64_t L, PartFn f,
-             int32_t *__restrict__ tile_counts, int32_t T) {
+             int32_t *__restrict__ tile_counts, int32_t T, SegTab seg) {
     extern __shared__ int32_t s_cnt[];  // [buckets]
     const int P = f.nbuckets();
+    if (seg.cbeg != nullptr && (int)blockIdx.x >= *seg.ctotal) return;
     for (int p = threadIdx.x; p < P; p += PT_THREADS) s_cnt[p] = 0;
     __syncthreads();
-    const int64_t beg = (int64_t)blockIdx.x * L;
-    const int64_t end = min(n, beg + L);
+    const int64_t beg = seg.cbeg ? seg.cbeg[blockIdx.x] : (int64_t)blockIdx.x * L;
+    const int64_t end = seg.cbeg ? seg.cend[blockIdx.x] : min(n, beg + L);
     const int lane = threadIdx.x & 31;
     constexpr int U = 4;
     for (int64_t i0 = beg; i0 < end; i0 += (int64_t)PT_THREADS * U) {
@@ -117,8 +132,11 @@ k_part_count(const KeyT *__restrict__ keys, int64_t n, int64_t L, PartFn f,
         }
     }
     __syncthreads();
-    for (int p = threadIdx.x; p < P; p += PT_THREADS)
-        tile_counts[(int64_t)p * T + blockIdx.x] = s_cnt[p];
+    if (seg.cbeg) {
+        for (int p = threadIdx.x; p < P; p += PT_THREADS) seg.chunk_counts[(int64_t)blockIdx.x * P + p] = s_cnt[p];
+    } else {
+        for (int p = threadIdx.x; p < P; p += PT_THREADS) tile_counts[(int64_t)p * T + blockIdx.x] = s_cnt[p];
+    }
 }
 
 // one CTA per bucket: exclusive scan of its T per-CTA counts, total -> totals[p]
@@ -183,7 +201,7 @@ __global__ void __launch_bounds__(PT_THREADS, 2)
 k_part_scatter(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, int64_t n, int64_t L,
                PartFn f, const int32_t *__restrict__ tile_off, int32_t T,
                const int64_t *__restrict__ bucket_base, KeyT *__restrict__ out_keys,
-               ValT *__restrict__ out_vals, ScatterSmem lay) {
+               ValT *__restrict__ out_vals, ScatterSmem lay, SegTab seg) {
     constexpr bool HAS_VAL = !std::is_same<ValT, NoVal>::value;
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_warp[PT_WARPS];
@@ -198,11 +216,16 @@ k_part_scatter(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, int
     const int P = f.nbuckets();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
-    const int64_t beg = (int64_t)blockIdx.x * L;
-    const int64_t end = min(n, beg + L);
+    if (seg.cbeg != nullptr && (int)blockIdx.x >= *seg.ctotal) return;
+    const int64_t beg = seg.cbeg ? seg.cbeg[blockIdx.x] : (int64_t)blockIdx.x * L;
+    const int64_t end = seg.cbeg ? seg.cend[blockIdx.x] : min(n, beg + L);
 
-    for (int p = threadIdx.x; p < P; p += PT_THREADS)
-        s_gpos[p] = bucket_base[p] + (int64_t)tile_off[(int64_t)p * T + blockIdx.x];
+    if (seg.cbeg) {
+        for (int p = threadIdx.x; p < P; p += PT_THREADS) s_gpos[p] = seg.chunk_off[(int64_t)blockIdx.x * P + p];
+    } else {
+        for (int p = threadIdx.x; p < P; p += PT_THREADS)
+            s_gpos[p] = bucket_base[p] + (int64_t)tile_off[(int64_t)p * T + blockIdx.x];
+    }
 
     const int E = (P + PT_THREADS - 1) / PT_THREADS;  // buckets per thread in the scan
 
@@ -303,7 +326,7 @@ template <typename KeyT, int PRE>
 static int launch_count(const void *keys, int64_t n, const Plan &pl, const PartFn &f,
                         int32_t *tile_counts, cudaStream_t st) {
     size_t sh = (size_t)f.nbuckets() * sizeof(int32_t);
-    DPK_LAUNCH("part_count", st, k_part_count<KeyT, PRE><<<pl.T, PT_THREADS, sh, st>>>((const KeyT *)keys, n, pl.L, f, tile_counts, pl.T));
+    DPK_LAUNCH(pl.seg.cbeg ? "seg_count" : "part_count", st, k_part_count<KeyT, PRE><<<pl.T, PT_THREADS, sh, st>>>((const KeyT *)keys, n, pl.L, f, tile_counts, pl.T, pl.seg));
     return DPK_OK;
 }
 
@@ -333,10 +356,10 @@ static int launch_scatter(const void *keys, const void *vals, int64_t n, const P
     if (lay.total > 227 * 1024)
         return fail(DPK_ERR_UNSUPPORTED, "%d buckets need %lld B of shared memory", f.nbuckets(), (long long)lay.total);
     DPK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
-    DPK_LAUNCH("part_scatter", st,
+    DPK_LAUNCH(pl.seg.cbeg ? "seg_scatter" : "part_scatter", st,
                kern<<<pl.T, PT_THREADS, (size_t)lay.total, st>>>((const KeyT *)keys, (const ValT *)vals, n, pl.L, f,
                                                                 tile_off, pl.T, bucket_base, (KeyT *)out_keys,
-                                                                (ValT *)out_vals, lay));
+                                                                (ValT *)out_vals, lay, pl.seg));
     return DPK_OK;
 }
 
@@ -380,6 +403,126 @@ static int check_common(const void *keys, int64_t n, int32_t P, int32_t sub_bits
     if (n > 0 && !keys) return fail(DPK_ERR_INVALID, "keys is NULL");
     if (!ws || ws_bytes < ws_total_bytes(P)) return fail(DPK_ERR_WORKSPACE, "workspace needs %lld B, got %lld", (long long)ws_total_bytes(P), (long long)ws_bytes);
     return DPK_OK;
+}
+
+// ---------------------------------------------------- segmented multisplit
+constexpr int SEG_CHUNK_TILES = 4;
+constexpr int64_t SEG_CHUNK = (int64_t)SEG_CHUNK_TILES * PT_TILE;  // rows per chunk
+
+static inline int64_t seg_max_chunks(int64_t n, int32_t F1, int32_t nsrc) {
+    return n / SEG_CHUNK + (int64_t)F1 * nsrc + 1;
+}
+
+// single CTA: chunk table + bucket-major row offsets from the segment matrix
+__global__ void __launch_bounds__(PT_THREADS)
+k_seg_plan(const int64_t *__restrict__ seg_start, const int64_t *__restrict__ seg_rows, int32_t nsrc, int32_t F1,
+           int64_t *__restrict__ brow_off, int64_t *__restrict__ cfirst, int64_t *__restrict__ cbeg,
+           int64_t *__restrict__ cend, int32_t *__restrict__ ctotal) {
+    __shared__ long long s_rows[PT_THREADS], s_chunks[PT_THREADS];
+    const int E = (F1 + PT_THREADS - 1) / PT_THREADS;
+    const int b0 = threadIdx.x * E, b1 = min(b0 + E, F1);
+    long long rows = 0, chunks = 0;
+    for (int b = b0; b < b1; b++)
+        for (int s = 0; s < nsrc; s++) {
+            long long r = seg_rows[(int64_t)s * F1 + b];
+            rows += r;
+            chunks += (r + SEG_CHUNK - 1) / SEG_CHUNK;
+        }
+    s_rows[threadIdx.x] = rows;
+    s_chunks[threadIdx.x] = chunks;
+    __syncthreads();
+    long long rbase = 0, cbase = 0;
+    for (int t = 0; t < (int)threadIdx.x; t++) { rbase += s_rows[t]; cbase += s_chunks[t]; }
+    for (int b = b0; b < b1; b++) {
+        brow_off[b] = rbase;
+        cfirst[b] = cbase;
+        for (int s = 0; s < nsrc; s++) {
+            const long long r0 = seg_start[(int64_t)s * F1 + b], r = seg_rows[(int64_t)s * F1 + b];
+            for (long long o = 0; o < r; o += SEG_CHUNK) {
+                cbeg[cbase] = r0 + o;
+                cend[cbase] = r0 + min(r, o + SEG_CHUNK);
+                cbase++;
+            }
+            rbase += r;
+        }
+    }
+    if (b0 < F1 && b1 == F1) { brow_off[F1] = rbase; cfirst[F1] = cbase; *ctotal = (int32_t)cbase; }
+    if (F1 == 0 && threadIdx.x == 0) { brow_off[0] = 0; cfirst[0] = 0; *ctotal = 0; }
+}
+
+// one CTA per first-level bucket: fine-bucket offsets and per-chunk output positions
+__global__ void __launch_bounds__(PT_THREADS)
+k_seg_scan(const int32_t *__restrict__ chunk_counts, const int64_t *__restrict__ cfirst,
+           const int64_t *__restrict__ brow_off, int32_t F1, int32_t S2, int64_t *__restrict__ chunk_off,
+           int64_t *__restrict__ fine_off) {
+    extern __shared__ int32_t s_tot[];  // [S2] totals, then exclusive bases
+    __shared__ int s_warp[PT_WARPS];
+    const int b = blockIdx.x;
+    const int64_t c0 = cfirst[b], c1 = cfirst[b + 1];
+    for (int p = threadIdx.x; p < S2; p += PT_THREADS) {
+        int t = 0;
+        for (int64_t c = c0; c < c1; c++) t += chunk_counts[c * S2 + p];
+        s_tot[p] = t;
+    }
+    __syncthreads();
+    const int E = (S2 + PT_THREADS - 1) / PT_THREADS;
+    const int p0 = threadIdx.x * E, p1 = min(p0 + E, S2);
+    int sum = 0;
+    for (int p = p0; p < p1; p++) sum += s_tot[p];
+    int tot;
+    int run = block_excl_scan(sum, s_warp, &tot);
+    for (int p = p0; p < p1; p++) {
+        int t = s_tot[p];
+        s_tot[p] = run;
+        run += t;
+    }
+    __syncthreads();
+    const int64_t base = brow_off[b];
+    for (int p = threadIdx.x; p < S2; p += PT_THREADS) {
+        int64_t pos = base + s_tot[p];
+        fine_off[(int64_t)b * S2 + p] = pos;
+        for (int64_t c = c0; c < c1; c++) {
+            chunk_off[c * S2 + p] = pos;
+            pos += chunk_counts[c * S2 + p];
+        }
+    }
+    if (b == F1 - 1 && threadIdx.x == 0) fine_off[(int64_t)F1 * S2] = brow_off[F1];
+}
+
+int64_t seg_multisplit_ws_bytes(int64_t n, int32_t F1, int32_t S2, int32_t nsrc) {
+    const int64_t maxc = seg_max_chunks(n, F1, nsrc);
+    return align_up((int64_t)(F1 + 1) * 8, 256) * 2 + 256 + align_up(maxc * 8, 256) * 2 +
+           align_up(maxc * S2 * 4, 256) + align_up(maxc * S2 * 8, 256);
+}
+
+int seg_multisplit(const void *keys, int key_kind, const void *vals, int32_t val_bytes, int64_t n,
+                   const PartFn &fine, int32_t F1, int32_t nsrc, const int64_t *seg_start,
+                   const int64_t *seg_rows, void *out_keys, void *out_vals, int64_t *fine_off, void *ws,
+                   int64_t ws_bytes, cudaStream_t st) {
+    const int32_t S2 = fine.nbuckets();
+    if (ws_bytes < seg_multisplit_ws_bytes(n, F1, S2, nsrc)) return fail(DPK_ERR_WORKSPACE, "segmented multisplit workspace too small");
+    const int64_t maxc = seg_max_chunks(n, F1, nsrc);
+    char *w = (char *)ws;
+    int64_t *brow_off = (int64_t *)w; w += align_up((int64_t)(F1 + 1) * 8, 256);
+    int64_t *cfirst = (int64_t *)w; w += align_up((int64_t)(F1 + 1) * 8, 256);
+    int32_t *ctotal = (int32_t *)w; w += 256;
+    int64_t *cbeg = (int64_t *)w; w += align_up(maxc * 8, 256);
+    int64_t *cend = (int64_t *)w; w += align_up(maxc * 8, 256);
+    int32_t *chunk_counts = (int32_t *)w; w += align_up(maxc * S2 * 4, 256);
+    int64_t *chunk_off = (int64_t *)w;
+    DPK_LAUNCH("seg_plan", st, k_seg_plan<<<1, PT_THREADS, 0, st>>>(seg_start, seg_rows, nsrc, F1, brow_off, cfirst, cbeg, cend, ctotal));
+    Plan pl;
+    pl.T = (int32_t)maxc;
+    pl.L = 0;
+    pl.seg = SegTab{cbeg, cend, ctotal, chunk_counts, chunk_off};
+    int rc = DPK_OK;
+    if (n > 0) {
+        rc = dispatch_count(keys, key_kind, n, pl, fine, nullptr, st);
+        if (rc) return rc;
+    }
+    DPK_LAUNCH("seg_scan", st, k_seg_scan<<<F1, PT_THREADS, (size_t)S2 * 4, st>>>(chunk_counts, cfirst, brow_off, F1, S2, chunk_off, fine_off));
+    if (n > 0) rc = dispatch_scatter(keys, key_kind, vals, val_bytes, n, pl, fine, nullptr, nullptr, out_keys, out_vals, st);
+    return rc;
 }
 
 }  // namespace dpk

@@ -23,10 +23,10 @@ import torch
 
 from . import _native as nv
 
-# rows per fine bucket the reduce side aims for: ~16 thread-block clusters work on
-# 16 buckets at once, each with a table region of 1.5 x 16 B x rows (~5 MB at
-# 2^17.6 rows), so the live tables take ~80 MB of the 126 MB L2
-TARGET_BUCKET_ROWS = 200_000
+# rows per first-level bucket the reduce side aims for: it splits every bucket once
+# more into <= 256 fine buckets of ~2 k rows that are merged in shared memory
+# (dpk_combine.cu, implementation 2), so 2^19 rows per bucket is the upper end
+TARGET_BUCKET_ROWS = 1 << 19
 
 
 def owner_blocks(P, G):
