@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--reduce-impl", type=int, default=2, help="A/B switch of the reduce-side kernel (dpk_set_option)")
     ap.add_argument("--sub-bits", type=int, default=-1, help="override the sub-bucket bits (default: auto)")
+    ap.add_argument("--agg-target-rows", type=int, default=0, help="override rows per fine bucket (dpk_set_option)")
     return ap.parse_args()
 
 
@@ -258,6 +259,8 @@ def run_ours(args):
 
     sub_bits = shuffle.choose_sub_bits(n * world, P) if args.sub_bits < 0 else args.sub_bits
     nv.set_option("reduce_impl", args.reduce_impl)
+    if args.agg_target_rows > 0:
+        nv.set_option("agg_target_rows", args.agg_target_rows)
 
     ex_events = []
 

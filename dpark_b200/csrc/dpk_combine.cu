@@ -448,35 +448,50 @@ k_smem_aggregate(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, i
             if (threadIdx.x == 0) { s_sp--; s_claims = 0; s_overflow = 0; s_side_used = 0; s_side_acc = ident; }
             for (int i = threadIdx.x; i < AG_CAP; i += AG_THREADS) { s_key[i] = kEmpty; s_acc[i] = ident; }
             __syncthreads();
-            for (int64_t i = r0 + threadIdx.x; i < r1; i += AG_THREADS) {
-                const int64_t kb = key_bits<KeyT>(keys[i]);
-                const uint64_t mx = mix64((uint64_t)kb);
-                if (m > 1 && (int)((mx >> 40) & (uint64_t)(m - 1)) != r) continue;
+            // rows are fetched AG_UNROLL per thread at a time (independent loads in flight),
+            // then inserted one by one into the shared-memory table
+            constexpr int AG_UNROLL = 8;
+            for (int64_t base = r0; base < r1; base += (int64_t)AG_THREADS * AG_UNROLL) {
+                KeyT kreg[AG_UNROLL];
+                ValT vreg[AG_UNROLL];
+#pragma unroll
+                for (int u = 0; u < AG_UNROLL; u++) {
+                    const int64_t i = base + (int64_t)u * AG_THREADS + threadIdx.x;
+                    if (i < r1) { kreg[u] = keys[i]; vreg[u] = vals[i]; }
+                }
                 if (*(volatile int *)&s_overflow) break;
-                const AccT v = (AccT)vals[i];
-                if (kb == kEmpty) {
-                    s_side_used = 1;
-                    Acc<AccT>::apply(op, (int64_t *)&s_side_acc, v);
-                    continue;
-                }
-                uint32_t h = (uint32_t)mx & (AG_CAP - 1);
-                bool placed = false;
-                for (;;) {
-                    long long cur = *(volatile long long *)&s_key[h];
-                    if (cur == kb) { placed = true; break; }
-                    if (cur == kEmpty) {
-                        unsigned long long prev = atomicCAS((unsigned long long *)&s_key[h], (unsigned long long)kEmpty,
-                                                            (unsigned long long)kb);
-                        if (prev == (unsigned long long)kEmpty) {
-                            placed = true;
-                            if (atomicAdd(&s_claims, 1) >= AG_LIMIT) s_overflow = 1;
-                            break;
-                        }
-                        if (prev == (unsigned long long)kb) { placed = true; break; }
+#pragma unroll
+                for (int u = 0; u < AG_UNROLL; u++) {
+                    const int64_t i = base + (int64_t)u * AG_THREADS + threadIdx.x;
+                    if (i >= r1) break;
+                    // at most AG_THREADS rows are inserted after the flag goes up; CAP - LIMIT slots stay free
+                    if (*(volatile int *)&s_overflow) break;
+                    const int64_t kb = key_bits<KeyT>(kreg[u]);
+                    const uint64_t mx = mix64((uint64_t)kb);
+                    if (m > 1 && (int)((mx >> 40) & (uint64_t)(m - 1)) != r) continue;
+                    const AccT v = (AccT)vreg[u];
+                    if (kb == kEmpty) {
+                        s_side_used = 1;
+                        Acc<AccT>::apply(op, (int64_t *)&s_side_acc, v);
+                        continue;
                     }
-                    h = (h + 1) & (AG_CAP - 1);
+                    uint32_t h = (uint32_t)mx & (AG_CAP - 1);
+                    for (;;) {
+                        long long cur = *(volatile long long *)&s_key[h];
+                        if (cur == kb) break;
+                        if (cur == kEmpty) {
+                            unsigned long long prev = atomicCAS((unsigned long long *)&s_key[h],
+                                                                (unsigned long long)kEmpty, (unsigned long long)kb);
+                            if (prev == (unsigned long long)kEmpty) {
+                                if (atomicAdd(&s_claims, 1) >= AG_LIMIT) s_overflow = 1;
+                                break;
+                            }
+                            if (prev == (unsigned long long)kb) break;
+                        }
+                        h = (h + 1) & (AG_CAP - 1);
+                    }
+                    Acc<AccT>::apply(op, (int64_t *)&s_acc[h], v);
                 }
-                if (placed) Acc<AccT>::apply(op, (int64_t *)&s_acc[h], v);
             }
             __syncthreads();
             if (s_overflow) {  // uniform after the barrier: split this pass in two and retry
@@ -556,11 +571,11 @@ static inline int grid_cap(int64_t items, int per_cta, int waves) {
 int g_reduce_impl = 2;  // dpk_set_option("reduce_impl", 0|1|2)
 
 constexpr int AG_MAX_SB2 = 8;        // at most 256 fine buckets per first-level bucket
-constexpr int AG_TARGET_ROWS = 2048; // rows per fine bucket the split aims for
+int g_agg_target_rows = 3072;        // rows per fine bucket the split aims for (table load <= 0.75)
 
 static inline int choose_sb2(int64_t n, int32_t F) {
     int sb2 = 0;
-    while (sb2 < AG_MAX_SB2 && n / ((int64_t)F << sb2) > AG_TARGET_ROWS) sb2++;
+    while (sb2 < AG_MAX_SB2 && n / ((int64_t)F << sb2) > g_agg_target_rows) sb2++;
     return sb2;
 }
 
@@ -690,6 +705,11 @@ int dpk_set_option(const char *name, int64_t value) {
     if (strcmp(name, "reduce_impl") == 0) {
         if (value < 0 || value > 2) return fail(DPK_ERR_INVALID, "reduce_impl must be 0, 1 or 2");
         g_reduce_impl = (int)value;
+        return DPK_OK;
+    }
+    if (strcmp(name, "agg_target_rows") == 0) {
+        if (value < 64 || value > AG_LIMIT) return fail(DPK_ERR_INVALID, "agg_target_rows must be in [64, %d]", AG_LIMIT);
+        g_agg_target_rows = (int)value;
         return DPK_OK;
     }
     return fail(DPK_ERR_INVALID, "unknown option %s", name);

@@ -1,0 +1,99 @@
+#!/usr/bin/env python
+"""Multi-GPU parity check of the shuffle engine (run under torchrun, one rank per GPU):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port 29511 scripts/multi_gpu_check.py
+
+Every rank holds its own map splits; reduceByKey and groupByKey run through
+map_side -> exchange (NCCL alltoallv) -> reduce_side / group_side; the per-partition
+results are gathered on rank 0 and compared with the oracle run on the union of all
+splits in (rank, split) order.  Test infrastructure: the oracle is only the checker."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from dpark_b200 import shuffle
+    from oracle import oracle as orc
+
+    dev = torch.device("cuda", local)
+    M, n = 3, 400_000
+    ok_all = True
+    for case, P, lo, hi, sb in (("uniform", 8 * world, 0, 2 ** 31, None), ("dups", 5, -3000, 3000, 2),
+                                ("one_partition", 1, 0, 1000, 0)):
+        def make(r):
+            rng = np.random.default_rng(1000 * r + 7)
+            k = rng.integers(lo, hi, n, dtype=np.int64)
+            v = rng.integers(-1000, 1000, n, dtype=np.int64)
+            return np.array_split(k, M), np.array_split(v, M)
+        ks, vs = make(rank)
+        res = shuffle.reduce_by_key([torch.from_numpy(x).to(dev) for x in ks],
+                                    [torch.from_numpy(x).to(dev) for x in vs], P, "sum", sub_bits=sb)
+        mine = [(p, k.cpu().numpy(), v.cpu().numpy()) for p, k, v in res]
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        # groupByKey: values = global row ids so the (rank, split, position) order is checkable
+        base = rank * n
+        vid = np.array_split(np.arange(base, base + n, dtype=np.int64), M)
+        mo = shuffle.map_side([torch.from_numpy(x).to(dev) for x in ks],
+                              [torch.from_numpy(x).to(dev) for x in vid], P)
+        rx = shuffle.exchange(mo)
+        gk, gs, ng, ov, off = shuffle.group_side(rx, P)
+        G = int(ng.item())
+        gmine = (rx.part_first, rx.nparts, gk[:G].cpu().numpy(), gs[:G + 1].cpu().numpy(), ov.cpu().numpy(),
+                 off.cpu().numpy())
+        ggath = [None] * world
+        dist.all_gather_object(ggath, gmine)
+        if rank == 0:
+            allk, allv, allid = [], [], []
+            for r in range(world):
+                a, b = make(r)
+                allk += a
+                allv += b
+                allid += np.array_split(np.arange(r * n, r * n + n, dtype=np.int64), M)
+            want = orc.reduce_by_key(allk, allv, P, "sum")
+            seen = set()
+            for r in range(world):
+                for p, gk_, gv_ in gathered[r]:
+                    assert p not in seen
+                    seen.add(p)
+                    o1, o2 = np.argsort(gk_), np.argsort(want[p][0])
+                    good = np.array_equal(gk_[o1], want[p][0][o2]) and np.array_equal(gv_[o1], want[p][1][o2])
+                    ok_all &= good
+                    if not good:
+                        print("MISMATCH reduce", case, "partition", p, "from rank", r)
+            assert seen == set(range(P)), (seen, P)
+            wantg = orc.group_by_key(allk, allid, P)
+            for r in range(world):
+                first, nparts, gkeys, gstarts, vals, poff = ggath[r]
+                fg = np.searchsorted(gstarts[:-1], poff, side="left")
+                for p in range(first, first + nparts):
+                    wk, wo, wv = wantg[p]
+                    g0, g1 = fg[p], fg[p + 1]
+                    got = {int(gkeys[g]): vals[gstarts[g]:gstarts[g + 1]] for g in range(g0, g1)}
+                    good = len(got) == len(wk)
+                    for i, key in enumerate(wk.tolist()):
+                        good &= key in got and np.array_equal(got[key], wv[wo[i]:wo[i + 1]])
+                    ok_all &= bool(good)
+                    if not good:
+                        print("MISMATCH group", case, "partition", p, "from rank", r)
+            print("case %-14s P=%-3d world=%d: %s" % (case, P, world, "ok" if ok_all else "FAILED"))
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0 and not ok_all:
+        sys.exit(1)
+
+
+if __name__ == "__main__":
+    main()
