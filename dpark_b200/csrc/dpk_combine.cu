@@ -407,140 +407,8 @@ k_bucket_reduce(const KeyT *__restrict__ keys, const int64_t *__restrict__ aux, 
     }
 }
 
-// ===== implementation 2: second-level split + shared-memory tables ==============
-// The L2 round trip per probe is what bounds implementations 0/1 (ncu: long-scoreboard
-// stalls on the probe loop, atomic units ~7 % busy).  Here every first-level bucket is
-// split once more (seg_multisplit, other hash bits) into fine buckets of ~1.5 k rows,
-// and one CTA merges a fine bucket in a 4096-slot table in SHARED memory: probes cost
-// ~30 cycles instead of ~600, HBM sees each row twice more (the split) but streaming.
-// A fine bucket with more distinct keys than the table holds is processed in
-// hash-disjoint passes (m, r): rows with ((mix >> 40) & (m-1)) == r, split on demand.
-constexpr int AG_THREADS = 256;
-constexpr int AG_CAP = 4096;
-constexpr int AG_LIMIT = AG_CAP - AG_CAP / 8;  // claims before a pass is declared overflowed
-constexpr int AG_STACK = 96;
-
-template <typename KeyT, typename ValT, typename AccT>
-__global__ void __launch_bounds__(AG_THREADS)
-k_smem_aggregate(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, int op, int64_t ident,
-                 const int64_t *__restrict__ fine_off, int32_t nfine, int32_t fine_per_part,
-                 const int64_t *__restrict__ part_offsets, KeyT *__restrict__ out_keys,
-                 int64_t *__restrict__ out_vals, unsigned long long *__restrict__ out_counts) {
-    extern __shared__ __align__(16) long long s_dyn[];  // [AG_CAP] keys | [AG_CAP] accumulators
-    long long *s_key = s_dyn;
-    long long *s_acc = s_dyn + AG_CAP;
-    __shared__ int s_claims, s_overflow, s_side_used, s_sp;
-    __shared__ long long s_side_acc, s_base;
-    __shared__ int s_stack_m[AG_STACK], s_stack_r[AG_STACK];
-    __shared__ int s_wsum[AG_THREADS / 32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int fb = blockIdx.x; fb < nfine; fb += gridDim.x) {
-        const int64_t r0 = fine_off[fb], r1 = fine_off[fb + 1];
-        if (r1 <= r0) continue;  // uniform
-        const int p = fb / fine_per_part;
-        const int64_t pbase = part_offsets[p];
-        if (threadIdx.x == 0) { s_stack_m[0] = 1; s_stack_r[0] = 0; s_sp = 1; }
-        __syncthreads();
-        while (s_sp > 0) {
-            __syncthreads();  // everyone has seen s_sp > 0
-            const int m = s_stack_m[s_sp - 1], r = s_stack_r[s_sp - 1];
-            __syncthreads();
-            if (threadIdx.x == 0) { s_sp--; s_claims = 0; s_overflow = 0; s_side_used = 0; s_side_acc = ident; }
-            for (int i = threadIdx.x; i < AG_CAP; i += AG_THREADS) { s_key[i] = kEmpty; s_acc[i] = ident; }
-            __syncthreads();
-            // rows are fetched AG_UNROLL per thread at a time (independent loads in flight),
-            // then inserted one by one into the shared-memory table
-            constexpr int AG_UNROLL = 8;
-            for (int64_t base = r0; base < r1; base += (int64_t)AG_THREADS * AG_UNROLL) {
-                KeyT kreg[AG_UNROLL];
-                ValT vreg[AG_UNROLL];
-#pragma unroll
-                for (int u = 0; u < AG_UNROLL; u++) {
-                    const int64_t i = base + (int64_t)u * AG_THREADS + threadIdx.x;
-                    if (i < r1) { kreg[u] = keys[i]; vreg[u] = vals[i]; }
-                }
-                if (*(volatile int *)&s_overflow) break;
-#pragma unroll
-                for (int u = 0; u < AG_UNROLL; u++) {
-                    const int64_t i = base + (int64_t)u * AG_THREADS + threadIdx.x;
-                    if (i >= r1) break;
-                    // at most AG_THREADS rows are inserted after the flag goes up; CAP - LIMIT slots stay free
-                    if (*(volatile int *)&s_overflow) break;
-                    const int64_t kb = key_bits<KeyT>(kreg[u]);
-                    const uint64_t mx = mix64((uint64_t)kb);
-                    if (m > 1 && (int)((mx >> 40) & (uint64_t)(m - 1)) != r) continue;
-                    const AccT v = (AccT)vreg[u];
-                    if (kb == kEmpty) {
-                        s_side_used = 1;
-                        Acc<AccT>::apply(op, (int64_t *)&s_side_acc, v);
-                        continue;
-                    }
-                    uint32_t h = (uint32_t)mx & (AG_CAP - 1);
-                    for (;;) {
-                        long long cur = *(volatile long long *)&s_key[h];
-                        if (cur == kb) break;
-                        if (cur == kEmpty) {
-                            unsigned long long prev = atomicCAS((unsigned long long *)&s_key[h],
-                                                                (unsigned long long)kEmpty, (unsigned long long)kb);
-                            if (prev == (unsigned long long)kEmpty) {
-                                if (atomicAdd(&s_claims, 1) >= AG_LIMIT) s_overflow = 1;
-                                break;
-                            }
-                            if (prev == (unsigned long long)kb) break;
-                        }
-                        h = (h + 1) & (AG_CAP - 1);
-                    }
-                    Acc<AccT>::apply(op, (int64_t *)&s_acc[h], v);
-                }
-            }
-            __syncthreads();
-            if (s_overflow) {  // uniform after the barrier: split this pass in two and retry
-                if (threadIdx.x == 0 && s_sp + 2 <= AG_STACK) {
-                    s_stack_m[s_sp] = m * 2; s_stack_r[s_sp] = r; s_sp++;
-                    s_stack_m[s_sp] = m * 2; s_stack_r[s_sp] = r + m; s_sp++;
-                }
-                __syncthreads();
-                continue;
-            }
-            // ---- compact the table into the partition's output range
-            constexpr int PER = AG_CAP / AG_THREADS;
-            int c = 0;
-#pragma unroll
-            for (int j = 0; j < PER; j++) c += s_key[threadIdx.x * PER + j] != kEmpty;
-            int inc = c;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                int t = __shfl_up_sync(0xffffffffu, inc, d);
-                if (lane >= d) inc += t;
-            }
-            if (lane == 31) s_wsum[warp] = inc;
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                int tot = 0;
-                for (int w = 0; w < AG_THREADS / 32; w++) { int t = s_wsum[w]; s_wsum[w] = tot; tot += t; }
-                const int all = tot + (s_side_used ? 1 : 0);
-                s_base = all ? (long long)atomicAdd(&out_counts[p], (unsigned long long)all) : 0;
-                if (s_side_used) {
-                    out_keys[pbase + s_base + tot] = key_from_bits<KeyT>(kEmpty);
-                    out_vals[pbase + s_base + tot] = s_side_acc;
-                }
-            }
-            __syncthreads();
-            int64_t dst = pbase + s_base + s_wsum[warp] + (inc - c);
-#pragma unroll
-            for (int j = 0; j < PER; j++) {
-                const long long kb = s_key[threadIdx.x * PER + j];
-                if (kb != kEmpty) {
-                    out_keys[dst] = key_from_bits<KeyT>(kb);
-                    out_vals[dst] = s_acc[threadIdx.x * PER + j];
-                    dst++;
-                }
-            }
-            __syncthreads();
-        }
-        __syncthreads();
-    }
-}
+// ===== implementation 2: second-level split + shared-memory tables (dpk_aggregate.cuh) =====
+#include "dpk_aggregate.cuh"
 
 // the key whose bits equal the free-slot marker lives in the side slot: append it
 template <typename KeyT>
@@ -571,7 +439,7 @@ static inline int grid_cap(int64_t items, int per_cta, int waves) {
 int g_reduce_impl = 2;  // dpk_set_option("reduce_impl", 0|1|2)
 
 constexpr int AG_MAX_SB2 = 8;        // at most 256 fine buckets per first-level bucket
-int g_agg_target_rows = 3072;        // rows per fine bucket the split aims for (table load <= 0.75)
+int g_agg_target_rows = 2048;        // rows per fine bucket the split aims for (table load <= 0.5)
 
 static inline int choose_sb2(int64_t n, int32_t F) {
     int sb2 = 0;
@@ -582,6 +450,7 @@ static inline int choose_sb2(int64_t n, int32_t F) {
 struct Ctx {
     int key_kind, val_bytes;
     int64_t *fine_off;
+    unsigned long long *fb_state;
     void *seg_ws;
     int64_t seg_ws_bytes;
     const void *keys, *vals;
@@ -622,9 +491,10 @@ static int dispatch_op(const Ctx &c) {
         auto agg = k_smem_aggregate<KeyT, ValT, AccT>;
         const int agg_smem = AG_CAP * 16;
         DPK_CUDA_TRY(cudaFuncSetAttribute(agg, cudaFuncAttributeMaxDynamicSharedMemorySize, agg_smem));
+        DPK_CUDA_TRY(cudaMemsetAsync(c.fb_state, 0, (size_t)nfine * 8, c.st));
         DPK_LAUNCH("smem_aggregate", c.st, agg<<<grid, AG_THREADS, agg_smem, c.st>>>(
             rekeys, revals, c.op, ident, c.fine_off, nfine, (1 << c.f.sub_bits) * S2, c.part_off,
-            (KeyT *)c.out_keys, c.out_vals, c.out_counts));
+            (KeyT *)c.out_keys, c.out_vals, c.out_counts, c.fb_state, c.bucket_counter));
         return DPK_OK;
     }
     if (g_reduce_impl == 1) {
@@ -680,7 +550,8 @@ static int run_combine(Ctx &c, int val_kind, int64_t *out_offsets, void *ws) {
     c.part_off = out_offsets;
     // implementation 2: fine_off[F * 256 + 1] | segmented-multisplit workspace
     c.fine_off = seg_start + (int64_t)c.nsrc * c.F + 2;
-    c.seg_ws = (void *)(((uintptr_t)(c.fine_off + ((int64_t)c.F << AG_MAX_SB2) + 2) + 255) & ~(uintptr_t)255);
+    c.fb_state = (unsigned long long *)(c.fine_off + ((int64_t)c.F << AG_MAX_SB2) + 2);
+    c.seg_ws = (void *)(((uintptr_t)(c.fb_state + ((int64_t)c.F << AG_MAX_SB2) + 2) + 255) & ~(uintptr_t)255);
     c.seg_ws_bytes = seg_multisplit_ws_bytes(c.n, c.F, 1 << AG_MAX_SB2, c.nsrc);
     // side slot: free marker + identity are written by the init below; flags cleared here
     DPK_CUDA_TRY(cudaMemsetAsync(c.side_used, 0, 16, c.st));
@@ -721,7 +592,7 @@ int64_t dpk_combine_workspace_bytes(int64_t n, int32_t nbuckets, int32_t nsrc) {
     if (nsrc < 1) nsrc = 1;
     return (max_slots_for(n, nbuckets) + 2) * (int64_t)sizeof(Slot) +
            ((int64_t)nbuckets + 4 + (int64_t)nbuckets * nsrc) * 8 + 64 +
-           (((int64_t)nbuckets << AG_MAX_SB2) + 4) * 8 + 512 +
+           (((int64_t)nbuckets << AG_MAX_SB2) + 4) * 16 + 512 +
            seg_multisplit_ws_bytes(n, nbuckets, 1 << AG_MAX_SB2, nsrc);
 }
 
