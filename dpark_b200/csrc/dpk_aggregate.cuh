@@ -5,7 +5,8 @@
 // stalls on the probe loop, atomic units ~7 % busy).  Here every first-level bucket has
 // been split once more (seg_multisplit, other hash bits) into fine buckets of ~1.5 k
 // rows, and one CTA merges a fine bucket in a 4096-slot table in SHARED memory: a probe
-// costs ~30 cycles instead of ~600.
+// costs ~30 cycles instead of ~600.  Table accesses are explicit shared-space PTX
+// (ld.volatile.shared / atom.shared.cas / red.shared.add), not generic atomics.
 //
 // Output placement without atomics on the critical path: fine buckets are handed out
 // in order (atomic work counter), and the position of a fine bucket's output inside its
@@ -30,6 +31,34 @@ constexpr unsigned long long AG_FLAG_AGG = 1ull << 62;
 constexpr unsigned long long AG_FLAG_INC = 2ull << 62;
 constexpr unsigned long long AG_VAL_MASK = (1ull << 62) - 1;
 
+// ---- shared-space table primitives (32-bit shared addresses) -------------------
+__device__ __forceinline__ long long sm_ld_volatile(uint32_t a) {
+    long long v;
+    asm volatile("ld.volatile.shared.b64 %0, [%1];" : "=l"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ long long sm_cas(uint32_t a, long long cmp, long long val) {
+    long long old;
+    asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "r"(a), "l"(cmp), "l"(val) : "memory");
+    return old;
+}
+__device__ __forceinline__ void sm_red_add_u64(uint32_t a, long long v) {
+    asm volatile("red.shared.add.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory");
+}
+__device__ __forceinline__ void sm_red_add_f64(uint32_t a, double v) {
+    asm volatile("red.shared.add.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+}
+// accumulate v into the shared-memory accumulator at 32-bit address a (generic pointer g for the rare ops)
+template <typename AccT>
+__device__ __forceinline__ void sm_apply(int op, uint32_t a, long long *g, AccT v) {
+    if (op == DPK_OP_SUM) {
+        if constexpr (std::is_same<AccT, double>::value) sm_red_add_f64(a, v);
+        else sm_red_add_u64(a, (long long)v);
+    } else {
+        Acc<AccT>::apply(op, (int64_t *)g, v);
+    }
+}
+
 // exclusive prefix of the distinct counts of fine buckets [first_fb, fb) -- warp 0 only
 __device__ __forceinline__ unsigned long long ag_look_back(const unsigned long long *state, int first_fb, int fb) {
     const int lane = threadIdx.x & 31;
@@ -53,6 +82,25 @@ __device__ __forceinline__ unsigned long long ag_look_back(const unsigned long l
     return excl;
 }
 
+// insert one row; returns false when the probe sequence got too long (table too full)
+template <typename AccT>
+__device__ __forceinline__ bool ag_insert(uint32_t key_base, uint32_t acc_base, long long *s_acc, int op, int64_t kb,
+                                          uint64_t mx, AccT v) {
+    uint32_t h = (uint32_t)mx & (AG_CAP - 1);
+#pragma unroll 1
+    for (int steps = 0; steps < AG_MAX_PROBE; steps++) {
+        const uint32_t ka = key_base + h * 8u;
+        long long cur = sm_ld_volatile(ka);
+        if (cur == kEmpty) cur = sm_cas(ka, kEmpty, kb);   // old value: kEmpty = claimed, kb = someone else claimed it
+        if (cur == kb || cur == kEmpty) {
+            sm_apply<AccT>(op, acc_base + h * 8u, s_acc + h, v);
+            return true;
+        }
+        h = (h + 1) & (AG_CAP - 1);
+    }
+    return false;
+}
+
 template <typename KeyT, typename ValT, typename AccT>
 __global__ void __launch_bounds__(AG_THREADS)
 k_smem_aggregate(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, int op, int64_t ident,
@@ -63,6 +111,8 @@ k_smem_aggregate(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, i
     extern __shared__ __align__(16) long long s_dyn[];  // [AG_CAP] keys | [AG_CAP] accumulators
     long long *s_key = s_dyn;
     long long *s_acc = s_dyn + AG_CAP;
+    const uint32_t key_base = (uint32_t)__cvta_generic_to_shared(s_key);
+    const uint32_t acc_base = (uint32_t)__cvta_generic_to_shared(s_acc);
     __shared__ int s_fb, s_overflow, s_side_used, s_sp;
     __shared__ long long s_side_acc;
     __shared__ unsigned long long s_excl;
@@ -89,45 +139,44 @@ k_smem_aggregate(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, i
             if (threadIdx.x == 0) { s_sp--; s_overflow = 0; s_side_used = 0; s_side_acc = ident; }
             for (int i = threadIdx.x; i < AG_CAP; i += AG_THREADS) { s_key[i] = kEmpty; s_acc[i] = ident; }
             __syncthreads();
-            for (int64_t base = r0; base < r1; base += (int64_t)AG_THREADS * AG_UNROLL) {
+            bool ok = true;
+            const int64_t nfull = (r1 - r0) / ((int64_t)AG_THREADS * AG_UNROLL) * ((int64_t)AG_THREADS * AG_UNROLL);
+            // ---- full batches: AG_UNROLL independent row loads in flight per thread, no bounds checks
+            for (int64_t base = r0; base < r0 + nfull; base += (int64_t)AG_THREADS * AG_UNROLL) {
                 KeyT kreg[AG_UNROLL];
                 ValT vreg[AG_UNROLL];
 #pragma unroll
                 for (int u = 0; u < AG_UNROLL; u++) {
-                    const int64_t i = base + (int64_t)u * AG_THREADS + threadIdx.x;
-                    if (i < r1) { kreg[u] = keys[i]; vreg[u] = vals[i]; }
+                    kreg[u] = keys[base + u * AG_THREADS + threadIdx.x];
+                    vreg[u] = vals[base + u * AG_THREADS + threadIdx.x];
                 }
 #pragma unroll
                 for (int u = 0; u < AG_UNROLL; u++) {
-                    const int64_t i = base + (int64_t)u * AG_THREADS + threadIdx.x;
-                    if (i >= r1) break;
                     const int64_t kb = key_bits<KeyT>(kreg[u]);
                     const uint64_t mx = mix64((uint64_t)kb);
                     if (m > 1 && (int)((mx >> 40) & (uint64_t)(m - 1)) != r) continue;
-                    const AccT v = (AccT)vreg[u];
                     if (kb == kEmpty) {
                         s_side_used = 1;
-                        Acc<AccT>::apply(op, (int64_t *)&s_side_acc, v);
-                        continue;
+                        Acc<AccT>::apply(op, (int64_t *)&s_side_acc, (AccT)vreg[u]);
+                    } else {
+                        ok &= ag_insert<AccT>(key_base, acc_base, s_acc, op, kb, mx, (AccT)vreg[u]);
                     }
-                    uint32_t h = (uint32_t)mx & (AG_CAP - 1);
-                    int steps = 0;
-                    bool placed = false;
-                    while (steps < AG_MAX_PROBE) {
-                        long long cur = *(volatile long long *)&s_key[h];
-                        if (cur == kb) { placed = true; break; }
-                        if (cur == kEmpty) {
-                            unsigned long long prev = atomicCAS((unsigned long long *)&s_key[h],
-                                                                (unsigned long long)kEmpty, (unsigned long long)kb);
-                            if (prev == (unsigned long long)kEmpty || prev == (unsigned long long)kb) { placed = true; break; }
-                        }
-                        h = (h + 1) & (AG_CAP - 1);
-                        steps++;
-                    }
-                    if (placed) Acc<AccT>::apply(op, (int64_t *)&s_acc[h], v);
-                    else s_overflow = 1;  // table too full for this pass: it will be split
                 }
+                if (!ok) s_overflow = 1;
                 if (*(volatile int *)&s_overflow) break;
+            }
+            // ---- tail
+            for (int64_t i = r0 + nfull + threadIdx.x; i < r1; i += AG_THREADS) {
+                const int64_t kb = key_bits<KeyT>(keys[i]);
+                const uint64_t mx = mix64((uint64_t)kb);
+                if (m > 1 && (int)((mx >> 40) & (uint64_t)(m - 1)) != r) continue;
+                const AccT v = (AccT)vals[i];
+                if (kb == kEmpty) {
+                    s_side_used = 1;
+                    Acc<AccT>::apply(op, (int64_t *)&s_side_acc, v);
+                } else if (!ag_insert<AccT>(key_base, acc_base, s_acc, op, kb, mx, v)) {
+                    s_overflow = 1;
+                }
             }
             __syncthreads();
             if (s_overflow) {  // uniform after the barrier: split this pass in two and retry
@@ -140,9 +189,13 @@ k_smem_aggregate(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, i
             }
             // ---- count + rank the occupied slots
             constexpr int PER = AG_CAP / AG_THREADS;
+            long long kslot[PER];
             int c = 0;
 #pragma unroll
-            for (int j = 0; j < PER; j++) c += s_key[threadIdx.x * PER + j] != kEmpty;
+            for (int j = 0; j < PER; j++) {
+                kslot[j] = s_key[threadIdx.x * PER + j];
+                c += kslot[j] != kEmpty;
+            }
             int inc = c;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -173,9 +226,8 @@ k_smem_aggregate(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, i
             int64_t dst = pbase + (int64_t)(s_excl + written) + wbase + (inc - c);
 #pragma unroll
             for (int j = 0; j < PER; j++) {
-                const long long kb = s_key[threadIdx.x * PER + j];
-                if (kb != kEmpty) {
-                    out_keys[dst] = key_from_bits<KeyT>(kb);
+                if (kslot[j] != kEmpty) {
+                    out_keys[dst] = key_from_bits<KeyT>(kslot[j]);
                     out_vals[dst] = s_acc[threadIdx.x * PER + j];
                     dst++;
                 }

@@ -24,6 +24,7 @@ constexpr int PT_THREADS = 256;
 constexpr int PT_WARPS = PT_THREADS / 32;
 constexpr int PT_ITEMS = 16;
 constexpr int PT_TILE = PT_THREADS * PT_ITEMS;  // 4096 rows per tile
+constexpr int PT_COUNT_PRIV = 1024;             // k_part_count: warp-private histograms up to this many buckets
 
 struct NoVal {};
 
@@ -106,15 +107,22 @@ template <typename KeyT, int PRE>
 __global__ void __launch_bounds__(PT_THREADS)
 k_part_count(const KeyT *__restrict__ keys, int64_t n, int64_t L, PartFn f,
              int32_t *__restrict__ tile_counts, int32_t T, SegTab seg) {
-    extern __shared__ int32_t s_cnt[];  // [buckets]
+    // Histograms: up to PT_COUNT_PRIV buckets every warp owns a private histogram and its
+    // match leader updates it with a plain read-modify-write (shared-memory atomics cost
+    // ~2 cycles per lane and were the bound of this kernel); beyond that one CTA histogram
+    // with atomics.  s_cnt: [PT_WARPS][P] or [P].
+    extern __shared__ int32_t s_cnt[];
     const int P = f.nbuckets();
     if (seg.cbeg != nullptr && (int)blockIdx.x >= *seg.ctotal) return;
-    for (int p = threadIdx.x; p < P; p += PT_THREADS) s_cnt[p] = 0;
+    const bool priv = P <= PT_COUNT_PRIV;
+    const int nhist = priv ? PT_WARPS * P : P;
+    for (int p = threadIdx.x; p < nhist; p += PT_THREADS) s_cnt[p] = 0;
     __syncthreads();
     const int64_t beg = seg.cbeg ? seg.cbeg[blockIdx.x] : (int64_t)blockIdx.x * L;
     const int64_t end = seg.cbeg ? seg.cend[blockIdx.x] : min(n, beg + L);
     const int lane = threadIdx.x & 31;
-    constexpr int U = 4;
+    int32_t *wh = s_cnt + (priv ? (threadIdx.x >> 5) * P : 0);
+    constexpr int U = 8;
     for (int64_t i0 = beg; i0 < end; i0 += (int64_t)PT_THREADS * U) {
         KeyT k[U];
         bool ok[U];
@@ -128,10 +136,24 @@ k_part_count(const KeyT *__restrict__ keys, int64_t n, int64_t L, PartFn f,
         for (int u = 0; u < U; u++) {
             int pid = ok[u] ? f.bucket(key_hash<KeyT, PRE>(k[u], f)) : -1;
             unsigned m = __match_any_sync(0xffffffffu, pid);
-            if (ok[u] && lane == __ffs(m) - 1) atomicAdd(&s_cnt[pid], __popc(m));
+            if (priv) {
+                if (ok[u] && lane == __ffs(m) - 1) wh[pid] += __popc(m);
+                __syncwarp();  // the next round's leader may be another lane touching the same counter
+            } else {
+                if (ok[u] && lane == __ffs(m) - 1) atomicAdd(&s_cnt[pid], __popc(m));
+            }
         }
     }
     __syncthreads();
+    if (priv) {  // fold the warp histograms into the first one
+        for (int p = threadIdx.x; p < P; p += PT_THREADS) {
+            int t = 0;
+#pragma unroll
+            for (int w = 0; w < PT_WARPS; w++) t += s_cnt[w * P + p];
+            s_cnt[p] = t;
+        }
+        __syncthreads();
+    }
     if (seg.cbeg) {
         for (int p = threadIdx.x; p < P; p += PT_THREADS) seg.chunk_counts[(int64_t)blockIdx.x * P + p] = s_cnt[p];
     } else {
@@ -325,7 +347,7 @@ k_part_scatter(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, int
 template <typename KeyT, int PRE>
 static int launch_count(const void *keys, int64_t n, const Plan &pl, const PartFn &f,
                         int32_t *tile_counts, cudaStream_t st) {
-    size_t sh = (size_t)f.nbuckets() * sizeof(int32_t);
+    size_t sh = (size_t)f.nbuckets() * sizeof(int32_t) * (f.nbuckets() <= PT_COUNT_PRIV ? PT_WARPS : 1);
     DPK_LAUNCH(pl.seg.cbeg ? "seg_count" : "part_count", st, k_part_count<KeyT, PRE><<<pl.T, PT_THREADS, sh, st>>>((const KeyT *)keys, n, pl.L, f, tile_counts, pl.T, pl.seg));
     return DPK_OK;
 }
