@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--reduce-impl", type=int, default=2, help="A/B switch of the reduce-side kernel (dpk_set_option)")
     ap.add_argument("--sub-bits", type=int, default=-1, help="override the sub-bucket bits (default: auto)")
     ap.add_argument("--agg-target-rows", type=int, default=0, help="override rows per fine bucket (dpk_set_option)")
+    ap.add_argument("--count-mode", type=int, default=0, help="A/B switch of the histogram pass (dpk_set_option)")
     return ap.parse_args()
 
 
@@ -261,6 +262,7 @@ def run_ours(args):
     nv.set_option("reduce_impl", args.reduce_impl)
     if args.agg_target_rows > 0:
         nv.set_option("agg_target_rows", args.agg_target_rows)
+    nv.set_option("count_mode", args.count_mode)
 
     ex_events = []
 

@@ -578,6 +578,11 @@ int dpk_set_option(const char *name, int64_t value) {
         g_reduce_impl = (int)value;
         return DPK_OK;
     }
+    if (strcmp(name, "count_mode") == 0) {
+        if (value != 0 && value != 1) return fail(DPK_ERR_INVALID, "count_mode must be 0 or 1");
+        g_count_mode = (int)value;
+        return DPK_OK;
+    }
     if (strcmp(name, "agg_target_rows") == 0) {
         if (value < 64 || value > AG_LIMIT) return fail(DPK_ERR_INVALID, "agg_target_rows must be in [64, %d]", AG_LIMIT);
         g_agg_target_rows = (int)value;

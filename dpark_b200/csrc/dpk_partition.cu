@@ -28,6 +28,8 @@ constexpr int PT_COUNT_PRIV = 1024;             // k_part_count: warp-private hi
 
 struct NoVal {};
 
+int g_count_mode = 0;  // dpk_set_option("count_mode", 0 = warp-match + leader update, 1 = one atomic per row)
+
 // Segmented mode (second-level split on the reduce side): the grid runs over a
 // device-resident chunk table instead of equal row ranges; every chunk lies inside
 // one first-level bucket and is split by OTHER hash bits into f.nbuckets() fine
@@ -49,21 +51,21 @@ struct Plan {
 static Plan make_plan(int64_t n) {
     Plan pl;
     pl.seg = SegTab{nullptr, nullptr, nullptr, nullptr, nullptr};
+    // CTA c owns the tiles [c*tiles/T, (c+1)*tiles/T): contiguous (stability), evenly spread
+    // (every CTA gets floor or ceil of tiles/T), T a multiple of the SM count when there is
+    // enough work.  pl.L carries the TOTAL tile count.
     int64_t tiles = (n + PT_TILE - 1) / PT_TILE;
     if (tiles < 1) tiles = 1;
-    int64_t maxT = (int64_t)sm_count() * 4;
-    int64_t T = tiles < maxT ? tiles : maxT;
-    int64_t per = (tiles + T - 1) / T;
-    pl.L = per * PT_TILE;
-    pl.T = (int32_t)((n + pl.L - 1) / pl.L);
-    if (pl.T < 1) pl.T = 1;
+    int64_t maxT = (int64_t)sm_count() * 8;
+    pl.T = (int32_t)(tiles < maxT ? tiles : maxT);
+    pl.L = tiles;
     return pl;
 }
 
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
 // workspace: int32 tile_counts[P][Tmax] | int64 totals[P] | int64 offsets[P+1]
-static int64_t ws_counts_bytes(int32_t P) { return align_up((int64_t)P * sm_count() * 4 * 4, 256); }
+static int64_t ws_counts_bytes(int32_t P) { return align_up((int64_t)P * sm_count() * 8 * 4, 256); }
 static int64_t ws_total_bytes(int32_t P) {
     return ws_counts_bytes(P) + align_up((int64_t)P * 8, 256) + align_up((int64_t)(P + 1) * 8, 256);
 }
@@ -106,7 +108,7 @@ __device__ __forceinline__ int block_excl_scan(int v, int *s_warp, int *total) {
 template <typename KeyT, int PRE>
 __global__ void __launch_bounds__(PT_THREADS)
 k_part_count(const KeyT *__restrict__ keys, int64_t n, int64_t L, PartFn f,
-             int32_t *__restrict__ tile_counts, int32_t T, SegTab seg) {
+             int32_t *__restrict__ tile_counts, int32_t T, SegTab seg, int count_mode) {
     // Histograms: up to PT_COUNT_PRIV buckets every warp owns a private histogram and its
     // match leader updates it with a plain read-modify-write (shared-memory atomics cost
     // ~2 cycles per lane and were the bound of this kernel); beyond that one CTA histogram
@@ -118,8 +120,8 @@ k_part_count(const KeyT *__restrict__ keys, int64_t n, int64_t L, PartFn f,
     const int nhist = priv ? PT_WARPS * P : P;
     for (int p = threadIdx.x; p < nhist; p += PT_THREADS) s_cnt[p] = 0;
     __syncthreads();
-    const int64_t beg = seg.cbeg ? seg.cbeg[blockIdx.x] : (int64_t)blockIdx.x * L;
-    const int64_t end = seg.cbeg ? seg.cend[blockIdx.x] : min(n, beg + L);
+    const int64_t beg = seg.cbeg ? seg.cbeg[blockIdx.x] : ((int64_t)blockIdx.x * L / T) * PT_TILE;
+    const int64_t end = seg.cbeg ? seg.cend[blockIdx.x] : min(n, ((int64_t)(blockIdx.x + 1) * L / T) * PT_TILE);
     const int lane = threadIdx.x & 31;
     int32_t *wh = s_cnt + (priv ? (threadIdx.x >> 5) * P : 0);
     constexpr int U = 8;
@@ -135,6 +137,10 @@ k_part_count(const KeyT *__restrict__ keys, int64_t n, int64_t L, PartFn f,
 #pragma unroll
         for (int u = 0; u < U; u++) {
             int pid = ok[u] ? f.bucket(key_hash<KeyT, PRE>(k[u], f)) : -1;
+            if (count_mode == 1) {  // one shared-memory atomic per row, no warp matching
+                if (ok[u]) atomicAdd(&wh[pid], 1);
+                continue;
+            }
             unsigned m = __match_any_sync(0xffffffffu, pid);
             if (priv) {
                 if (ok[u] && lane == __ffs(m) - 1) wh[pid] += __popc(m);
@@ -239,8 +245,8 @@ k_part_scatter(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, int
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     if (seg.cbeg != nullptr && (int)blockIdx.x >= *seg.ctotal) return;
-    const int64_t beg = seg.cbeg ? seg.cbeg[blockIdx.x] : (int64_t)blockIdx.x * L;
-    const int64_t end = seg.cbeg ? seg.cend[blockIdx.x] : min(n, beg + L);
+    const int64_t beg = seg.cbeg ? seg.cbeg[blockIdx.x] : ((int64_t)blockIdx.x * L / T) * PT_TILE;
+    const int64_t end = seg.cbeg ? seg.cend[blockIdx.x] : min(n, ((int64_t)(blockIdx.x + 1) * L / T) * PT_TILE);
 
     if (seg.cbeg) {
         for (int p = threadIdx.x; p < P; p += PT_THREADS) s_gpos[p] = seg.chunk_off[(int64_t)blockIdx.x * P + p];
@@ -348,7 +354,7 @@ template <typename KeyT, int PRE>
 static int launch_count(const void *keys, int64_t n, const Plan &pl, const PartFn &f,
                         int32_t *tile_counts, cudaStream_t st) {
     size_t sh = (size_t)f.nbuckets() * sizeof(int32_t) * (f.nbuckets() <= PT_COUNT_PRIV ? PT_WARPS : 1);
-    DPK_LAUNCH(pl.seg.cbeg ? "seg_count" : "part_count", st, k_part_count<KeyT, PRE><<<pl.T, PT_THREADS, sh, st>>>((const KeyT *)keys, n, pl.L, f, tile_counts, pl.T, pl.seg));
+    DPK_LAUNCH(pl.seg.cbeg ? "seg_count" : "part_count", st, k_part_count<KeyT, PRE><<<pl.T, PT_THREADS, sh, st>>>((const KeyT *)keys, n, pl.L, f, tile_counts, pl.T, pl.seg, g_count_mode));
     return DPK_OK;
 }
 
