@@ -226,7 +226,7 @@ def run_reference(args):
                                    "shuffle.py:600-608 with marshal dumps" % (sample, cores, P)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------
@@ -421,13 +421,29 @@ def run_ours(args):
             "cpu_baseline": cpu_baseline, "clocks": clk,
             "distinct_keys": int(tot[2]),
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The one JSON line goes to the process's real stdout; everything else any library prints
+    (NCCL's version banner, warnings) was diverted to stderr in main()."""
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    global _REAL_STDOUT
     args = parse()
+    # keep stdout clean: fd 1 -> stderr for the whole run, the JSON line is written to a dup of the original fd 1
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -3,7 +3,7 @@
 //
 // The L2 round trip per probe is what bounds implementations 0/1 (ncu: long-scoreboard
 // stalls on the probe loop, atomic units ~7 % busy).  Here every first-level bucket has
-// been split once more (seg_multisplit, other hash bits) into fine buckets of ~1.5 k
+// been split once more (seg_multisplit, other hash bits) into fine buckets of ~2 k
 // rows, and one CTA merges a fine bucket in a 4096-slot table in SHARED memory: a probe
 // costs ~30 cycles instead of ~600.  Table accesses are explicit shared-space PTX
 // (ld.volatile.shared / atom.shared.cas / red.shared.add), not generic atomics.
@@ -15,9 +15,12 @@
 // words, 2 flag bits + 62 value bits).  The partition's final count is the inclusive
 // value of its last fine bucket.
 //
-// A fine bucket with more distinct keys than the table holds is processed in
-// hash-disjoint passes (m, r): rows with ((mix >> 40) & (m-1)) == r, split on demand
-// (probe sequences longer than AG_MAX_PROBE declare the pass overflowed).
+// Per fine bucket (common case, 4 block barriers): insert all rows -> count/rank the
+// occupied slots -> look back -> write the pairs out and reset the slots in the same
+// sweep (the table is clean again for the next bucket).  A fine bucket with more
+// distinct keys than the table holds takes the slow path: hash-disjoint passes (m, r),
+// rows with ((mix >> 40) & (m-1)) == r, split on demand (a probe sequence longer than
+// AG_MAX_PROBE declares a pass overflowed).
 #pragma once
 
 constexpr int AG_THREADS = 256;
@@ -26,6 +29,7 @@ constexpr int AG_LIMIT = AG_CAP - AG_CAP / 8;  // upper end for "rows per fine b
 constexpr int AG_MAX_PROBE = 96;
 constexpr int AG_STACK = 96;
 constexpr int AG_UNROLL = 4;
+constexpr int AG_PER = AG_CAP / AG_THREADS;     // slots each thread sweeps
 
 constexpr unsigned long long AG_FLAG_AGG = 1ull << 62;
 constexpr unsigned long long AG_FLAG_INC = 2ull << 62;
@@ -101,6 +105,85 @@ __device__ __forceinline__ bool ag_insert(uint32_t key_base, uint32_t acc_base, 
     return false;
 }
 
+struct AgShared {
+    int fb, overflow, side_used, sp;
+    long long side_acc;
+    unsigned long long excl;
+    int stack_m[AG_STACK], stack_r[AG_STACK];
+    int wsum[AG_THREADS / 32];
+};
+
+// insert the rows [r0, r1) whose pass id matches (m, r); sets sh.overflow when the table is too full
+template <typename KeyT, typename ValT, typename AccT>
+__device__ __forceinline__ void ag_insert_rows(const KeyT *__restrict__ keys, const ValT *__restrict__ vals,
+                                               int64_t r0, int64_t r1, int m, int r, int op, uint32_t key_base,
+                                               uint32_t acc_base, long long *s_acc, AgShared &sh) {
+    bool ok = true;
+    const int64_t step = (int64_t)AG_THREADS * AG_UNROLL;
+    const int64_t nfull = (r1 - r0) / step * step;
+    for (int64_t base = r0; base < r0 + nfull; base += step) {  // AG_UNROLL independent loads in flight per thread
+        KeyT kreg[AG_UNROLL];
+        ValT vreg[AG_UNROLL];
+#pragma unroll
+        for (int u = 0; u < AG_UNROLL; u++) {
+            kreg[u] = keys[base + u * AG_THREADS + threadIdx.x];
+            vreg[u] = vals[base + u * AG_THREADS + threadIdx.x];
+        }
+#pragma unroll
+        for (int u = 0; u < AG_UNROLL; u++) {
+            const int64_t kb = key_bits<KeyT>(kreg[u]);
+            const uint64_t mx = mix64((uint64_t)kb);
+            if (m > 1 && (int)((mx >> 40) & (uint64_t)(m - 1)) != r) continue;
+            if (kb == kEmpty) {
+                sh.side_used = 1;
+                Acc<AccT>::apply(op, (int64_t *)&sh.side_acc, (AccT)vreg[u]);
+            } else {
+                ok &= ag_insert<AccT>(key_base, acc_base, s_acc, op, kb, mx, (AccT)vreg[u]);
+            }
+        }
+        if (!ok) sh.overflow = 1;
+        if (*(volatile int *)&sh.overflow) return;
+    }
+    for (int64_t i = r0 + nfull + threadIdx.x; i < r1; i += AG_THREADS) {  // tail
+        const int64_t kb = key_bits<KeyT>(keys[i]);
+        const uint64_t mx = mix64((uint64_t)kb);
+        if (m > 1 && (int)((mx >> 40) & (uint64_t)(m - 1)) != r) continue;
+        const AccT v = (AccT)vals[i];
+        if (kb == kEmpty) {
+            sh.side_used = 1;
+            Acc<AccT>::apply(op, (int64_t *)&sh.side_acc, v);
+        } else if (!ag_insert<AccT>(key_base, acc_base, s_acc, op, kb, mx, v)) {
+            sh.overflow = 1;
+        }
+    }
+}
+
+// count + rank the occupied slots of this thread's sweep range; returns this thread's exclusive
+// rank inside the CTA and the CTA total.  One barrier.
+__device__ __forceinline__ int ag_rank(const long long *kslot, AgShared &sh, int *tot) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int c = 0;
+#pragma unroll
+    for (int j = 0; j < AG_PER; j++) c += kslot[j] != kEmpty;
+    int inc = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) sh.wsum[warp] = inc;
+    __syncthreads();
+    int wbase = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < AG_THREADS / 32; w++) {
+        const int t = sh.wsum[w];
+        if (w < warp) wbase += t;
+        total += t;
+    }
+    *tot = total;
+    return wbase + inc - c;
+}
+
 template <typename KeyT, typename ValT, typename AccT>
 __global__ void __launch_bounds__(AG_THREADS)
 k_smem_aggregate(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, int op, int64_t ident,
@@ -113,143 +196,126 @@ k_smem_aggregate(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, i
     long long *s_acc = s_dyn + AG_CAP;
     const uint32_t key_base = (uint32_t)__cvta_generic_to_shared(s_key);
     const uint32_t acc_base = (uint32_t)__cvta_generic_to_shared(s_acc);
-    __shared__ int s_fb, s_overflow, s_side_used, s_sp;
-    __shared__ long long s_side_acc;
-    __shared__ unsigned long long s_excl;
-    __shared__ int s_stack_m[AG_STACK], s_stack_r[AG_STACK];
-    __shared__ int s_wsum[AG_THREADS / 32];
+    __shared__ AgShared sh;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // the table is kept clean between fine buckets: every sweep that reads a slot resets it
+    for (int i = threadIdx.x; i < AG_CAP; i += AG_THREADS) { s_key[i] = kEmpty; s_acc[i] = ident; }
+    if (threadIdx.x == 0) { sh.overflow = 0; sh.side_used = 0; sh.side_acc = ident; }
     for (;;) {
-        if (threadIdx.x == 0) s_fb = atomicAdd(work_counter, 1);  // in-order hand-out
-        __syncthreads();
-        const int fb = s_fb;
+        if (threadIdx.x == 0) sh.fb = atomicAdd(work_counter, 1);  // in-order hand-out
+        __syncthreads();                                            // (A) also: previous sweep finished, table clean
+        const int fb = sh.fb;
         if (fb >= nfine) break;
         const int64_t r0 = fine_off[fb], r1 = fine_off[fb + 1];
         const int p = fb / fine_per_part;
         const int first_fb = p * fine_per_part;
         const int64_t pbase = part_offsets[p];
-        unsigned long long written = 0;   // distinct pairs of this fine bucket written so far (uniform)
+        unsigned long long written = 0;  // distinct pairs of this fine bucket written so far (uniform)
+        unsigned long long excl = 0;
         bool have_excl = false;
-        if (threadIdx.x == 0) { s_stack_m[0] = 1; s_stack_r[0] = 0; s_sp = r1 > r0 ? 1 : 0; }
-        __syncthreads();
-        while (s_sp > 0) {
-            __syncthreads();  // everyone has seen s_sp > 0
-            const int m = s_stack_m[s_sp - 1], r = s_stack_r[s_sp - 1];
-            __syncthreads();
-            if (threadIdx.x == 0) { s_sp--; s_overflow = 0; s_side_used = 0; s_side_acc = ident; }
-            for (int i = threadIdx.x; i < AG_CAP; i += AG_THREADS) { s_key[i] = kEmpty; s_acc[i] = ident; }
-            __syncthreads();
-            bool ok = true;
-            const int64_t nfull = (r1 - r0) / ((int64_t)AG_THREADS * AG_UNROLL) * ((int64_t)AG_THREADS * AG_UNROLL);
-            // ---- full batches: AG_UNROLL independent row loads in flight per thread, no bounds checks
-            for (int64_t base = r0; base < r0 + nfull; base += (int64_t)AG_THREADS * AG_UNROLL) {
-                KeyT kreg[AG_UNROLL];
-                ValT vreg[AG_UNROLL];
+
+        // ---- fast path: one pass over all rows
+        ag_insert_rows<KeyT, ValT, AccT>(keys, vals, r0, r1, 1, 0, op, key_base, acc_base, s_acc, sh);
+        __syncthreads();                                            // (B)
+        const bool slow = sh.overflow != 0;                         // uniform
+        if (!slow) {
+            long long kslot[AG_PER];
 #pragma unroll
-                for (int u = 0; u < AG_UNROLL; u++) {
-                    kreg[u] = keys[base + u * AG_THREADS + threadIdx.x];
-                    vreg[u] = vals[base + u * AG_THREADS + threadIdx.x];
-                }
-#pragma unroll
-                for (int u = 0; u < AG_UNROLL; u++) {
-                    const int64_t kb = key_bits<KeyT>(kreg[u]);
-                    const uint64_t mx = mix64((uint64_t)kb);
-                    if (m > 1 && (int)((mx >> 40) & (uint64_t)(m - 1)) != r) continue;
-                    if (kb == kEmpty) {
-                        s_side_used = 1;
-                        Acc<AccT>::apply(op, (int64_t *)&s_side_acc, (AccT)vreg[u]);
-                    } else {
-                        ok &= ag_insert<AccT>(key_base, acc_base, s_acc, op, kb, mx, (AccT)vreg[u]);
-                    }
-                }
-                if (!ok) s_overflow = 1;
-                if (*(volatile int *)&s_overflow) break;
-            }
-            // ---- tail
-            for (int64_t i = r0 + nfull + threadIdx.x; i < r1; i += AG_THREADS) {
-                const int64_t kb = key_bits<KeyT>(keys[i]);
-                const uint64_t mx = mix64((uint64_t)kb);
-                if (m > 1 && (int)((mx >> 40) & (uint64_t)(m - 1)) != r) continue;
-                const AccT v = (AccT)vals[i];
-                if (kb == kEmpty) {
-                    s_side_used = 1;
-                    Acc<AccT>::apply(op, (int64_t *)&s_side_acc, v);
-                } else if (!ag_insert<AccT>(key_base, acc_base, s_acc, op, kb, mx, v)) {
-                    s_overflow = 1;
+            for (int j = 0; j < AG_PER; j++) kslot[j] = s_key[threadIdx.x * AG_PER + j];
+            int tot;
+            const int rank = ag_rank(kslot, sh, &tot);              // (C)
+            const int side = sh.side_used ? 1 : 0;
+            if (warp == 0) {
+                if (lane == 0) atomicExch(&fb_state[fb], AG_FLAG_AGG | (unsigned long long)(tot + side));
+                const unsigned long long e = ag_look_back(fb_state, first_fb, fb);
+                if (lane == 0) {
+                    sh.excl = e;
+                    atomicExch(&fb_state[fb], AG_FLAG_INC | (e + (unsigned long long)(tot + side)));
+                    if (fb == first_fb + fine_per_part - 1) out_counts[p] = e + (unsigned long long)(tot + side);
                 }
             }
-            __syncthreads();
-            if (s_overflow) {  // uniform after the barrier: split this pass in two and retry
-                if (threadIdx.x == 0 && s_sp + 2 <= AG_STACK) {
-                    s_stack_m[s_sp] = m * 2; s_stack_r[s_sp] = r; s_sp++;
-                    s_stack_m[s_sp] = m * 2; s_stack_r[s_sp] = r + m; s_sp++;
-                }
-                __syncthreads();
-                continue;
-            }
-            // ---- count + rank the occupied slots
-            constexpr int PER = AG_CAP / AG_THREADS;
-            long long kslot[PER];
-            int c = 0;
+            __syncthreads();                                        // (D)
+            int64_t dst = pbase + (int64_t)sh.excl + rank;
 #pragma unroll
-            for (int j = 0; j < PER; j++) {
-                kslot[j] = s_key[threadIdx.x * PER + j];
-                c += kslot[j] != kEmpty;
-            }
-            int inc = c;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                int t = __shfl_up_sync(0xffffffffu, inc, d);
-                if (lane >= d) inc += t;
-            }
-            if (lane == 31) s_wsum[warp] = inc;
-            __syncthreads();
-            int wbase = 0, tot = 0;
-#pragma unroll
-            for (int w = 0; w < AG_THREADS / 32; w++) {
-                const int t = s_wsum[w];
-                if (w < warp) wbase += t;
-                tot += t;
-            }
-            const int side = s_side_used ? 1 : 0;
-            // ---- where does this fine bucket start inside its partition?  (first pass only)
-            if (!have_excl) {
-                if (warp == 0) {
-                    // single-pass buckets publish their count right away so successors do not wait for our look-back
-                    if (lane == 0 && s_sp == 0) atomicExch(&fb_state[fb], AG_FLAG_AGG | (unsigned long long)(tot + side));
-                    const unsigned long long e = ag_look_back(fb_state, first_fb, fb);
-                    if (lane == 0) s_excl = e;
-                }
-                __syncthreads();
-                have_excl = true;
-            }
-            int64_t dst = pbase + (int64_t)(s_excl + written) + wbase + (inc - c);
-#pragma unroll
-            for (int j = 0; j < PER; j++) {
+            for (int j = 0; j < AG_PER; j++) {
                 if (kslot[j] != kEmpty) {
+                    const int s = threadIdx.x * AG_PER + j;
                     out_keys[dst] = key_from_bits<KeyT>(kslot[j]);
-                    out_vals[dst] = s_acc[threadIdx.x * PER + j];
+                    out_vals[dst] = s_acc[s];
+                    s_key[s] = kEmpty;
+                    s_acc[s] = ident;
                     dst++;
                 }
             }
             if (side && threadIdx.x == 0) {
-                out_keys[pbase + (int64_t)(s_excl + written) + tot] = key_from_bits<KeyT>(kEmpty);
-                out_vals[pbase + (int64_t)(s_excl + written) + tot] = s_side_acc;
+                out_keys[pbase + (int64_t)sh.excl + tot] = key_from_bits<KeyT>(kEmpty);
+                out_vals[pbase + (int64_t)sh.excl + tot] = sh.side_acc;
+                sh.side_used = 0;
+                sh.side_acc = ident;
+            }
+            continue;  // barrier (A) of the next iteration orders the resets before the next inserts
+        }
+
+        // ---- slow path: hash-disjoint passes, split on demand
+        if (threadIdx.x == 0) { sh.stack_m[0] = 2; sh.stack_r[0] = 0; sh.stack_m[1] = 2; sh.stack_r[1] = 1; sh.sp = 2; }
+        __syncthreads();
+        while (sh.sp > 0) {
+            __syncthreads();  // everyone has seen sp > 0
+            const int m = sh.stack_m[sh.sp - 1], r = sh.stack_r[sh.sp - 1];
+            __syncthreads();
+            if (threadIdx.x == 0) { sh.sp--; sh.overflow = 0; sh.side_used = 0; sh.side_acc = ident; }
+            for (int i = threadIdx.x; i < AG_CAP; i += AG_THREADS) { s_key[i] = kEmpty; s_acc[i] = ident; }
+            __syncthreads();
+            ag_insert_rows<KeyT, ValT, AccT>(keys, vals, r0, r1, m, r, op, key_base, acc_base, s_acc, sh);
+            __syncthreads();
+            if (sh.overflow) {  // uniform after the barrier: split this pass in two and retry
+                if (threadIdx.x == 0 && sh.sp + 2 <= AG_STACK) {
+                    sh.stack_m[sh.sp] = m * 2; sh.stack_r[sh.sp] = r; sh.sp++;
+                    sh.stack_m[sh.sp] = m * 2; sh.stack_r[sh.sp] = r + m; sh.sp++;
+                }
+                __syncthreads();
+                continue;
+            }
+            long long kslot[AG_PER];
+#pragma unroll
+            for (int j = 0; j < AG_PER; j++) kslot[j] = s_key[threadIdx.x * AG_PER + j];
+            int tot;
+            const int rank = ag_rank(kslot, sh, &tot);
+            const int side = sh.side_used ? 1 : 0;
+            if (!have_excl) {  // multi-pass buckets publish only their inclusive value, at the end
+                if (warp == 0) {
+                    const unsigned long long e = ag_look_back(fb_state, first_fb, fb);
+                    if (lane == 0) sh.excl = e;
+                }
+                __syncthreads();
+                excl = sh.excl;
+                have_excl = true;
+            }
+            int64_t dst = pbase + (int64_t)(excl + written) + rank;
+#pragma unroll
+            for (int j = 0; j < AG_PER; j++) {
+                if (kslot[j] != kEmpty) {
+                    out_keys[dst] = key_from_bits<KeyT>(kslot[j]);
+                    out_vals[dst] = s_acc[threadIdx.x * AG_PER + j];
+                    dst++;
+                }
+            }
+            if (side && threadIdx.x == 0) {
+                out_keys[pbase + (int64_t)(excl + written) + tot] = key_from_bits<KeyT>(kEmpty);
+                out_vals[pbase + (int64_t)(excl + written) + tot] = sh.side_acc;
             }
             written += (unsigned long long)(tot + side);
             __syncthreads();
         }
-        // ---- publish the inclusive value (empty buckets too, so chains stay short)
+        // leave the table clean and publish the inclusive value
+        for (int i = threadIdx.x; i < AG_CAP; i += AG_THREADS) { s_key[i] = kEmpty; s_acc[i] = ident; }
         if (warp == 0) {
-            unsigned long long e;
-            if (have_excl) e = s_excl;
-            else e = ag_look_back(fb_state, first_fb, fb);
+            unsigned long long e = have_excl ? excl : ag_look_back(fb_state, first_fb, fb);
             if (lane == 0) {
-                __threadfence();
+                sh.overflow = 0; sh.side_used = 0; sh.side_acc = ident;
                 atomicExch(&fb_state[fb], AG_FLAG_INC | (e + written));
                 if (fb == first_fb + fine_per_part - 1) out_counts[p] = e + written;
             }
         }
-        __syncthreads();
     }
 }
