@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--reduce-impl", type=int, default=2, help="A/B switch of the reduce-side kernel (dpk_set_option)")
     ap.add_argument("--sub-bits", type=int, default=-1, help="override the sub-bucket bits (default: auto)")
     ap.add_argument("--agg-target-rows", type=int, default=0, help="override rows per fine bucket (dpk_set_option)")
-    ap.add_argument("--count-mode", type=int, default=0, help="A/B switch of the histogram pass (dpk_set_option)")
+    ap.add_argument("--count-mode", type=int, default=1, help="A/B switch of the histogram pass (dpk_set_option)")
     return ap.parse_args()
 
 

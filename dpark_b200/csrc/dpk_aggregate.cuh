@@ -46,8 +46,18 @@ __device__ __forceinline__ long long sm_cas(uint32_t a, long long cmp, long long
     asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "r"(a), "l"(cmp), "l"(val) : "memory");
     return old;
 }
+// 64-bit integer add into shared memory.  sm_100 has no native 64-bit shared-memory add
+// (red.shared.add.u64 compiles to an ATOMS.CAST.SPIN.64 retry loop), so the add is done on
+// the two 32-bit halves with native atomics: the low half returns its old value, from which
+// this row's carry follows exactly; the high half gets (hi + carry) when that is non-zero.
+// Additions commute and every carry is accounted for by the row that produced it, so the
+// final 64-bit word is exact under any interleaving.
 __device__ __forceinline__ void sm_red_add_u64(uint32_t a, long long v) {
-    asm volatile("red.shared.add.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory");
+    const uint32_t vlo = (uint32_t)(unsigned long long)v, vhi = (uint32_t)((unsigned long long)v >> 32);
+    uint32_t old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(vlo) : "memory");
+    const uint32_t addhi = vhi + ((uint32_t)(old + vlo) < old ? 1u : 0u);
+    if (addhi) asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a + 4u), "r"(addhi) : "memory");
 }
 __device__ __forceinline__ void sm_red_add_f64(uint32_t a, double v) {
     asm volatile("red.shared.add.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");

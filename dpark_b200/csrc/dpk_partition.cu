@@ -28,7 +28,9 @@ constexpr int PT_COUNT_PRIV = 1024;             // k_part_count: warp-private hi
 
 struct NoVal {};
 
-int g_count_mode = 0;  // dpk_set_option("count_mode", 0 = warp-match + leader update, 1 = one atomic per row)
+// dpk_set_option("count_mode"): 1 (default) = one shared-memory atomic per row into a warp-private
+// histogram; 0 = warp peer mask + leader update (slower: measured 1.01 ms vs 0.47 ms per 1e8 rows)
+int g_count_mode = 1;
 
 // Segmented mode (second-level split on the reduce side): the grid runs over a
 // device-resident chunk table instead of equal row ranges; every chunk lies inside
@@ -78,6 +80,21 @@ __device__ __forceinline__ int64_t key_hash(KeyT k, const PartFn &f) {
     if constexpr (PRE == 1) return (int64_t)k;
     else if constexpr (PRE == 2) return __ldg(&f.row_hash[(int64_t)k]);
     else return KeyHash<KeyT>::of(k);
+}
+
+// Lanes of the warp holding the same bucket id.  MATCH.ANY costs ~200 issue cycles on
+// sm_100 (measured: the histogram pass halved without it), so the peer mask is built
+// from one ballot per bit of the id instead (nbits <= 13, warp-uniform).
+__device__ __forceinline__ unsigned warp_peers(int id, int nbits) {
+    unsigned peers = 0xffffffffu;
+#pragma unroll
+    for (int b = 0; b < 13; b++) {
+        if (b < nbits) {
+            const unsigned set = __ballot_sync(0xffffffffu, (id >> b) & 1);
+            peers &= ((id >> b) & 1) ? set : ~set;
+        }
+    }
+    return peers;
 }
 
 // exclusive scan of one int per thread over the 256-thread CTA; returns the
@@ -141,7 +158,7 @@ k_part_count(const KeyT *__restrict__ keys, int64_t n, int64_t L, PartFn f,
                 if (ok[u]) atomicAdd(&wh[pid], 1);
                 continue;
             }
-            unsigned m = __match_any_sync(0xffffffffu, pid);
+            unsigned m = warp_peers(pid, 32 - __clz(P));
             if (priv) {
                 if (ok[u] && lane == __ffs(m) - 1) wh[pid] += __popc(m);
                 __syncwarp();  // the next round's leader may be another lane touching the same counter
@@ -256,6 +273,7 @@ k_part_scatter(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, int
     }
 
     const int E = (P + PT_THREADS - 1) / PT_THREADS;  // buckets per thread in the scan
+    const int nbits = 32 - __clz(P);                   // bits of a bucket id, incl. the "no row" id P
 
     for (int64_t tile = beg; tile < end; tile += PT_TILE) {
         const int rows = (int)min((int64_t)PT_TILE, end - tile);
@@ -286,7 +304,7 @@ k_part_scatter(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, int
         for (int j = 0; j < PT_ITEMS; j++) {
             const bool ok = (wbase + j * 32) < end;
             const int p = ok ? f.bucket(key_hash<KeyT, PRE>(k[j], f)) : P;  // P = "no row"
-            const unsigned m = __match_any_sync(0xffffffffu, p);
+            const unsigned m = warp_peers(p, nbits);
             int base = 0;
             if (ok) base = wh[p];
             __syncwarp();
