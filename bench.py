@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--sub-bits", type=int, default=-1, help="override the sub-bucket bits (default: auto)")
     ap.add_argument("--agg-target-rows", type=int, default=0, help="override rows per fine bucket (dpk_set_option)")
     ap.add_argument("--count-mode", type=int, default=1, help="A/B switch of the histogram pass (dpk_set_option)")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N>1: fused scatter into peer memory over NVLink, or a separate NCCL alltoallv")
     return ap.parse_args()
 
 
@@ -265,8 +267,21 @@ def run_ours(args):
     nv.set_option("count_mode", args.count_mode)
 
     ex_events = []
+    # exchange: "peer" = the scatter kernel stores rows straight into the owning GPU's receive buffer
+    # (NVLink peer memory, dpark_b200/peer.py); "nccl" = separate alltoallv (shuffle.exchange)
+    px = None
+    if world > 1 and args.exchange == "peer":
+        try:
+            from dpark_b200 import peer
+            px = peer.PeerExchange(int(n * 1.25) + (1 << 20), torch.int64, torch.int64, dev)
+        except Exception as e:  # symmetric memory unavailable on this box/build: say so, use NCCL
+            sys.stderr.write("peer exchange unavailable (%s: %s); using NCCL alltoallv\n" % (type(e).__name__, e))
+            px = None
 
     def step():
+        if px is not None:
+            rx = peer.map_side_push(px, kc, vc, P, None, sub_bits)
+            return shuffle.reduce_side(rx, "sum", P)
         mo = shuffle.map_side(kc, vc, P, None, False, sub_bits)
         if world > 1:      # bracket the one collective (alltoallv) for the NVLink roofline
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -319,6 +334,18 @@ def run_ours(args):
         roofline_exchange = {"bound": "nvlink", "kernel": "alltoallv (counts all-gather + 2 x all_to_all_single)",
                              "achieved": gbs, "peak": 770.0, "unit": "GB/s per GPU per direction",
                              "frac": gbs / 770.0, "ms_per_step": float(ex_ms),
+                             "peak_source": "measured peer copy on this pool (B200_PROFILING.md); nominal 900"}
+    if world > 1 and px is not None:
+        # fused: the NVLink traffic rides inside k_part_scatter; rate = bytes sent / time of those kernels
+        sc_ms = sum(t for name, t in nv.prof_collect() if name == "part_scatter") / args.steps
+        sc = torch.tensor([sc_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(sc, op=dist.ReduceOp.MAX)
+        sent = (KEY_BYTES + VAL_BYTES) * n * (world - 1) / world
+        gbs = sent / (float(sc) * 1e-3) / 1e9
+        roofline_exchange = {"bound": "nvlink", "kernel": "k_part_scatter storing into peer receive buffers "
+                             "(fused scatter + exchange, no separate alltoallv pass)",
+                             "achieved": gbs, "peak": 770.0, "unit": "GB/s per GPU per direction",
+                             "frac": gbs / 770.0, "ms_per_step": float(sc),
                              "peak_source": "measured peer copy on this pool (B200_PROFILING.md); nominal 900"}
     launches = nv.launch_count() - launches0
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -378,7 +405,7 @@ def run_ours(args):
         roofline_reduce = None
 
     # ---- e2e: host buffers through the public HostShuffle call ------------------
-    hs = shuffle.HostShuffle(n, torch.int64, torch.int64, P, "sum", splits=M, sub_bits=sub_bits)
+    hs = shuffle.HostShuffle(n, torch.int64, torch.int64, P, "sum", splits=M, sub_bits=sub_bits, peer_exchange=px)
     hs.h_keys.copy_(keys.cpu())
     hs.h_vals.copy_(vals.cpu())
     del keys, vals, kc, vc

@@ -33,6 +33,7 @@ EXPORTS = [
     "dpk_launch_count", "dpk_prof_enable", "dpk_prof_count", "dpk_prof_get",
     "dpk_dict_encode_workspace_bytes", "dpk_dict_encode", "dpk_set_option",
     "dpk_key_or", "dpk_radix_pass", "dpk_group_heads_workspace_bytes", "dpk_group_heads", "dpk_gather_i64",
+    "dpk_partition_scatter_ptrs",
 ]
 
 _lib = None
@@ -65,6 +66,7 @@ def lib():
         L.dpk_partition_count.argtypes = [vp, ci, vp, i64, i32, vp, i32, i32, vp, vp, i64, vp]
         L.dpk_partition_scatter.argtypes = [vp, ci, vp, vp, i32, i64, i32, vp, i32, i32, vp, vp, vp, vp, i64, vp]
         L.dpk_partition.argtypes = [vp, ci, vp, vp, i32, i64, i32, vp, i32, i32, vp, vp, vp, vp, i64, vp]
+        L.dpk_partition_scatter_ptrs.argtypes = [vp, ci, vp, vp, i32, i64, i32, vp, i32, i32, vp, vp, vp, i64, vp]
         L.dpk_combine_workspace_bytes.argtypes = [i64, i32, i32]
         L.dpk_combine.argtypes = [vp, ci, vp, vp, ci, i64, ci, i32, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp,
                                   vp, vp, i64, vp]
@@ -206,6 +208,18 @@ def partition_scatter(keys, vals, P, bucket_base, out_keys, out_vals, ws, thresh
                                        keys.numel(), P,
                                        _ptr(thr), nthr, sub_bits, _ptr(bucket_base), _ptr(out_keys),
                                        _ptr(out_vals), _ptr(ws), ws.numel(), _stream()))
+
+
+def partition_scatter_ptrs(keys, vals, P, key_ptrs, val_ptrs, ws, thresholds=None, prehashed=False, sub_bits=0,
+                           row_hash=None):
+    """Fused scatter + exchange: bucket b of this chunk is written through key_ptrs[b] / val_ptrs[b]
+    (device int64 tensors holding absolute device addresses, possibly peer-GPU memory)."""
+    _need_cuda(keys, vals, key_ptrs, val_ptrs, ws, row_hash)
+    thr, nthr = _thr(thresholds, keys.device)
+    vb = 0 if vals is None else vals.element_size()
+    _check(lib().dpk_partition_scatter_ptrs(_ptr(keys), _kk(keys, prehashed, row_hash), _ptr(row_hash), _ptr(vals),
+                                            vb, keys.numel(), P, _ptr(thr), nthr, sub_bits, _ptr(key_ptrs),
+                                            _ptr(val_ptrs), _ptr(ws), ws.numel(), _stream()))
 
 
 def partition(keys, vals, P, thresholds=None, prehashed=False, sub_bits=0, row_hash=None):

@@ -42,6 +42,10 @@ struct SegTab {
     const int32_t *ctotal;          // number of chunks (device)
     int32_t *chunk_counts;          // [chunk][F]   (count kernel writes)
     const int64_t *chunk_off;       // [chunk][F]   absolute output position (scatter kernel reads)
+    // Pointer mode (fused scatter + exchange): bucket b of this chunk is written to the memory at
+    // key_ptrs[b] / val_ptrs[b] -- absolute device addresses, which may be peer-GPU memory mapped
+    // over NVLink -- at element offset (rows of b in earlier CTAs of this chunk) + rank.
+    const uint64_t *key_ptrs, *val_ptrs;
 };
 
 struct Plan {
@@ -52,7 +56,7 @@ struct Plan {
 
 static Plan make_plan(int64_t n) {
     Plan pl;
-    pl.seg = SegTab{nullptr, nullptr, nullptr, nullptr, nullptr};
+    pl.seg = SegTab{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // CTA c owns the tiles [c*tiles/T, (c+1)*tiles/T): contiguous (stability), evenly spread
     // (every CTA gets floor or ceil of tiles/T), T a multiple of the SM count when there is
     // enough work.  pl.L carries the TOTAL tile count.
@@ -82,9 +86,9 @@ __device__ __forceinline__ int64_t key_hash(KeyT k, const PartFn &f) {
     else return KeyHash<KeyT>::of(k);
 }
 
-// Lanes of the warp holding the same bucket id.  MATCH.ANY costs ~200 issue cycles on
-// sm_100 (measured: the histogram pass halved without it), so the peer mask is built
-// from one ballot per bit of the id instead (nbits <= 13, warp-uniform).
+// Lanes of the warp holding the same bucket id, built from one ballot per bit of the id
+// (nbits <= 13, warp-uniform).  Only used by the histogram pass's count_mode 0; the scatter
+// kernel keeps MATCH.ANY, which measured faster there.
 __device__ __forceinline__ unsigned warp_peers(int id, int nbits) {
     unsigned peers = 0xffffffffu;
 #pragma unroll
@@ -225,9 +229,9 @@ k_part_offsets(const int64_t *__restrict__ totals, int32_t P, int64_t *__restric
 
 // ---------------------------------------------------------------- scatter
 struct ScatterSmem {
-    int64_t key_off, val_off, pid_off, gpos_off, tstart_off, tcount_off, whist_off, total;
+    int64_t key_off, val_off, pid_off, gpos_off, tstart_off, tcount_off, whist_off, kptr_off, vptr_off, total;
 };
-static ScatterSmem scatter_smem(int kb, int vb, int32_t P) {
+static ScatterSmem scatter_smem(int kb, int vb, int32_t P, bool ptr_mode = false) {
     ScatterSmem s;
     int64_t o = 0;
     s.key_off = o; o += align_up((int64_t)PT_TILE * kb, 16);
@@ -237,6 +241,8 @@ static ScatterSmem scatter_smem(int kb, int vb, int32_t P) {
     s.tcount_off = o; o += align_up((int64_t)P * 4, 16);
     s.pid_off = o; o += align_up((int64_t)PT_TILE * 2, 16);
     s.whist_off = o; o += align_up((int64_t)PT_WARPS * P * 2, 16);
+    s.kptr_off = o; if (ptr_mode) o += align_up((int64_t)P * 8, 16);
+    s.vptr_off = o; if (ptr_mode) o += align_up((int64_t)P * 8, 16);
     s.total = o;
     return s;
 }
@@ -265,7 +271,15 @@ k_part_scatter(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, int
     const int64_t beg = seg.cbeg ? seg.cbeg[blockIdx.x] : ((int64_t)blockIdx.x * L / T) * PT_TILE;
     const int64_t end = seg.cbeg ? seg.cend[blockIdx.x] : min(n, ((int64_t)(blockIdx.x + 1) * L / T) * PT_TILE);
 
-    if (seg.cbeg) {
+    uint64_t *s_kptr = reinterpret_cast<uint64_t *>(smem + lay.kptr_off);
+    uint64_t *s_vptr = reinterpret_cast<uint64_t *>(smem + lay.vptr_off);
+    if (seg.key_ptrs) {
+        for (int p = threadIdx.x; p < P; p += PT_THREADS) {
+            s_gpos[p] = (int64_t)tile_off[(int64_t)p * T + blockIdx.x];
+            s_kptr[p] = seg.key_ptrs[p];
+            if constexpr (HAS_VAL) s_vptr[p] = seg.val_ptrs[p];
+        }
+    } else if (seg.cbeg) {
         for (int p = threadIdx.x; p < P; p += PT_THREADS) s_gpos[p] = seg.chunk_off[(int64_t)blockIdx.x * P + p];
     } else {
         for (int p = threadIdx.x; p < P; p += PT_THREADS)
@@ -273,7 +287,6 @@ k_part_scatter(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, int
     }
 
     const int E = (P + PT_THREADS - 1) / PT_THREADS;  // buckets per thread in the scan
-    const int nbits = 32 - __clz(P);                   // bits of a bucket id, incl. the "no row" id P
 
     for (int64_t tile = beg; tile < end; tile += PT_TILE) {
         const int rows = (int)min((int64_t)PT_TILE, end - tile);
@@ -304,7 +317,8 @@ k_part_scatter(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, int
         for (int j = 0; j < PT_ITEMS; j++) {
             const bool ok = (wbase + j * 32) < end;
             const int p = ok ? f.bucket(key_hash<KeyT, PRE>(k[j], f)) : P;  // P = "no row"
-            const unsigned m = warp_peers(p, nbits);
+            // MATCH.ANY beats a ballot-per-bit peer mask here (A/B on B200: 1.79 vs 1.99 ms per 1e8 rows)
+            const unsigned m = __match_any_sync(0xffffffffu, p);
             int base = 0;
             if (ok) base = wh[p];
             __syncwarp();
@@ -358,8 +372,13 @@ k_part_scatter(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, int
         for (int i = threadIdx.x; i < rows; i += PT_THREADS) {
             const int p = s_pid[i];
             const int64_t dst = s_gpos[p] + (int64_t)(i - s_tstart[p]);
-            out_keys[dst] = s_key[i];
-            if constexpr (HAS_VAL) out_vals[dst] = s_val[i];
+            if (seg.key_ptrs) {  // pointer mode: the bucket's destination may be a peer GPU
+                reinterpret_cast<KeyT *>(s_kptr[p])[dst] = s_key[i];
+                if constexpr (HAS_VAL) reinterpret_cast<ValT *>(s_vptr[p])[dst] = s_val[i];
+            } else {
+                out_keys[dst] = s_key[i];
+                if constexpr (HAS_VAL) out_vals[dst] = s_val[i];
+            }
         }
         __syncthreads();
         for (int p = threadIdx.x; p < P; p += PT_THREADS) s_gpos[p] += s_tcount[p];
@@ -397,7 +416,7 @@ static int launch_scatter(const void *keys, const void *vals, int64_t n, const P
                           const int32_t *tile_off, const int64_t *bucket_base, void *out_keys,
                           void *out_vals, cudaStream_t st) {
     constexpr int vb = std::is_same<ValT, NoVal>::value ? 0 : (int)sizeof(ValT);
-    ScatterSmem lay = scatter_smem((int)sizeof(KeyT), vb, f.nbuckets());
+    ScatterSmem lay = scatter_smem((int)sizeof(KeyT), vb, f.nbuckets(), pl.seg.key_ptrs != nullptr);
     auto kern = k_part_scatter<KeyT, ValT, PRE>;
     if (lay.total > 227 * 1024)
         return fail(DPK_ERR_UNSUPPORTED, "%d buckets need %lld B of shared memory", f.nbuckets(), (long long)lay.total);
@@ -560,7 +579,7 @@ int seg_multisplit(const void *keys, int key_kind, const void *vals, int32_t val
     Plan pl;
     pl.T = (int32_t)maxc;
     pl.L = 0;
-    pl.seg = SegTab{cbeg, cend, ctotal, chunk_counts, chunk_off};
+    pl.seg = SegTab{cbeg, cend, ctotal, chunk_counts, chunk_off, nullptr, nullptr};
     int rc = DPK_OK;
     if (n > 0) {
         rc = dispatch_count(keys, key_kind, n, pl, fine, nullptr, st);
@@ -639,6 +658,30 @@ int dpk_partition(const void *keys, int key_kind, const int64_t *key_aux, const 
     DPK_LAUNCH("part_offsets", st, k_part_offsets<<<1, PT_THREADS, 0, st>>>(totals, F, out_offsets));
     return dpk_partition_scatter(keys, key_kind, key_aux, vals, val_bytes, n, P, thresholds, nthr, sub_bits, out_offsets,
                                  out_keys, out_vals, ws, ws_bytes, stream);
+}
+
+// Fused scatter + exchange: like dpk_partition_scatter, but bucket b is written through
+// key_dst_ptrs[b] / val_dst_ptrs[b] (absolute device addresses, device arrays of F entries): the
+// caller points each bucket at its slot in the owning GPU's receive buffer (peer memory mapped over
+// NVLink, or local memory), so the rows land where the reducer reads them and no separate
+// alltoallv pass over HBM is needed.  Must follow dpk_partition_count with the same arguments.
+int dpk_partition_scatter_ptrs(const void *keys, int key_kind, const int64_t *key_aux, const void *vals,
+                               int32_t val_bytes, int64_t n, int32_t P, const int64_t *thresholds, int32_t nthr,
+                               int32_t sub_bits, const uint64_t *key_dst_ptrs, const uint64_t *val_dst_ptrs,
+                               void *ws, int64_t ws_bytes, dpk_stream_t stream) {
+    int rc = check_common(keys, n, P, sub_bits, ws, ws_bytes);
+    if (rc) return rc;
+    if (n == 0) return DPK_OK;
+    if (!key_dst_ptrs || (vals && val_bytes && !val_dst_ptrs)) return fail(DPK_ERR_INVALID, "NULL pointer table");
+    PartFn f;
+    rc = make_partfn(P, thresholds, nthr, sub_bits, &f);
+    if (rc) return rc;
+    f.row_hash = key_aux;
+    Plan pl = make_plan(n);
+    pl.seg.key_ptrs = key_dst_ptrs;
+    pl.seg.val_ptrs = val_dst_ptrs;
+    return dispatch_scatter(keys, key_kind, vals, val_bytes, n, pl, f, (const int32_t *)ws, nullptr, nullptr, nullptr,
+                            (cudaStream_t)stream);
 }
 
 // One stable LSD radix pass over int64 key bits: the same multisplit with the

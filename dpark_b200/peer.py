@@ -1,0 +1,87 @@
+"""Fused scatter + exchange over NVLink peer memory.
+
+The reference's reducers PULL every map's bucket over files + HTTP
+(ShuffleFetcher, dpark/shuffle.py:309-420).  shuffle.exchange() replaces that by one NCCL
+alltoallv -- still a separate pass that reads the bucket-major buffer from HBM and writes it
+into the peer's HBM.  Here the map-side scatter kernel PUSHES instead: every rank maps its
+peers' receive buffers into its address space (torch symmetric memory = cuMem allocations
+exchanged between the ranks of one node) and dpk_partition_scatter_ptrs stores each bucket's
+rows straight into the owning GPU's receive buffer while it is partitioning.  The exchange
+costs no extra HBM pass and overlaps with the scatter's own work; what remains of the
+collective is the small all-gather of the counts matrix (the MapOutputTracker) and two
+barriers.
+
+Layout of a receive buffer = what exchange() delivers: source-rank-major, bucket-major inside.
+"""
+import torch
+import torch.distributed as dist
+
+from . import _native as nv
+from .shuffle import Received, owner_blocks
+
+
+class PeerExchange(object):
+    """Symmetric receive buffers (keys + values) of `capacity` rows on every rank."""
+
+    def __init__(self, capacity, key_dtype, val_dtype, device=None, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self.group = group or dist.group.WORLD
+        self.rank = dist.get_rank(self.group)
+        self.world = dist.get_world_size(self.group)
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.capacity = int(capacity)
+        self.keys = symm.empty(self.capacity, dtype=key_dtype, device=self.device)
+        self.vals = symm.empty(self.capacity, dtype=val_dtype, device=self.device)
+        name = self.group.group_name
+        self.hk = symm.rendezvous(self.keys, name)
+        self.hv = symm.rendezvous(self.vals, name)
+        self.key_base = torch.tensor([int(p) for p in self.hk.buffer_ptrs], dtype=torch.int64, device=self.device)
+        self.val_base = torch.tensor([int(p) for p in self.hv.buffer_ptrs], dtype=torch.int64, device=self.device)
+
+    def barrier(self):
+        self.hk.barrier()
+
+
+def map_side_push(px, key_chunks, val_chunks, P, thresholds=None, sub_bits=0):
+    """Map side + exchange in one pass: returns the Received view of THIS rank's buffer."""
+    G, rank, dev = px.world, px.rank, px.device
+    F = P << sub_bits
+    counts, wss = [], []
+    for k in key_chunks:
+        c, ws = nv.partition_count(k, P, thresholds, False, sub_bits)
+        counts.append(c)
+        wss.append(ws)
+    cm = torch.stack(counts)                                        # [M, F] rows per chunk and bucket
+    mine = cm.sum(0).contiguous()                                   # [F]
+    all_counts = torch.empty(G * F, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(all_counts, mine, group=px.group)   # the MapOutputTracker
+    all_counts = all_counts.view(G, F)
+    blocks = [b << sub_bits for b in owner_blocks(P, G)]
+    # rows every source sends to every destination: R[s][d]
+    R = torch.stack([all_counts[:, blocks[d]:blocks[d + 1]].sum(1) for d in range(G)], dim=1)   # [G, G]
+    src_base = torch.cumsum(R, 0) - R                               # [s][d]: rows of earlier sources at d
+    need = int(R.sum(0).max().item())                               # host read: capacity check + recv sizes
+    if need > px.capacity:
+        raise RuntimeError("peer receive buffer too small: need %d rows, capacity %d" % (need, px.capacity))
+    # offset of my bucket b inside its owner's buffer
+    dst_off = torch.empty(F, dtype=torch.int64, device=dev)
+    owner = torch.empty(F, dtype=torch.int64, device=dev)
+    for d in range(G):
+        b0, b1 = blocks[d], blocks[d + 1]
+        if b1 > b0:
+            seg = all_counts[rank, b0:b1]
+            dst_off[b0:b1] = src_base[rank, d] + (torch.cumsum(seg, 0) - seg)
+            owner[b0:b1] = d
+    chunk_off = torch.cumsum(cm, 0) - cm                            # rows of earlier local chunks per bucket
+    ksz, vsz = key_chunks[0].element_size(), val_chunks[0].element_size()
+    kbase, vbase = px.key_base[owner], px.val_base[owner]
+    px.barrier()                                                    # nobody still reads the buffers of the last step
+    for m, (k, v) in enumerate(zip(key_chunks, val_chunks)):
+        off = dst_off + chunk_off[m]
+        nv.partition_scatter_ptrs(k, v, P, (kbase + off * ksz).contiguous(), (vbase + off * vsz).contiguous(),
+                                  wss[m], thresholds, False, sub_bits)
+    px.barrier()                                                    # every peer's stores have landed
+    b0, b1 = blocks[rank], blocks[rank + 1]
+    nrecv = int(R[:, rank].sum().item())
+    seg = all_counts[:, b0:b1].contiguous()
+    return Received(px.keys[:nrecv], px.vals[:nrecv], seg, b0 >> sub_bits, (b1 - b0) >> sub_bits, sub_bits)

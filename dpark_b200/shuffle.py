@@ -199,8 +199,9 @@ class HostShuffle(object):
     distinct (key, combined) rows.  Buffers are allocated once and reused."""
 
     def __init__(self, n_rows, key_dtype, val_dtype, P, op="sum", splits=8, thresholds=None, group=None,
-                 device=None, sub_bits=None, world=1):
+                 device=None, sub_bits=None, world=1, peer_exchange=None):
         self.P, self.op, self.splits, self.thresholds, self.group = P, op, splits, thresholds, group
+        self.peer_exchange = peer_exchange
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         self.n = n_rows
         self.sub_bits = choose_sub_bits(n_rows * world, P) if sub_bits is None else sub_bits
@@ -224,8 +225,12 @@ class HostShuffle(object):
             self.d_vals[a:b].copy_(self.h_vals[a:b], non_blocking=True)
             kc.append(self.d_keys[a:b])
             vc.append(self.d_vals[a:b])
-        mo = map_side(kc, vc, self.P, self.thresholds, False, self.sub_bits)
-        rx = exchange(mo, self.group)
+        if self.peer_exchange is not None:     # fused scatter + exchange over NVLink peer memory
+            from . import peer
+            rx = peer.map_side_push(self.peer_exchange, kc, vc, self.P, self.thresholds, self.sub_bits)
+        else:
+            mo = map_side(kc, vc, self.P, self.thresholds, False, self.sub_bits)
+            rx = exchange(mo, self.group)
         ok, ov, po, cnt = reduce_side(rx, self.op, self.P, self.thresholds)
         po_h, cnt_h = po.cpu().tolist(), cnt.cpu().tolist()      # the one host sync: result sizes
         nrx = int(ok.numel())

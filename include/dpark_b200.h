@@ -117,6 +117,16 @@ int dpk_partition(const void *keys, int key_kind, const int64_t *key_aux, const 
                   int32_t val_bytes, int64_t n, int32_t P, const int64_t *thresholds, int32_t nthr,
                   int32_t sub_bits, void *out_keys, void *out_vals, int64_t *out_offsets, void *ws,
                   int64_t ws_bytes, dpk_stream_t stream);
+/* Fused scatter + exchange (replaces the ShuffleFetcher pull, dpark/shuffle.py:309-420, by a
+ * push): like dpk_partition_scatter, but bucket b of this chunk is written to the memory at
+ * key_dst_ptrs[b] / val_dst_ptrs[b] -- absolute device addresses (uint64, device arrays of F
+ * entries) that may point into a PEER GPU's receive buffer mapped over NVLink.  Rows land at
+ * element offset (rows of b in this chunk before them), in input order. */
+int dpk_partition_scatter_ptrs(const void *keys, int key_kind, const int64_t *key_aux,
+                               const void *vals, int32_t val_bytes, int64_t n, int32_t P,
+                               const int64_t *thresholds, int32_t nthr, int32_t sub_bits,
+                               const uint64_t *key_dst_ptrs, const uint64_t *val_dst_ptrs, void *ws,
+                               int64_t ws_bytes, dpk_stream_t stream);
 
 /* ---- a9: reduce side, DiskHashMerger._merge (dpark/shuffle.py:600-608) ----
  * combined[k] = op(combined[k], v) over the n rows fetched for the nparts reduce

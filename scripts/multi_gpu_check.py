@@ -30,6 +30,13 @@ def main():
     dev = torch.device("cuda", local)
     M, n = 3, 400_000
     ok_all = True
+    px = None
+    try:
+        from dpark_b200 import peer
+        px = peer.PeerExchange(2 * n + 4096, torch.int64, torch.int64, dev)
+    except Exception as e:
+        if rank == 0:
+            print("peer exchange unavailable:", type(e).__name__, e)
     for case, P, lo, hi, sb in (("uniform", 8 * world, 0, 2 ** 31, None), ("dups", 5, -3000, 3000, 2),
                                 ("one_partition", 1, 0, 1000, 0)):
         def make(r):
@@ -41,6 +48,20 @@ def main():
         res = shuffle.reduce_by_key([torch.from_numpy(x).to(dev) for x in ks],
                                     [torch.from_numpy(x).to(dev) for x in vs], P, "sum", sub_bits=sb)
         mine = [(p, k.cpu().numpy(), v.cpu().numpy()) for p, k, v in res]
+        if px is not None:
+            # fused scatter + exchange must deliver bit-identical receive buffers to the NCCL alltoallv
+            sb_eff = shuffle.choose_sub_bits(n * world, P) if sb is None else sb
+            kd = [torch.from_numpy(x).to(dev) for x in ks]
+            vd = [torch.from_numpy(x).to(dev) for x in vs]
+            rx_nccl = shuffle.exchange(shuffle.map_side(kd, vd, P, None, False, sb_eff))
+            rx_peer = peer.map_side_push(px, kd, vd, P, None, sb_eff)
+            same = (torch.equal(rx_nccl.keys, rx_peer.keys) and torch.equal(rx_nccl.vals, rx_peer.vals)
+                    and torch.equal(rx_nccl.seg, rx_peer.seg) and rx_nccl.part_first == rx_peer.part_first)
+            flags = [None] * world
+            dist.all_gather_object(flags, bool(same))
+            if rank == 0:
+                print("case %-14s peer-memory push == NCCL alltoallv on every rank: %s" % (case, all(flags)))
+                ok_all &= all(flags)
         gathered = [None] * world
         dist.all_gather_object(gathered, mine)
         # groupByKey: values = global row ids so the (rank, split, position) order is checkable

@@ -122,6 +122,38 @@ def test_reduce_with_thresholds_and_sub_buckets():
         assert np.array_equal(gv[o1], want[p][1][o2])
 
 
+def test_pointer_mode_scatter_equals_plain_scatter():
+    """dpk_partition_scatter_ptrs (the fused scatter + exchange entry point) with pointers that
+    happen to be local: two chunks interleaved into one bucket-major buffer, bit-identical to
+    the plain multi-chunk scatter."""
+    from dpark_b200 import shuffle
+    rng = np.random.default_rng(99)
+    n, P, sb = 500000, 4, 3
+    F = P << sb
+    k = rng.integers(-2 ** 40, 2 ** 40, n, dtype=np.int64)
+    v = np.arange(n, dtype=np.int64)
+    cut = 123457
+    kc = [dev(k[:cut]), dev(k[cut:])]
+    vc = [dev(v[:cut]), dev(v[cut:])]
+    mo = shuffle.map_side(kc, vc, P, sub_bits=sb)
+    counts, wss = [], []
+    for x in kc:
+        c, ws = nv().partition_count(x, P, sub_bits=sb)
+        counts.append(c)
+        wss.append(ws)
+    cm = torch.stack(counts)
+    off = torch.zeros(F + 1, dtype=torch.int64, device="cuda")
+    off[1:] = torch.cumsum(cm.sum(0), 0)
+    base = off[:-1].unsqueeze(0) + (torch.cumsum(cm, 0) - cm)
+    ok = torch.empty(n, dtype=torch.int64, device="cuda")
+    ov = torch.empty(n, dtype=torch.int64, device="cuda")
+    for m in range(2):
+        kp = (ok.data_ptr() + base[m] * 8).contiguous()
+        vp = (ov.data_ptr() + base[m] * 8).contiguous()
+        nv().partition_scatter_ptrs(kc[m], vc[m], P, kp, vp, wss[m], sub_bits=sb)
+    assert torch.equal(ok, mo.keys) and torch.equal(ov, mo.vals) and torch.equal(off, mo.offsets)
+
+
 def test_choose_sub_bits_bounds():
     from dpark_b200 import shuffle
     assert shuffle.choose_sub_bits(1000, 8) == 0
