@@ -438,7 +438,7 @@ static inline int grid_cap(int64_t items, int per_cta, int waves) {
 
 int g_reduce_impl = 2;  // dpk_set_option("reduce_impl", 0|1|2)
 
-constexpr int AG_MAX_SB2 = 8;        // at most 256 fine buckets per first-level bucket
+constexpr int AG_MAX_SB2 = 10;       // at most 1024 fine buckets per first-level bucket
 int g_agg_target_rows = 2048;        // rows per fine bucket the split aims for (table load <= 0.5)
 
 static inline int choose_sb2(int64_t n, int32_t F) {
@@ -550,9 +550,10 @@ static int run_combine(Ctx &c, int val_kind, int64_t *out_offsets, void *ws) {
     c.part_off = out_offsets;
     // implementation 2: fine_off[F * 256 + 1] | segmented-multisplit workspace
     c.fine_off = seg_start + (int64_t)c.nsrc * c.F + 2;
-    c.fb_state = (unsigned long long *)(c.fine_off + ((int64_t)c.F << AG_MAX_SB2) + 2);
-    c.seg_ws = (void *)(((uintptr_t)(c.fb_state + ((int64_t)c.F << AG_MAX_SB2) + 2) + 255) & ~(uintptr_t)255);
-    c.seg_ws_bytes = seg_multisplit_ws_bytes(c.n, c.F, 1 << AG_MAX_SB2, c.nsrc);
+    const int sb2 = choose_sb2(c.n, c.F);
+    c.fb_state = (unsigned long long *)(c.fine_off + ((int64_t)c.F << sb2) + 2);
+    c.seg_ws = (void *)(((uintptr_t)(c.fb_state + ((int64_t)c.F << sb2) + 2) + 255) & ~(uintptr_t)255);
+    c.seg_ws_bytes = seg_multisplit_ws_bytes(c.n, c.F, 1 << sb2, c.nsrc);
     // side slot: free marker + identity are written by the init below; flags cleared here
     DPK_CUDA_TRY(cudaMemsetAsync(c.side_used, 0, 16, c.st));
     DPK_CUDA_TRY(cudaMemsetAsync(c.out_counts, 0, (size_t)c.nparts * 8, c.st));
@@ -597,8 +598,8 @@ int64_t dpk_combine_workspace_bytes(int64_t n, int32_t nbuckets, int32_t nsrc) {
     if (nsrc < 1) nsrc = 1;
     return (max_slots_for(n, nbuckets) + 2) * (int64_t)sizeof(Slot) +
            ((int64_t)nbuckets + 4 + (int64_t)nbuckets * nsrc) * 8 + 64 +
-           (((int64_t)nbuckets << AG_MAX_SB2) + 4) * 16 + 512 +
-           seg_multisplit_ws_bytes(n, nbuckets, 1 << AG_MAX_SB2, nsrc);
+           (((int64_t)nbuckets << choose_sb2(n, nbuckets)) + 4) * 16 + 512 +
+           seg_multisplit_ws_bytes(n, nbuckets, 1 << choose_sb2(n, nbuckets), nsrc);
 }
 
 int dpk_combine(const void *keys, int key_kind, const int64_t *key_aux, const void *vals, int val_kind, int64_t n,
