@@ -11,7 +11,9 @@ for extra in "$@"; do
 import json
 try:
     b = json.load(open("gpurun_out/sweep_$i.json"))
-    print("  value %.3e rows/s  %.2f ms/step  e2e %.3e  scatter_frac %.3f" % (b["value"], b["ms_per_step"], b["e2e"]["value"], b["roofline"]["frac"]))
+    ms = b.get("roofline_map_scatter") or b["roofline"]
+    print("  value %.3e rows/s  %.2f ms/step  e2e %.3e  map_scatter_frac %.3f  dominant %s frac %.3f" % (
+        b["value"], b["ms_per_step"], b["e2e"]["value"], ms["frac"], b["roofline"]["kernel"][:18], b["roofline"]["frac"]))
     for k in b["kernels"][:6]:
         print("   %-14s %7.3f ms  share %.3f" % (k["kernel"], k["ms_per_step"], k["share"]))
 except Exception as e:
