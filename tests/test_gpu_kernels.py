@@ -267,3 +267,62 @@ def test_full_size_properties_1e8():
     assert sum(int(x.sum()) for _, _, x in res) == int(v.sum())
     allk = torch.cat([x for _, x, _ in res])
     assert bool((torch.sort(allk).values == uk).all())
+
+
+def _zipf_keys(n, support, s, seed):
+    """Zipf(s) ranks by inverse CDF over a finite support, pushed through an odd-multiplier
+    permutation so hot keys are not adjacent (SURVEY.md §8d, config C3 generator)."""
+    rng = np.random.default_rng(seed)
+    w = 1.0 / np.arange(1, support + 1, dtype=np.float64) ** s
+    cdf = np.cumsum(w / w.sum())
+    ranks = np.searchsorted(cdf, rng.random(n), side="left").astype(np.int64)
+    return (ranks * 2654435761 + 12345) % (1 << 40)
+
+
+def test_group_by_key_zipf_c3_shape_matches_oracle():
+    """BASELINE config 3 shape scaled down: groupByKey over Zipf(1.1) int64 keys, 64 partitions,
+    values = row index.  Per partition the same keys and, for every key, the SAME value list in
+    (map split, position) order as the oracle's ordered-group merge."""
+    from dpark_b200 import shuffle
+    n, P, M = 1_000_000, 64, 8
+    k = _zipf_keys(n, 200_000, 1.1, 2025)
+    v = np.arange(n, dtype=np.int64)
+    ks, vs = np.array_split(k, M), np.array_split(v, M)
+    mo = shuffle.map_side([dev(x) for x in ks], [dev(x) for x in vs], P)
+    rx = shuffle.exchange(mo)
+    gk, gs, ng, ov, off = shuffle.group_side(rx, P)
+    G = int(ng.item())
+    gk, gs, ov, off = gk[:G].cpu().numpy(), gs[:G + 1].cpu().numpy(), ov.cpu().numpy(), off.cpu().numpy()
+    want = orc.group_by_key(ks, vs, P)
+    first = np.searchsorted(gs[:-1], off, side="left")
+    hot = 0
+    for p in range(P):
+        wk, wo, wv = want[p]
+        g0, g1 = first[p], first[p + 1]
+        assert g1 - g0 == len(wk)
+        pos = {int(key): g for g, key in zip(range(g0, g1), gk[g0:g1])}
+        for i, key in enumerate(wk.tolist()):
+            g = pos[key]
+            assert np.array_equal(ov[gs[g]:gs[g + 1]], wv[wo[i]:wo[i + 1]])
+            hot = max(hot, int(wo[i + 1] - wo[i]))
+    assert hot > n // 20          # the skew is really there: the hottest key holds > 5 % of the rows
+
+
+def test_reduce_by_key_zipf_hot_keys_all_impls_sum_exact():
+    """Skewed reduceByKey (hot key = ~10 % of the rows): shared-memory and global atomics pile up
+    on one accumulator; sums stay exact."""
+    from dpark_b200 import shuffle
+    n, P = 2_000_000, 8
+    k = _zipf_keys(n, 100_000, 1.1, 7)
+    v = np.random.default_rng(8).integers(-5, 6, n, dtype=np.int64)
+    want = orc.reduce_by_key([k], [v], P, "sum")
+    for impl in (2, 1):
+        nv().set_option("reduce_impl", impl)
+        try:
+            got = _parts_from(shuffle.reduce_by_key([dev(k)], [dev(v)], P, "sum"))
+        finally:
+            nv().set_option("reduce_impl", 2)
+        for p in range(P):
+            o1, o2 = np.argsort(got[p][0]), np.argsort(want[p][0])
+            assert np.array_equal(got[p][0][o1], want[p][0][o2])
+            assert np.array_equal(got[p][1][o1], want[p][1][o2])
