@@ -3,10 +3,15 @@
 //
 // The L2 round trip per probe is what bounds implementations 0/1 (ncu: long-scoreboard
 // stalls on the probe loop, atomic units ~7 % busy).  Here every first-level bucket has
-// been split once more (seg_multisplit, other hash bits) into fine buckets of ~2 k
+// been split once more (seg_multisplit, other hash bits) into fine buckets of ~1.5-2 k
 // rows, and one CTA merges a fine bucket in a 4096-slot table in SHARED memory: a probe
 // costs ~30 cycles instead of ~600.  Table accesses are explicit shared-space PTX
-// (ld.volatile.shared / atom.shared.cas / red.shared.add), not generic atomics.
+// (ld.volatile.shared / atom.shared.cas / atom.shared.add), not generic atomics.
+//
+// Claim list: a row that claims a free slot appends the slot index to a per-CTA list
+// (warp-aggregated counter), so the number of distinct keys is known the moment the
+// inserts are done, the output is written by walking the list (coalesced, no sweep of
+// the 4096 slots, no block scan) and only the touched slots are reset for the next bucket.
 //
 // Output placement without atomics on the critical path: fine buckets are handed out
 // in order (atomic work counter), and the position of a fine bucket's output inside its
@@ -15,21 +20,16 @@
 // words, 2 flag bits + 62 value bits).  The partition's final count is the inclusive
 // value of its last fine bucket.
 //
-// Per fine bucket (common case, 4 block barriers): insert all rows -> count/rank the
-// occupied slots -> look back -> write the pairs out and reset the slots in the same
-// sweep (the table is clean again for the next bucket).  A fine bucket with more
-// distinct keys than the table holds takes the slow path: hash-disjoint passes (m, r),
-// rows with ((mix >> 40) & (m-1)) == r, split on demand (a probe sequence longer than
-// AG_MAX_PROBE declares a pass overflowed).
+// A fine bucket with more distinct keys than the table holds takes the slow path:
+// hash-disjoint passes (m, r), rows with ((mix >> 40) & (m-1)) == r, split on demand.
 #pragma once
 
 constexpr int AG_THREADS = 256;
 constexpr int AG_CAP = 4096;
-constexpr int AG_LIMIT = AG_CAP - AG_CAP / 8;  // upper end for "rows per fine bucket" settings
+constexpr int AG_LIMIT = AG_CAP - AG_CAP / 8;  // distinct keys a pass may hold
 constexpr int AG_MAX_PROBE = 96;
 constexpr int AG_STACK = 96;
 constexpr int AG_UNROLL = 4;
-constexpr int AG_PER = AG_CAP / AG_THREADS;     // slots each thread sweeps
 
 constexpr unsigned long long AG_FLAG_AGG = 1ull << 62;
 constexpr unsigned long long AG_FLAG_INC = 2ull << 62;
@@ -96,102 +96,76 @@ __device__ __forceinline__ unsigned long long ag_look_back(const unsigned long l
     return excl;
 }
 
-// insert one row; returns false when the probe sequence got too long (table too full)
-template <typename AccT>
-__device__ __forceinline__ bool ag_insert(uint32_t key_base, uint32_t acc_base, long long *s_acc, int op, int64_t kb,
-                                          uint64_t mx, AccT v) {
-    uint32_t h = (uint32_t)mx & (AG_CAP - 1);
-#pragma unroll 1
-    for (int steps = 0; steps < AG_MAX_PROBE; steps++) {
-        const uint32_t ka = key_base + h * 8u;
-        long long cur = sm_ld_volatile(ka);
-        if (cur == kEmpty) cur = sm_cas(ka, kEmpty, kb);   // old value: kEmpty = claimed, kb = someone else claimed it
-        if (cur == kb || cur == kEmpty) {
-            sm_apply<AccT>(op, acc_base + h * 8u, s_acc + h, v);
-            return true;
-        }
-        h = (h + 1) & (AG_CAP - 1);
-    }
-    return false;
-}
-
 struct AgShared {
-    int fb, overflow, side_used, sp;
+    int fb, overflow, side_used, sp, nclaim;
     long long side_acc;
     unsigned long long excl;
     int stack_m[AG_STACK], stack_r[AG_STACK];
-    int wsum[AG_THREADS / 32];
 };
 
-// insert the rows [r0, r1) whose pass id matches (m, r); sets sh.overflow when the table is too full
+// insert the rows [r0, r1) whose pass id matches (m, r).  Whole warps walk the rows together
+// (predicated on validity) so the claim ballot below is always converged.
 template <typename KeyT, typename ValT, typename AccT>
 __device__ __forceinline__ void ag_insert_rows(const KeyT *__restrict__ keys, const ValT *__restrict__ vals,
                                                int64_t r0, int64_t r1, int m, int r, int op, uint32_t key_base,
-                                               uint32_t acc_base, long long *s_acc, AgShared &sh) {
-    bool ok = true;
+                                               uint32_t acc_base, long long *s_acc, uint16_t *s_list, AgShared &sh) {
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
     const int64_t step = (int64_t)AG_THREADS * AG_UNROLL;
-    const int64_t nfull = (r1 - r0) / step * step;
-    for (int64_t base = r0; base < r0 + nfull; base += step) {  // AG_UNROLL independent loads in flight per thread
+    for (int64_t base = r0; base < r1; base += step) {
         KeyT kreg[AG_UNROLL];
         ValT vreg[AG_UNROLL];
 #pragma unroll
-        for (int u = 0; u < AG_UNROLL; u++) {
-            kreg[u] = keys[base + u * AG_THREADS + threadIdx.x];
-            vreg[u] = vals[base + u * AG_THREADS + threadIdx.x];
+        for (int u = 0; u < AG_UNROLL; u++) {  // AG_UNROLL independent loads in flight per thread
+            const int64_t i = base + u * AG_THREADS + threadIdx.x;
+            if (i < r1) { kreg[u] = keys[i]; vreg[u] = vals[i]; }
         }
 #pragma unroll
         for (int u = 0; u < AG_UNROLL; u++) {
-            const int64_t kb = key_bits<KeyT>(kreg[u]);
+            const int64_t i = base + u * AG_THREADS + threadIdx.x;
+            const int64_t kb = i < r1 ? key_bits<KeyT>(kreg[u]) : 0;
             const uint64_t mx = mix64((uint64_t)kb);
-            if (m > 1 && (int)((mx >> 40) & (uint64_t)(m - 1)) != r) continue;
-            if (kb == kEmpty) {
+            bool live = i < r1 && (m == 1 || (int)((mx >> 40) & (uint64_t)(m - 1)) == r);
+            if (live && kb == kEmpty) {  // the key whose bits equal the free-slot marker: side accumulator
                 sh.side_used = 1;
                 Acc<AccT>::apply(op, (int64_t *)&sh.side_acc, (AccT)vreg[u]);
-            } else {
-                ok &= ag_insert<AccT>(key_base, acc_base, s_acc, op, kb, mx, (AccT)vreg[u]);
+                live = false;
+            }
+            bool claimed = false;
+            uint32_t h = (uint32_t)mx & (AG_CAP - 1);
+            if (live) {
+                bool placed = false;
+#pragma unroll 1
+                for (int steps = 0; steps < AG_MAX_PROBE; steps++) {
+                    const uint32_t ka = key_base + h * 8u;
+                    long long cur = sm_ld_volatile(ka);
+                    if (cur == kEmpty) {
+                        cur = sm_cas(ka, kEmpty, kb);  // old value: kEmpty = we claimed it, kb = a peer did
+                        claimed = cur == kEmpty;
+                    }
+                    if (cur == kb || claimed) { placed = true; break; }
+                    h = (h + 1) & (AG_CAP - 1);
+                }
+                if (placed) sm_apply<AccT>(op, acc_base + h * 8u, s_acc + h, (AccT)vreg[u]);
+                else sh.overflow = 1;  // table too full for this pass: it will be split
+            }
+            // ---- append the newly claimed slots to the claim list (one atomic per warp)
+            const unsigned cm = __ballot_sync(0xffffffffu, claimed);
+            if (cm) {
+                const int leader = __ffs(cm) - 1;
+                int pos = 0;
+                if (lane == leader) pos = atomicAdd(&sh.nclaim, __popc(cm));
+                pos = __shfl_sync(0xffffffffu, pos, leader);
+                if (claimed) {
+                    const int at = pos + __popc(cm & lt);
+                    if (at < AG_CAP) s_list[at] = (uint16_t)h;
+                }
+                if (pos + __popc(cm) > AG_LIMIT) sh.overflow = 1;
             }
         }
-        if (!ok) sh.overflow = 1;
-        if (*(volatile int *)&sh.overflow) return;
+        // warp-uniform exit (the ballots above need whole warps)
+        if (__any_sync(0xffffffffu, *(volatile int *)&sh.overflow != 0)) return;
     }
-    for (int64_t i = r0 + nfull + threadIdx.x; i < r1; i += AG_THREADS) {  // tail
-        const int64_t kb = key_bits<KeyT>(keys[i]);
-        const uint64_t mx = mix64((uint64_t)kb);
-        if (m > 1 && (int)((mx >> 40) & (uint64_t)(m - 1)) != r) continue;
-        const AccT v = (AccT)vals[i];
-        if (kb == kEmpty) {
-            sh.side_used = 1;
-            Acc<AccT>::apply(op, (int64_t *)&sh.side_acc, v);
-        } else if (!ag_insert<AccT>(key_base, acc_base, s_acc, op, kb, mx, v)) {
-            sh.overflow = 1;
-        }
-    }
-}
-
-// count + rank the occupied slots of this thread's sweep range; returns this thread's exclusive
-// rank inside the CTA and the CTA total.  One barrier.
-__device__ __forceinline__ int ag_rank(const long long *kslot, AgShared &sh, int *tot) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int c = 0;
-#pragma unroll
-    for (int j = 0; j < AG_PER; j++) c += kslot[j] != kEmpty;
-    int inc = c;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, inc, d);
-        if (lane >= d) inc += t;
-    }
-    if (lane == 31) sh.wsum[warp] = inc;
-    __syncthreads();
-    int wbase = 0, total = 0;
-#pragma unroll
-    for (int w = 0; w < AG_THREADS / 32; w++) {
-        const int t = sh.wsum[w];
-        if (w < warp) wbase += t;
-        total += t;
-    }
-    *tot = total;
-    return wbase + inc - c;
 }
 
 template <typename KeyT, typename ValT, typename AccT>
@@ -201,82 +175,75 @@ k_smem_aggregate(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, i
                  const int64_t *__restrict__ part_offsets, KeyT *__restrict__ out_keys,
                  int64_t *__restrict__ out_vals, unsigned long long *__restrict__ out_counts,
                  unsigned long long *__restrict__ fb_state, int *__restrict__ work_counter) {
-    extern __shared__ __align__(16) long long s_dyn[];  // [AG_CAP] keys | [AG_CAP] accumulators
+    extern __shared__ __align__(16) long long s_dyn[];  // [AG_CAP] keys | [AG_CAP] accumulators | [AG_CAP] u16 claim list
     long long *s_key = s_dyn;
     long long *s_acc = s_dyn + AG_CAP;
+    uint16_t *s_list = reinterpret_cast<uint16_t *>(s_dyn + 2 * AG_CAP);
     const uint32_t key_base = (uint32_t)__cvta_generic_to_shared(s_key);
     const uint32_t acc_base = (uint32_t)__cvta_generic_to_shared(s_acc);
     __shared__ AgShared sh;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // the table is kept clean between fine buckets: every sweep that reads a slot resets it
+    // the table is kept clean between fine buckets: writing a bucket out resets exactly the slots it touched
     for (int i = threadIdx.x; i < AG_CAP; i += AG_THREADS) { s_key[i] = kEmpty; s_acc[i] = ident; }
-    if (threadIdx.x == 0) { sh.overflow = 0; sh.side_used = 0; sh.side_acc = ident; }
+    if (threadIdx.x == 0) { sh.overflow = 0; sh.side_used = 0; sh.side_acc = ident; sh.nclaim = 0; }
     for (;;) {
         if (threadIdx.x == 0) sh.fb = atomicAdd(work_counter, 1);  // in-order hand-out
-        __syncthreads();                                            // (A) also: previous sweep finished, table clean
+        __syncthreads();                                            // (A) also: previous write-out finished, table clean
         const int fb = sh.fb;
         if (fb >= nfine) break;
         const int64_t r0 = fine_off[fb], r1 = fine_off[fb + 1];
         const int p = fb / fine_per_part;
         const int first_fb = p * fine_per_part;
         const int64_t pbase = part_offsets[p];
-        unsigned long long written = 0;  // distinct pairs of this fine bucket written so far (uniform)
-        unsigned long long excl = 0;
-        bool have_excl = false;
 
         // ---- fast path: one pass over all rows
-        ag_insert_rows<KeyT, ValT, AccT>(keys, vals, r0, r1, 1, 0, op, key_base, acc_base, s_acc, sh);
+        ag_insert_rows<KeyT, ValT, AccT>(keys, vals, r0, r1, 1, 0, op, key_base, acc_base, s_acc, s_list, sh);
         __syncthreads();                                            // (B)
-        const bool slow = sh.overflow != 0;                         // uniform
-        if (!slow) {
-            long long kslot[AG_PER];
-#pragma unroll
-            for (int j = 0; j < AG_PER; j++) kslot[j] = s_key[threadIdx.x * AG_PER + j];
-            int tot;
-            const int rank = ag_rank(kslot, sh, &tot);              // (C)
-            const int side = sh.side_used ? 1 : 0;
+        if (sh.overflow == 0) {                                     // uniform
+            const int cnt = sh.nclaim, side = sh.side_used ? 1 : 0;
             if (warp == 0) {
-                if (lane == 0) atomicExch(&fb_state[fb], AG_FLAG_AGG | (unsigned long long)(tot + side));
+                if (lane == 0) atomicExch(&fb_state[fb], AG_FLAG_AGG | (unsigned long long)(cnt + side));
                 const unsigned long long e = ag_look_back(fb_state, first_fb, fb);
                 if (lane == 0) {
                     sh.excl = e;
-                    atomicExch(&fb_state[fb], AG_FLAG_INC | (e + (unsigned long long)(tot + side)));
-                    if (fb == first_fb + fine_per_part - 1) out_counts[p] = e + (unsigned long long)(tot + side);
+                    atomicExch(&fb_state[fb], AG_FLAG_INC | (e + (unsigned long long)(cnt + side)));
+                    if (fb == first_fb + fine_per_part - 1) out_counts[p] = e + (unsigned long long)(cnt + side);
                 }
             }
             __syncthreads();                                        // (D)
-            int64_t dst = pbase + (int64_t)sh.excl + rank;
-#pragma unroll
-            for (int j = 0; j < AG_PER; j++) {
-                if (kslot[j] != kEmpty) {
-                    const int s = threadIdx.x * AG_PER + j;
-                    out_keys[dst] = key_from_bits<KeyT>(kslot[j]);
-                    out_vals[dst] = s_acc[s];
-                    s_key[s] = kEmpty;
-                    s_acc[s] = ident;
-                    dst++;
-                }
+            const int64_t obase = pbase + (int64_t)sh.excl;
+            for (int j = threadIdx.x; j < cnt; j += AG_THREADS) {   // coalesced: list order is output order
+                const int s = s_list[j];
+                out_keys[obase + j] = key_from_bits<KeyT>(s_key[s]);
+                out_vals[obase + j] = s_acc[s];
+                s_key[s] = kEmpty;
+                s_acc[s] = ident;
             }
-            if (side && threadIdx.x == 0) {
-                out_keys[pbase + (int64_t)sh.excl + tot] = key_from_bits<KeyT>(kEmpty);
-                out_vals[pbase + (int64_t)sh.excl + tot] = sh.side_acc;
-                sh.side_used = 0;
-                sh.side_acc = ident;
+            if (threadIdx.x == 0) {
+                if (side) {
+                    out_keys[obase + cnt] = key_from_bits<KeyT>(kEmpty);
+                    out_vals[obase + cnt] = sh.side_acc;
+                    sh.side_used = 0;
+                    sh.side_acc = ident;
+                }
+                sh.nclaim = 0;
             }
             continue;  // barrier (A) of the next iteration orders the resets before the next inserts
         }
 
         // ---- slow path: hash-disjoint passes, split on demand
+        unsigned long long written = 0, excl = 0;  // uniform
+        bool have_excl = false;
         if (threadIdx.x == 0) { sh.stack_m[0] = 2; sh.stack_r[0] = 0; sh.stack_m[1] = 2; sh.stack_r[1] = 1; sh.sp = 2; }
         __syncthreads();
         while (sh.sp > 0) {
             __syncthreads();  // everyone has seen sp > 0
             const int m = sh.stack_m[sh.sp - 1], r = sh.stack_r[sh.sp - 1];
             __syncthreads();
-            if (threadIdx.x == 0) { sh.sp--; sh.overflow = 0; sh.side_used = 0; sh.side_acc = ident; }
+            if (threadIdx.x == 0) { sh.sp--; sh.overflow = 0; sh.side_used = 0; sh.side_acc = ident; sh.nclaim = 0; }
             for (int i = threadIdx.x; i < AG_CAP; i += AG_THREADS) { s_key[i] = kEmpty; s_acc[i] = ident; }
             __syncthreads();
-            ag_insert_rows<KeyT, ValT, AccT>(keys, vals, r0, r1, m, r, op, key_base, acc_base, s_acc, sh);
+            ag_insert_rows<KeyT, ValT, AccT>(keys, vals, r0, r1, m, r, op, key_base, acc_base, s_acc, s_list, sh);
             __syncthreads();
             if (sh.overflow) {  // uniform after the barrier: split this pass in two and retry
                 if (threadIdx.x == 0 && sh.sp + 2 <= AG_STACK) {
@@ -286,12 +253,7 @@ k_smem_aggregate(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, i
                 __syncthreads();
                 continue;
             }
-            long long kslot[AG_PER];
-#pragma unroll
-            for (int j = 0; j < AG_PER; j++) kslot[j] = s_key[threadIdx.x * AG_PER + j];
-            int tot;
-            const int rank = ag_rank(kslot, sh, &tot);
-            const int side = sh.side_used ? 1 : 0;
+            const int cnt = sh.nclaim, side = sh.side_used ? 1 : 0;
             if (!have_excl) {  // multi-pass buckets publish only their inclusive value, at the end
                 if (warp == 0) {
                     const unsigned long long e = ag_look_back(fb_state, first_fb, fb);
@@ -301,20 +263,17 @@ k_smem_aggregate(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, i
                 excl = sh.excl;
                 have_excl = true;
             }
-            int64_t dst = pbase + (int64_t)(excl + written) + rank;
-#pragma unroll
-            for (int j = 0; j < AG_PER; j++) {
-                if (kslot[j] != kEmpty) {
-                    out_keys[dst] = key_from_bits<KeyT>(kslot[j]);
-                    out_vals[dst] = s_acc[threadIdx.x * AG_PER + j];
-                    dst++;
-                }
+            const int64_t obase = pbase + (int64_t)(excl + written);
+            for (int j = threadIdx.x; j < cnt; j += AG_THREADS) {
+                const int s = s_list[j];
+                out_keys[obase + j] = key_from_bits<KeyT>(s_key[s]);
+                out_vals[obase + j] = s_acc[s];
             }
             if (side && threadIdx.x == 0) {
-                out_keys[pbase + (int64_t)(excl + written) + tot] = key_from_bits<KeyT>(kEmpty);
-                out_vals[pbase + (int64_t)(excl + written) + tot] = sh.side_acc;
+                out_keys[obase + cnt] = key_from_bits<KeyT>(kEmpty);
+                out_vals[obase + cnt] = sh.side_acc;
             }
-            written += (unsigned long long)(tot + side);
+            written += (unsigned long long)(cnt + side);
             __syncthreads();
         }
         // leave the table clean and publish the inclusive value
@@ -322,7 +281,7 @@ k_smem_aggregate(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, i
         if (warp == 0) {
             unsigned long long e = have_excl ? excl : ag_look_back(fb_state, first_fb, fb);
             if (lane == 0) {
-                sh.overflow = 0; sh.side_used = 0; sh.side_acc = ident;
+                sh.overflow = 0; sh.side_used = 0; sh.side_acc = ident; sh.nclaim = 0;
                 atomicExch(&fb_state[fb], AG_FLAG_INC | (e + written));
                 if (fb == first_fb + fine_per_part - 1) out_counts[p] = e + written;
             }

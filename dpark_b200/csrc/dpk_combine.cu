@@ -489,7 +489,7 @@ static int dispatch_op(const Ctx &c) {
         int grid = sm_count() * 8;
         if (grid > nfine) grid = nfine;
         auto agg = k_smem_aggregate<KeyT, ValT, AccT>;
-        const int agg_smem = AG_CAP * 16;
+        const int agg_smem = AG_CAP * 16 + AG_CAP * 2;  // keys | accumulators | claim list
         DPK_CUDA_TRY(cudaFuncSetAttribute(agg, cudaFuncAttributeMaxDynamicSharedMemorySize, agg_smem));
         DPK_CUDA_TRY(cudaMemsetAsync(c.fb_state, 0, (size_t)nfine * 8, c.st));
         DPK_LAUNCH("smem_aggregate", c.st, agg<<<grid, AG_THREADS, agg_smem, c.st>>>(

@@ -1,0 +1,65 @@
+#!/usr/bin/env python
+"""BASELINE config 1 (examples/wc.py shape) through the operator surface on the GPU:
+1 M lines x 10 tokens from a 50 k-word vocabulary `w<i>` with Zipf(1.0) frequencies,
+4 input partitions, reduceByKey(+, numSplits=6), saveAsTextFile.  Reports where the time goes
+(the upstream tokeniser is Python, as in the reference: the end-to-end number is host-bound)
+and checks the word counts against a plain Python Counter."""
+import collections
+import os
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    lines_n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
+    sys.argv = sys.argv[:1]
+    rng = np.random.default_rng(1)
+    vocab = 50_000
+    w = 1.0 / np.arange(1, vocab + 1)
+    cdf = np.cumsum(w / w.sum())
+    ids = np.searchsorted(cdf, rng.random(lines_n * 10)).reshape(lines_n, 10)
+    tmp = tempfile.mkdtemp(prefix="dpk_wc_")
+    inp = os.path.join(tmp, "in.txt")
+    with open(inp, "w") as f:
+        for row in ids:
+            f.write(" ".join("w%d" % i for i in row) + "\n")
+    from dpark_b200 import DparkContext
+    from dpark_b200 import _native as nv
+    dc = DparkContext("local")
+
+    def fm(x):
+        for wd in x.strip().split():
+            yield (wd, 1)
+
+    out = os.path.join(tmp, "out")
+    t0 = time.perf_counter()
+    rdd = dc.textFile(inp, numSplits=4).flatMap(fm)
+    sh = rdd.reduceByKey(lambda x, y: x + y, numSplits=6)
+    l0 = nv.launch_count()
+    t1 = time.perf_counter()
+    sh._materialize()                      # ingest (Python tokeniser + columnarise) + GPU shuffle
+    t2 = time.perf_counter()
+    sh.map(lambda x: " ".join(list(map(str, x)))).saveAsTextFile(out, overwrite=False)
+    t3 = time.perf_counter()
+    got = {}
+    for fn in sorted(os.listdir(out)):
+        for line in open(os.path.join(out, fn)):
+            k, c = line.split()
+            got[k] = int(c)
+    want = collections.Counter("w%d" % i for i in ids.ravel())
+    assert got == dict(want), "word counts differ"
+    rows = lines_n * 10
+    print("wc: %d lines, %d tokens, %d distinct words, 6 partitions -> counts identical to a Python Counter" %
+          (lines_n, rows, len(got)))
+    print("  ingest + GPU shuffle %.2f s, egress + save %.2f s, total %.2f s (%.2e tokens/s end to end); "
+          "%d kernel launches" % (t2 - t1, t3 - t2, t3 - t0, rows / (t3 - t0), nv.launch_count() - l0))
+
+
+if __name__ == "__main__":
+    main()
