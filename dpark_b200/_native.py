@@ -181,11 +181,15 @@ def partition_workspace(nbuckets, device):
     return torch.empty(nbytes, dtype=torch.uint8, device=device)
 
 
-def _kk(keys, prehashed, row_hash):
-    return K_ROWID if row_hash is not None else key_kind(keys, prehashed)
+K_UNORDERED = 0x100   # DPK_K_UNORDERED: rows of a bucket may come out in any order
 
 
-def partition_count(keys, P, thresholds=None, prehashed=False, sub_bits=0, ws=None, row_hash=None):
+def _kk(keys, prehashed, row_hash, unordered=False):
+    kk = K_ROWID if row_hash is not None else key_kind(keys, prehashed)
+    return kk | K_UNORDERED if (unordered and kk >= 0) else kk
+
+
+def partition_count(keys, P, thresholds=None, prehashed=False, sub_bits=0, ws=None, row_hash=None, unordered=False):
     """Rows per bucket of one chunk; returns (counts[P << sub_bits] int64 device, ws)."""
     _need_cuda(keys, row_hash)
     F = P << sub_bits
@@ -193,36 +197,36 @@ def partition_count(keys, P, thresholds=None, prehashed=False, sub_bits=0, ws=No
     if ws is None:
         ws = partition_workspace(F, keys.device)
     counts = torch.empty(F, dtype=torch.int64, device=keys.device)
-    _check(lib().dpk_partition_count(_ptr(keys), _kk(keys, prehashed, row_hash), _ptr(row_hash), keys.numel(), P,
+    _check(lib().dpk_partition_count(_ptr(keys), _kk(keys, prehashed, row_hash, unordered), _ptr(row_hash), keys.numel(), P,
                                      _ptr(thr), nthr,
                                      sub_bits, _ptr(counts), _ptr(ws), ws.numel(), _stream()))
     return counts, ws
 
 
 def partition_scatter(keys, vals, P, bucket_base, out_keys, out_vals, ws, thresholds=None, prehashed=False,
-                      sub_bits=0, row_hash=None):
+                      sub_bits=0, row_hash=None, unordered=False):
     _need_cuda(keys, vals, bucket_base, out_keys, out_vals, ws, row_hash)
     thr, nthr = _thr(thresholds, keys.device)
     vb = 0 if vals is None else vals.element_size()
-    _check(lib().dpk_partition_scatter(_ptr(keys), _kk(keys, prehashed, row_hash), _ptr(row_hash), _ptr(vals), vb,
+    _check(lib().dpk_partition_scatter(_ptr(keys), _kk(keys, prehashed, row_hash, unordered), _ptr(row_hash), _ptr(vals), vb,
                                        keys.numel(), P,
                                        _ptr(thr), nthr, sub_bits, _ptr(bucket_base), _ptr(out_keys),
                                        _ptr(out_vals), _ptr(ws), ws.numel(), _stream()))
 
 
 def partition_scatter_ptrs(keys, vals, P, key_ptrs, val_ptrs, ws, thresholds=None, prehashed=False, sub_bits=0,
-                           row_hash=None):
+                           row_hash=None, unordered=False):
     """Fused scatter + exchange: bucket b of this chunk is written through key_ptrs[b] / val_ptrs[b]
     (device int64 tensors holding absolute device addresses, possibly peer-GPU memory)."""
     _need_cuda(keys, vals, key_ptrs, val_ptrs, ws, row_hash)
     thr, nthr = _thr(thresholds, keys.device)
     vb = 0 if vals is None else vals.element_size()
-    _check(lib().dpk_partition_scatter_ptrs(_ptr(keys), _kk(keys, prehashed, row_hash), _ptr(row_hash), _ptr(vals),
+    _check(lib().dpk_partition_scatter_ptrs(_ptr(keys), _kk(keys, prehashed, row_hash, unordered), _ptr(row_hash), _ptr(vals),
                                             vb, keys.numel(), P, _ptr(thr), nthr, sub_bits, _ptr(key_ptrs),
                                             _ptr(val_ptrs), _ptr(ws), ws.numel(), _stream()))
 
 
-def partition(keys, vals, P, thresholds=None, prehashed=False, sub_bits=0, row_hash=None):
+def partition(keys, vals, P, thresholds=None, prehashed=False, sub_bits=0, row_hash=None, unordered=False):
     """Stable hash-partition of one chunk (ShuffleMapTask._run, dpark/task.py:209-226).
     Returns (out_keys, out_vals, offsets[(P << sub_bits) + 1] int64 device)."""
     _need_cuda(keys, vals, row_hash)
@@ -236,7 +240,7 @@ def partition(keys, vals, P, thresholds=None, prehashed=False, sub_bits=0, row_h
     out_vals = None if vals is None else torch.empty_like(vals)
     offsets = torch.empty(F + 1, dtype=torch.int64, device=keys.device)
     vb = 0 if vals is None else vals.element_size()
-    _check(lib().dpk_partition(_ptr(keys), _kk(keys, prehashed, row_hash), _ptr(row_hash), _ptr(vals), vb,
+    _check(lib().dpk_partition(_ptr(keys), _kk(keys, prehashed, row_hash, unordered), _ptr(row_hash), _ptr(vals), vb,
                                keys.numel(), P,
                                _ptr(thr), nthr, sub_bits, _ptr(out_keys), _ptr(out_vals), _ptr(offsets),
                                _ptr(ws), ws.numel(), _stream()))

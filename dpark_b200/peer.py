@@ -42,13 +42,13 @@ class PeerExchange(object):
         self.hk.barrier()
 
 
-def map_side_push(px, key_chunks, val_chunks, P, thresholds=None, sub_bits=0):
+def map_side_push(px, key_chunks, val_chunks, P, thresholds=None, sub_bits=0, unordered=True):
     """Map side + exchange in one pass: returns the Received view of THIS rank's buffer."""
     G, rank, dev = px.world, px.rank, px.device
     F = P << sub_bits
     counts, wss = [], []
     for k in key_chunks:
-        c, ws = nv.partition_count(k, P, thresholds, False, sub_bits)
+        c, ws = nv.partition_count(k, P, thresholds, False, sub_bits, None, None, unordered)
         counts.append(c)
         wss.append(ws)
     cm = torch.stack(counts)                                        # [M, F] rows per chunk and bucket
@@ -79,7 +79,7 @@ def map_side_push(px, key_chunks, val_chunks, P, thresholds=None, sub_bits=0):
     for m, (k, v) in enumerate(zip(key_chunks, val_chunks)):
         off = dst_off + chunk_off[m]
         nv.partition_scatter_ptrs(k, v, P, (kbase + off * ksz).contiguous(), (vbase + off * vsz).contiguous(),
-                                  wss[m], thresholds, False, sub_bits)
+                                  wss[m], thresholds, False, sub_bits, None, unordered)
     px.barrier()                                                    # every peer's stores have landed
     b0, b1 = blocks[rank], blocks[rank + 1]
     nrecv = int(R[:, rank].sum().item())

@@ -55,7 +55,8 @@ class MapOutput(object):
         self.keys, self.vals, self.offsets, self.P, self.sub_bits = keys, vals, offsets, P, sub_bits
 
 
-def map_side(key_chunks, val_chunks, P, thresholds=None, prehashed=False, sub_bits=0, row_hash=None):
+def map_side(key_chunks, val_chunks, P, thresholds=None, prehashed=False, sub_bits=0, row_hash=None,
+             unordered=False):
     """Hash-partition all local map splits into ONE bucket-major buffer.
 
     key_chunks/val_chunks: lists of CUDA tensors (the rank's map splits in map_id
@@ -63,12 +64,12 @@ def map_side(key_chunks, val_chunks, P, thresholds=None, prehashed=False, sub_bi
     OrderedGroupByDiskHashMerger produces (dpark/shuffle.py:626-646)."""
     F = P << sub_bits
     if len(key_chunks) == 1:
-        k, v, off = nv.partition(key_chunks[0], val_chunks[0], P, thresholds, prehashed, sub_bits, row_hash)
+        k, v, off = nv.partition(key_chunks[0], val_chunks[0], P, thresholds, prehashed, sub_bits, row_hash, unordered)
         return MapOutput(k, v, off, P, sub_bits)
     dev = key_chunks[0].device
     counts, wss = [], []
     for k in key_chunks:
-        c, ws = nv.partition_count(k, P, thresholds, prehashed, sub_bits, None, row_hash)
+        c, ws = nv.partition_count(k, P, thresholds, prehashed, sub_bits, None, row_hash, unordered)
         counts.append(c)
         wss.append(ws)
     cm = torch.stack(counts)                       # [M, F]
@@ -83,7 +84,7 @@ def map_side(key_chunks, val_chunks, P, thresholds=None, prehashed=False, sub_bi
     out_v = torch.empty(n, dtype=val_chunks[0].dtype, device=dev) if has_v else None
     for m, (k, v) in enumerate(zip(key_chunks, val_chunks)):
         nv.partition_scatter(k, v, P, base[m].contiguous(), out_k, out_v, wss[m], thresholds, prehashed, sub_bits,
-                             row_hash)
+                             row_hash, unordered)
     return MapOutput(out_k, out_v, offsets, P, sub_bits)
 
 
@@ -229,7 +230,7 @@ class HostShuffle(object):
             from . import peer
             rx = peer.map_side_push(self.peer_exchange, kc, vc, self.P, self.thresholds, self.sub_bits)
         else:
-            mo = map_side(kc, vc, self.P, self.thresholds, False, self.sub_bits)
+            mo = map_side(kc, vc, self.P, self.thresholds, False, self.sub_bits, unordered=True)
             rx = exchange(mo, self.group)
         ok, ov, po, cnt = reduce_side(rx, self.op, self.P, self.thresholds)
         po_h, cnt_h = po.cpu().tolist(), cnt.cpu().tolist()      # the one host sync: result sizes
@@ -256,7 +257,7 @@ def reduce_by_key(key_chunks, val_chunks, P, op="sum", thresholds=None, group=No
         import torch.distributed as dist
         G = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
         sub_bits = choose_sub_bits(sum(int(k.numel()) for k in key_chunks) * G, P)
-    mo = map_side(key_chunks, val_chunks, P, thresholds, False, sub_bits)
+    mo = map_side(key_chunks, val_chunks, P, thresholds, False, sub_bits, unordered=True)
     rx = exchange(mo, group)
     ok, ov, po, cnt = reduce_side(rx, op, P, thresholds)
     po_h, cnt_h = po.cpu().tolist(), cnt.cpu().tolist()

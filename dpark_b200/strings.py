@@ -58,7 +58,7 @@ def reduce_by_key_bytes(splits, key_kind, P, thresholds, op, dev, res):
     rep = nv.dict_encode(d_data, d_off, h)
     # map side: bucket-major by the hash of the string each id stands for; reduce side: merge per id
     sb = shuffle.choose_sub_bits(n, P)
-    mo = shuffle.map_side([rep], [d_vals], P, thresholds, False, sb, row_hash=h)
+    mo = shuffle.map_side([rep], [d_vals], P, thresholds, False, sb, row_hash=h, unordered=True)
     rx = shuffle.exchange(mo)
     ok, ov, off, cnt = nv.combine(rx.keys, rx.vals, op, P, rx.seg.contiguous(), rx.part_first, rx.nparts,
                                   thresholds, sb, row_hash=h)

@@ -43,6 +43,10 @@ enum {
  * ints and floats -> Python's builtin hash(); see dpk_hash_keys. */
 enum { DPK_K_I64 = 0, DPK_K_I32 = 1, DPK_K_F64 = 2, DPK_K_U64 = 3, DPK_K_F32 = 4,
        DPK_K_ROWID = 5 /* int64 ids of representative rows; their hash is looked up in key_aux */ };
+/* OR-able into key_kind of the dpk_partition* calls (not with -1): the caller does not need the rows
+ * of a bucket in input order (reduceByKey merges them anyway; groupByKey does need the order), which
+ * lets the multisplit rank rows with one native shared-memory atomic instead of a warp match. */
+#define DPK_K_UNORDERED 0x100
 /* value column kinds */
 enum { DPK_V_I64 = 0, DPK_V_F64 = 1, DPK_V_I32 = 2, DPK_V_F32 = 3 };
 /* combiner ops a reduceByKey(func) lowers to (dpark/rdd.py:543-545 builds

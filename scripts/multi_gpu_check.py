@@ -54,7 +54,7 @@ def main():
             kd = [torch.from_numpy(x).to(dev) for x in ks]
             vd = [torch.from_numpy(x).to(dev) for x in vs]
             rx_nccl = shuffle.exchange(shuffle.map_side(kd, vd, P, None, False, sb_eff))
-            rx_peer = peer.map_side_push(px, kd, vd, P, None, sb_eff)
+            rx_peer = peer.map_side_push(px, kd, vd, P, None, sb_eff, unordered=False)   # stable mode: bit-comparable
             same = (torch.equal(rx_nccl.keys, rx_peer.keys) and torch.equal(rx_nccl.vals, rx_peer.vals)
                     and torch.equal(rx_nccl.seg, rx_peer.seg) and rx_nccl.part_first == rx_peer.part_first)
             flags = [None] * world
