@@ -43,14 +43,17 @@ def parse():
     ap.add_argument("--parts-per-gpu", type=int, default=8)
     ap.add_argument("--map-splits", type=int, default=8)
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-depth", type=int, default=2, help="batches in flight in the e2e leg (1 = serial)")
     ap.add_argument("--cpu-sample-rows", type=int, default=4_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--reduce-impl", type=int, default=2, help="A/B switch of the reduce-side kernel (dpk_set_option)")
     ap.add_argument("--sub-bits", type=int, default=-1, help="override the sub-bucket bits (default: auto)")
     ap.add_argument("--agg-target-rows", type=int, default=0, help="override rows per fine bucket (dpk_set_option)")
     ap.add_argument("--count-mode", type=int, default=1, help="A/B switch of the histogram pass (dpk_set_option)")
-    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
-                    help="N>1: fused scatter into peer memory over NVLink, or a separate NCCL alltoallv")
+    ap.add_argument("--scatter-items", type=int, default=0, help="A/B: rows per thread and tile of the multisplit (8|16)")
+    ap.add_argument("--exchange", default="push", choices=["push", "fused", "peer", "nccl"],
+                    help="N>1: push = local scatter, then one kernel pushing each peer's block over NVLink; "
+                         "fused (alias peer) = the scatter kernel stores into peer memory; nccl = alltoallv")
     return ap.parse_args()
 
 
@@ -61,6 +64,7 @@ def workload_config(args, world):
                     % (args.rows_per_gpu, args.map_splits, args.parts_per_gpu),
         "rows_per_gpu": args.rows_per_gpu, "partitions": args.parts_per_gpu * world,
         "map_splits_per_gpu": args.map_splits, "parallelism": "dp%d" % world,
+        "exchange": None if world == 1 else args.exchange,
         "l2_policy": "inputs_larger_than_l2 (1.6 GB of rows per GPU per step vs 126 MB L2)",
         "sub_buckets_per_partition": 1 << __import__("dpark_b200.shuffle", fromlist=["x"]).choose_sub_bits(
             args.rows_per_gpu * world, args.parts_per_gpu * world),
@@ -265,25 +269,30 @@ def run_ours(args):
     if args.agg_target_rows > 0:
         nv.set_option("agg_target_rows", args.agg_target_rows)
     nv.set_option("count_mode", args.count_mode)
+    if args.scatter_items:
+        nv.set_option("scatter_items", args.scatter_items)
 
     ex_events = []
     # exchange: "peer" = the scatter kernel stores rows straight into the owning GPU's receive buffer
     # (NVLink peer memory, dpark_b200/peer.py); "nccl" = separate alltoallv (shuffle.exchange)
     px = None
-    if world > 1 and args.exchange == "peer":
+    if world > 1 and args.exchange != "nccl":
         try:
             from dpark_b200 import peer
-            px = peer.PeerExchange(int(n * 1.25) + (1 << 20), torch.int64, torch.int64, dev)
+            px = peer.PeerExchange(int(n * 1.25) + (1 << 20), torch.int64, torch.int64, dev,
+                                   mode="push" if args.exchange == "push" else "fused")
         except Exception as e:  # symmetric memory unavailable on this box/build: say so, use NCCL
             sys.stderr.write("peer exchange unavailable (%s: %s); using NCCL alltoallv\n" % (type(e).__name__, e))
             px = None
 
     def step():
-        if px is not None:
+        if px is not None and px.mode == "fused":
             rx = peer.map_side_push(px, kc, vc, P, None, sub_bits)
             return shuffle.reduce_side(rx, "sum", P)
         mo = shuffle.map_side(kc, vc, P, None, False, sub_bits, unordered=True)
-        if world > 1:      # bracket the one collective (alltoallv) for the NVLink roofline
+        if px is not None:
+            rx = peer.exchange_push(px, mo)
+        elif world > 1:    # bracket the one collective (alltoallv) for the NVLink roofline
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             rx = shuffle.exchange(mo)
@@ -336,14 +345,17 @@ def run_ours(args):
                              "frac": gbs / 770.0, "ms_per_step": float(ex_ms),
                              "peak_source": "measured peer copy on this pool (B200_PROFILING.md); nominal 900"}
     if world > 1 and px is not None:
-        # fused: the NVLink traffic rides inside k_part_scatter; rate = bytes sent / time of those kernels
-        sc_ms = sum(t for name, t in nv.prof_collect() if name == "part_scatter") / args.steps
+        # fused: the NVLink traffic rides inside k_part_scatter; push: inside k_copy_segments.
+        # rate = bytes sent / time of those kernels
+        exk = "part_scatter" if px.mode == "fused" else "copy_segments"
+        sc_ms = sum(t for name, t in nv.prof_collect() if name == exk) / args.steps
         sc = torch.tensor([sc_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(sc, op=dist.ReduceOp.MAX)
         sent = (KEY_BYTES + VAL_BYTES) * n * (world - 1) / world
         gbs = sent / (float(sc) * 1e-3) / 1e9
         roofline_exchange = {"bound": "nvlink", "kernel": "k_part_scatter storing into peer receive buffers "
-                             "(fused scatter + exchange, no separate alltoallv pass)",
+                             "(fused scatter + exchange, no separate alltoallv pass)" if px.mode == "fused" else
+                             "k_copy_segments: one launch pushing every peer's block into its receive buffer",
                              "achieved": gbs, "peak": 770.0, "unit": "GB/s per GPU per direction",
                              "frac": gbs / 770.0, "ms_per_step": float(sc),
                              "peak_source": "measured peer copy on this pool (B200_PROFILING.md); nominal 900"}
@@ -449,6 +461,41 @@ def run_ours(args):
            "steps": args.e2e_steps, "h2d_bytes_per_step": hs.h2d_bytes * world,
            "d2h_bytes_per_step": hs.d2h_bytes * world,
            "api": "dpark_b200.shuffle.HostShuffle.run (pinned host in, pinned host out)"}
+    if world == 1 and args.e2e_depth > 1:
+        # Same batches, same copies every step, but `depth` batches in flight: the H2D of batch i+1
+        # overlaps the reduce + D2H of batch i (full-duplex PCIe).  Every step still moves its own
+        # inputs in and its own result out inside the timed region.
+        h_keys, h_vals = hs.h_keys, hs.h_vals
+        d2h_serial = hs.d2h_bytes
+        hs.d_keys = hs.d_vals = None
+        torch.cuda.empty_cache()
+        st = shuffle.HostShuffleStream(n, torch.int64, torch.int64, P, "sum", splits=M, sub_bits=sub_bits,
+                                       depth=args.e2e_depth)
+        for _ in range(args.e2e_depth):
+            st.submit(h_keys, h_vals)
+        for _ in range(args.e2e_depth):
+            st.collect()
+        torch.cuda.synchronize()
+        K2 = max(args.e2e_steps, 2) * 2
+        t0 = time.perf_counter()
+        inflight = 0
+        for i in range(K2):
+            if inflight == args.e2e_depth:
+                st.collect()
+                inflight -= 1
+            st.submit(h_keys, h_vals)
+            inflight += 1
+        while inflight:
+            st.collect()
+            inflight -= 1
+        torch.cuda.synchronize()
+        pipe_step = (time.perf_counter() - t0) * 1e3 / K2
+        assert st.d2h_bytes == d2h_serial
+        e2e = {"value": n / (pipe_step * 1e-3), "unit": UNIT, "ms_per_step": pipe_step, "steps": K2,
+               "h2d_bytes_per_step": st.h2d_bytes, "d2h_bytes_per_step": st.d2h_bytes,
+               "serial_ms_per_step": e2e_step, "serial_value": n / (e2e_step * 1e-3), "depth": args.e2e_depth,
+               "api": "dpark_b200.shuffle.HostShuffleStream.submit/collect (pinned host in, pinned host out, "
+                      "%d batches in flight); serial_* = HostShuffle.run one batch at a time" % args.e2e_depth}
     clk = clocks.stop() if clocks else None
 
     cpu_baseline = None

@@ -33,7 +33,7 @@ EXPORTS = [
     "dpk_launch_count", "dpk_prof_enable", "dpk_prof_count", "dpk_prof_get",
     "dpk_dict_encode_workspace_bytes", "dpk_dict_encode", "dpk_set_option",
     "dpk_key_or", "dpk_radix_pass", "dpk_group_heads_workspace_bytes", "dpk_group_heads", "dpk_gather_i64",
-    "dpk_partition_scatter_ptrs",
+    "dpk_partition_scatter_ptrs", "dpk_copy_segments",
 ]
 
 _lib = None
@@ -67,6 +67,7 @@ def lib():
         L.dpk_partition_scatter.argtypes = [vp, ci, vp, vp, i32, i64, i32, vp, i32, i32, vp, vp, vp, vp, i64, vp]
         L.dpk_partition.argtypes = [vp, ci, vp, vp, i32, i64, i32, vp, i32, i32, vp, vp, vp, vp, i64, vp]
         L.dpk_partition_scatter_ptrs.argtypes = [vp, ci, vp, vp, i32, i64, i32, vp, i32, i32, vp, vp, vp, i64, vp]
+        L.dpk_copy_segments.argtypes = [vp, vp, vp, i32, vp]
         L.dpk_combine_workspace_bytes.argtypes = [i64, i32, i32]
         L.dpk_combine.argtypes = [vp, ci, vp, vp, ci, i64, ci, i32, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp,
                                   vp, vp, i64, vp]
@@ -224,6 +225,15 @@ def partition_scatter_ptrs(keys, vals, P, key_ptrs, val_ptrs, ws, thresholds=Non
     _check(lib().dpk_partition_scatter_ptrs(_ptr(keys), _kk(keys, prehashed, row_hash, unordered), _ptr(row_hash), _ptr(vals),
                                             vb, keys.numel(), P, _ptr(thr), nthr, sub_bits, _ptr(key_ptrs),
                                             _ptr(val_ptrs), _ptr(ws), ws.numel(), _stream()))
+
+
+def copy_segments(src_ptrs, dst_ptrs, nbytes):
+    """One launch copying nbytes[s] bytes from device address src_ptrs[s] to dst_ptrs[s] (int64 device
+    tensors; destinations may be peer-GPU memory): the exchange as block pushes over NVLink."""
+    _need_cuda(src_ptrs, dst_ptrs, nbytes)
+    if not (src_ptrs.numel() == dst_ptrs.numel() == nbytes.numel()):
+        raise ValueError("segment table columns differ in length")
+    _check(lib().dpk_copy_segments(_ptr(src_ptrs), _ptr(dst_ptrs), _ptr(nbytes), nbytes.numel(), _stream()))
 
 
 def partition(keys, vals, P, thresholds=None, prehashed=False, sub_bits=0, row_hash=None, unordered=False):

@@ -579,6 +579,11 @@ int dpk_set_option(const char *name, int64_t value) {
         g_reduce_impl = (int)value;
         return DPK_OK;
     }
+    if (strcmp(name, "scatter_items") == 0) {
+        if (value != 8 && value != 16) return fail(DPK_ERR_INVALID, "scatter_items must be 8 or 16");
+        g_scatter_items = (int)value;
+        return DPK_OK;
+    }
     if (strcmp(name, "count_mode") == 0) {
         if (value != 0 && value != 1) return fail(DPK_ERR_INVALID, "count_mode must be 0 or 1");
         g_count_mode = (int)value;

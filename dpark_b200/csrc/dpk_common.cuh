@@ -29,6 +29,7 @@ int fail(int code, const char *fmt, ...);
 #define DPK_LAUNCH_CHECK() DPK_CUDA_TRY(cudaGetLastError())
 
 int sm_count();
+extern int g_scatter_items;  // dpk_partition.cu, rows per thread and tile of the scatter (16 or 8)
 extern int g_count_mode;  // dpk_partition.cu, A/B switch of the histogram pass
 
 // every kernel launch goes through DPK_LAUNCH: counts it and, when profiling

@@ -31,6 +31,7 @@ struct NoVal {};
 // dpk_set_option("count_mode"): 1 (default) = one shared-memory atomic per row into a warp-private
 // histogram; 0 = warp peer mask + leader update (slower: measured 1.01 ms vs 0.47 ms per 1e8 rows)
 int g_count_mode = 1;
+int g_scatter_items = 16;
 
 // Segmented mode (second-level split on the reduce side): the grid runs over a
 // device-resident chunk table instead of equal row ranges; every chunk lies inside
@@ -233,15 +234,15 @@ k_part_offsets(const int64_t *__restrict__ totals, int32_t P, int64_t *__restric
 struct ScatterSmem {
     int64_t key_off, val_off, pid_off, gpos_off, tstart_off, tcount_off, whist_off, kptr_off, vptr_off, total;
 };
-static ScatterSmem scatter_smem(int kb, int vb, int32_t P, bool ptr_mode = false) {
+static ScatterSmem scatter_smem(int kb, int vb, int32_t P, bool ptr_mode, int tile) {
     ScatterSmem s;
     int64_t o = 0;
-    s.key_off = o; o += align_up((int64_t)PT_TILE * kb, 16);
-    s.val_off = o; o += align_up((int64_t)PT_TILE * vb, 16);
+    s.key_off = o; o += align_up((int64_t)tile * kb, 16);
+    s.val_off = o; o += align_up((int64_t)tile * vb, 16);
     s.gpos_off = o; o += align_up((int64_t)P * 8, 16);
     s.tstart_off = o; o += align_up((int64_t)P * 4, 16);
     s.tcount_off = o; o += align_up((int64_t)P * 4, 16);
-    s.pid_off = o; o += align_up((int64_t)PT_TILE * 2, 16);
+    s.pid_off = o; o += align_up((int64_t)tile * 2, 16);
     s.whist_off = o; o += align_up((int64_t)PT_WARPS * P * 2, 16);
     s.kptr_off = o; if (ptr_mode) o += align_up((int64_t)P * 8, 16);
     s.vptr_off = o; if (ptr_mode) o += align_up((int64_t)P * 8, 16);
@@ -249,13 +250,17 @@ static ScatterSmem scatter_smem(int kb, int vb, int32_t P, bool ptr_mode = false
     return s;
 }
 
-template <typename KeyT, typename ValT, int PRE>
-__global__ void __launch_bounds__(PT_THREADS, 2)
+// ITEMS rows per thread and tile: 16 (4096-row tiles, 2 CTAs per SM) or 8 (2048-row tiles, half the
+// registers and shared memory, 4 CTAs per SM -- more warps to hide the phase barriers; bucket runs
+// inside a tile are half as long).  The CTA's row range comes from the plan in PT_TILE units either way.
+template <typename KeyT, typename ValT, int PRE, int ITEMS>
+__global__ void __launch_bounds__(PT_THREADS, ITEMS == 16 ? 2 : 4)
 k_part_scatter(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, int64_t n, int64_t L,
                PartFn f, const int32_t *__restrict__ tile_off, int32_t T,
                const int64_t *__restrict__ bucket_base, KeyT *__restrict__ out_keys,
                ValT *__restrict__ out_vals, ScatterSmem lay, SegTab seg) {
     constexpr bool HAS_VAL = !std::is_same<ValT, NoVal>::value;
+    constexpr int TILE = PT_THREADS * ITEMS;
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_warp[PT_WARPS];
     KeyT *s_key = reinterpret_cast<KeyT *>(smem + lay.key_off);
@@ -290,22 +295,22 @@ k_part_scatter(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, int
 
     const int E = (P + PT_THREADS - 1) / PT_THREADS;  // buckets per thread in the scan
 
-    for (int64_t tile = beg; tile < end; tile += PT_TILE) {
-        const int rows = (int)min((int64_t)PT_TILE, end - tile);
+    for (int64_t tile = beg; tile < end; tile += TILE) {
+        const int rows = (int)min((int64_t)TILE, end - tile);
         for (int i = threadIdx.x; i < PT_WARPS * P; i += PT_THREADS) s_whist[i] = 0;
 
         // ---- load: warp w owns rows [w*512, w*512+512) of the tile, item j = 32 consecutive rows
-        KeyT k[PT_ITEMS];
-        ValT v[PT_ITEMS];
-        const int64_t wbase = tile + (int64_t)warp * (32 * PT_ITEMS) + lane;
+        KeyT k[ITEMS];
+        ValT v[ITEMS];
+        const int64_t wbase = tile + (int64_t)warp * (32 * ITEMS) + lane;
 #pragma unroll
-        for (int j = 0; j < PT_ITEMS; j++) {
+        for (int j = 0; j < ITEMS; j++) {
             int64_t idx = wbase + j * 32;
             k[j] = idx < end ? keys[idx] : KeyT(0);
         }
         if constexpr (HAS_VAL) {
 #pragma unroll
-            for (int j = 0; j < PT_ITEMS; j++) {
+            for (int j = 0; j < ITEMS; j++) {
                 int64_t idx = wbase + j * 32;
                 if (idx < end) v[j] = vals[idx];
             }
@@ -313,10 +318,10 @@ k_part_scatter(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, int
         __syncthreads();  // whist zeroed; previous tile's copy-out done with the staging buffers
 
         // ---- warp-level ranks (stable: lanes in order, items in order)
-        uint16_t pid[PT_ITEMS], rank[PT_ITEMS];
+        uint16_t pid[ITEMS], rank[ITEMS];
         uint16_t *wh = s_whist + warp * P;
 #pragma unroll
-        for (int j = 0; j < PT_ITEMS; j++) {
+        for (int j = 0; j < ITEMS; j++) {
             const bool ok = (wbase + j * 32) < end;
             const int p = ok ? f.bucket(key_hash<KeyT, PRE>(k[j], f)) : P;  // P = "no row"
             if (seg.unordered) {
@@ -370,7 +375,7 @@ k_part_scatter(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, int
 
         // ---- place rows at their sorted position in the staging tile
 #pragma unroll
-        for (int j = 0; j < PT_ITEMS; j++) {
+        for (int j = 0; j < ITEMS; j++) {
             const int p = pid[j];
             if (p < P) {
                 const int pos = s_tstart[p] + s_whist[warp * P + p] + rank[j];
@@ -425,13 +430,13 @@ static int dispatch_count(const void *keys, int key_kind, int64_t n, const Plan 
     return fail(DPK_ERR_UNSUPPORTED, "key kind %d is unhashable by portable_hash", key_kind);
 }
 
-template <typename KeyT, typename ValT, int PRE>
-static int launch_scatter(const void *keys, const void *vals, int64_t n, const Plan &pl, const PartFn &f,
-                          const int32_t *tile_off, const int64_t *bucket_base, void *out_keys,
-                          void *out_vals, cudaStream_t st) {
+template <typename KeyT, typename ValT, int PRE, int ITEMS>
+static int launch_scatter_items(const void *keys, const void *vals, int64_t n, const Plan &pl, const PartFn &f,
+                                const int32_t *tile_off, const int64_t *bucket_base, void *out_keys,
+                                void *out_vals, cudaStream_t st) {
     constexpr int vb = std::is_same<ValT, NoVal>::value ? 0 : (int)sizeof(ValT);
-    ScatterSmem lay = scatter_smem((int)sizeof(KeyT), vb, f.nbuckets(), pl.seg.key_ptrs != nullptr);
-    auto kern = k_part_scatter<KeyT, ValT, PRE>;
+    ScatterSmem lay = scatter_smem((int)sizeof(KeyT), vb, f.nbuckets(), pl.seg.key_ptrs != nullptr, PT_THREADS * ITEMS);
+    auto kern = k_part_scatter<KeyT, ValT, PRE, ITEMS>;
     if (lay.total > 227 * 1024)
         return fail(DPK_ERR_UNSUPPORTED, "%d buckets need %lld B of shared memory", f.nbuckets(), (long long)lay.total);
     DPK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
@@ -440,6 +445,16 @@ static int launch_scatter(const void *keys, const void *vals, int64_t n, const P
                                                                 tile_off, pl.T, bucket_base, (KeyT *)out_keys,
                                                                 (ValT *)out_vals, lay, pl.seg));
     return DPK_OK;
+}
+
+template <typename KeyT, typename ValT, int PRE>
+static int launch_scatter(const void *keys, const void *vals, int64_t n, const Plan &pl, const PartFn &f,
+                          const int32_t *tile_off, const int64_t *bucket_base, void *out_keys,
+                          void *out_vals, cudaStream_t st) {
+    // dpk_set_option("scatter_items"): 16 or 8 rows per thread and tile (A/B switch)
+    if (g_scatter_items == 8)
+        return launch_scatter_items<KeyT, ValT, PRE, 8>(keys, vals, n, pl, f, tile_off, bucket_base, out_keys, out_vals, st);
+    return launch_scatter_items<KeyT, ValT, PRE, 16>(keys, vals, n, pl, f, tile_off, bucket_base, out_keys, out_vals, st);
 }
 
 template <typename KeyT, int PRE>

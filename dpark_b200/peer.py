@@ -23,8 +23,12 @@ from .shuffle import Received, owner_blocks
 class PeerExchange(object):
     """Symmetric receive buffers (keys + values) of `capacity` rows on every rank."""
 
-    def __init__(self, capacity, key_dtype, val_dtype, device=None, group=None):
+    def __init__(self, capacity, key_dtype, val_dtype, device=None, group=None, mode="push"):
         import torch.distributed._symmetric_memory as symm
+        if mode not in ("push", "fused"):
+            raise ValueError("mode must be 'push' (scatter locally, then block pushes) or 'fused' "
+                             "(the scatter kernel stores into peer memory)")
+        self.mode = mode
         self.group = group or dist.group.WORLD
         self.rank = dist.get_rank(self.group)
         self.world = dist.get_world_size(self.group)
@@ -40,6 +44,45 @@ class PeerExchange(object):
 
     def barrier(self):
         self.hk.barrier()
+
+
+def exchange_push(px, mo):
+    """shuffle.exchange() over peer memory: the bucket-major map output `mo` stays local, and ONE
+    launch of dpk_copy_segments pushes each peer's contiguous block (keys and values) into that
+    peer's receive buffer with full-width stores.  The segment table is computed on the device from
+    the gathered counts; the only host read is the capacity check."""
+    G, rank, dev = px.world, px.rank, px.device
+    P, sb = mo.P, mo.sub_bits
+    F = P << sb
+    counts = (mo.offsets[1:] - mo.offsets[:-1]).contiguous()
+    all_counts = torch.empty(G * F, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(all_counts, counts, group=px.group)   # the MapOutputTracker
+    all_counts = all_counts.view(G, F)
+    blocks = [b << sb for b in owner_blocks(P, G)]
+    csum = torch.zeros(G, F + 1, dtype=torch.int64, device=dev)
+    csum[:, 1:] = torch.cumsum(all_counts, 1)
+    bidx = torch.tensor(blocks, dtype=torch.int64, device=dev)
+    edge = csum[:, bidx]                                              # [s][d]: first row of d's block at source s
+    R = edge[:, 1:] - edge[:, :-1]                                    # rows s sends to d
+    src_base = torch.cumsum(R, 0) - R                                 # rows of earlier sources inside d's buffer
+    recv_rows = R.sum(0).cpu().tolist()                               # the one host read
+    need, nrecv = max(recv_rows), recv_rows[rank]
+    if need > px.capacity:
+        raise RuntimeError("peer receive buffer too small: need %d rows, capacity %d" % (need, px.capacity))
+    ksz = mo.keys.element_size()
+    cols = [(mo.keys.data_ptr(), px.key_base, ksz)]
+    if mo.vals is not None:
+        cols.append((mo.vals.data_ptr(), px.val_base, mo.vals.element_size()))
+    src = torch.cat([a + edge[rank, :-1] * sz for a, _, sz in cols])
+    dst = torch.cat([base + src_base[rank] * sz for _, base, sz in cols])
+    nby = torch.cat([R[rank] * sz for _, _, sz in cols])
+    px.barrier()                                                      # nobody still reads the buffers of the last step
+    nv.copy_segments(src.contiguous(), dst.contiguous(), nby.contiguous())
+    px.barrier()                                                      # every peer's stores have landed
+    b0, b1 = blocks[rank], blocks[rank + 1]
+    seg = all_counts[:, b0:b1].contiguous()
+    vals = px.vals[:nrecv] if mo.vals is not None else None
+    return Received(px.keys[:nrecv], vals, seg, b0 >> sb, (b1 - b0) >> sb, sb)
 
 
 def map_side_push(px, key_chunks, val_chunks, P, thresholds=None, sub_bits=0, unordered=True):

@@ -228,7 +228,11 @@ class HostShuffle(object):
             vc.append(self.d_vals[a:b])
         if self.peer_exchange is not None:     # fused scatter + exchange over NVLink peer memory
             from . import peer
-            rx = peer.map_side_push(self.peer_exchange, kc, vc, self.P, self.thresholds, self.sub_bits)
+            if self.peer_exchange.mode == "fused":
+                rx = peer.map_side_push(self.peer_exchange, kc, vc, self.P, self.thresholds, self.sub_bits)
+            else:
+                rx = peer.exchange_push(self.peer_exchange, map_side(kc, vc, self.P, self.thresholds, False,
+                                                                     self.sub_bits, unordered=True))
         else:
             mo = map_side(kc, vc, self.P, self.thresholds, False, self.sub_bits, unordered=True)
             rx = exchange(mo, self.group)
@@ -246,6 +250,84 @@ class HostShuffle(object):
             d2h += c * (ok.element_size() + ov.element_size())
             res.append((rx.part_first + j, self.out_keys[a:a + c], self.out_vals[a:a + c]))
         torch.cuda.current_stream().synchronize()
+        self.d2h_bytes = d2h
+        return res
+
+
+class HostShuffleStream(object):
+    """Streaming form of HostShuffle for back-to-back batches on one GPU: `depth` batches are in
+    flight on their own CUDA streams, so the host->device copy of batch i+1 runs while batch i is
+    reduced and its result is copied back (PCIe is full duplex, the copy engines are separate).
+
+        s = HostShuffleStream(n, torch.int64, torch.int64, P)
+        s.submit(h_keys, h_vals)            # pinned host columns; returns immediately
+        s.submit(h_keys2, h_vals2)
+        parts = s.collect()                 # result of the OLDEST batch: [(partition, keys, vals)] pinned host
+    """
+
+    class _Slot(object):
+        pass
+
+    def __init__(self, n_rows, key_dtype, val_dtype, P, op="sum", splits=8, thresholds=None, device=None,
+                 sub_bits=None, depth=2):
+        self.P, self.op, self.splits, self.thresholds = P, op, splits, thresholds
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.n = n_rows
+        self.sub_bits = choose_sub_bits(n_rows, P) if sub_bits is None else sub_bits
+        self.slots = []
+        for _ in range(depth):
+            s = self._Slot()
+            s.stream = torch.cuda.Stream(device=self.device)
+            s.d_keys = torch.empty(n_rows, dtype=key_dtype, device=self.device)
+            s.d_vals = torch.empty(n_rows, dtype=val_dtype, device=self.device)
+            s.out_keys = torch.empty(n_rows, dtype=key_dtype).pin_memory()
+            s.out_vals = torch.empty(n_rows, dtype=nv.acc_dtype(val_dtype)).pin_memory()
+            s.busy = False
+            self.slots.append(s)
+        self.next_submit = 0
+        self.next_collect = 0
+        self.h2d_bytes = n_rows * (torch.empty(0, dtype=key_dtype).element_size() +
+                                   torch.empty(0, dtype=val_dtype).element_size())
+        self.d2h_bytes = 0
+
+    def submit(self, h_keys, h_vals):
+        s = self.slots[self.next_submit % len(self.slots)]
+        if s.busy:
+            raise RuntimeError("all %d slots are in flight: collect() first" % len(self.slots))
+        self.next_submit += 1
+        per = (self.n + self.splits - 1) // self.splits
+        with torch.cuda.stream(s.stream):
+            kc, vc = [], []
+            for i in range(self.splits):
+                a, b = min(self.n, i * per), min(self.n, (i + 1) * per)
+                s.d_keys[a:b].copy_(h_keys[a:b], non_blocking=True)
+                s.d_vals[a:b].copy_(h_vals[a:b], non_blocking=True)
+                kc.append(s.d_keys[a:b])
+                vc.append(s.d_vals[a:b])
+            mo = map_side(kc, vc, self.P, self.thresholds, False, self.sub_bits, unordered=True)
+            rx = exchange(mo)
+            s.result = reduce_side(rx, self.op, self.P, self.thresholds)
+            s.nparts, s.part_first = rx.nparts, rx.part_first
+        s.busy = True
+
+    def collect(self):
+        s = self.slots[self.next_collect % len(self.slots)]
+        if not s.busy:
+            raise RuntimeError("nothing in flight")
+        self.next_collect += 1
+        ok, ov, po, cnt = s.result
+        with torch.cuda.stream(s.stream):
+            po_h, cnt_h = po.cpu().tolist(), cnt.cpu().tolist()      # waits for THIS batch only
+            res, d2h = [], 0
+            for j in range(s.nparts):
+                a, c = po_h[j], cnt_h[j]
+                s.out_keys[a:a + c].copy_(ok[a:a + c], non_blocking=True)
+                s.out_vals[a:a + c].copy_(ov[a:a + c], non_blocking=True)
+                d2h += c * (ok.element_size() + ov.element_size())
+                res.append((s.part_first + j, s.out_keys[a:a + c], s.out_vals[a:a + c]))
+            s.stream.synchronize()
+        s.result = None
+        s.busy = False
         self.d2h_bytes = d2h
         return res
 

@@ -131,6 +131,16 @@ int dpk_partition_scatter_ptrs(const void *keys, int key_kind, const int64_t *ke
                                const int64_t *thresholds, int32_t nthr, int32_t sub_bits,
                                const uint64_t *key_dst_ptrs, const uint64_t *val_dst_ptrs, void *ws,
                                int64_t ws_bytes, dpk_stream_t stream);
+/* The exchange as block pushes (also replaces ShuffleFetcher, dpark/shuffle.py:309-420, and the
+ * MapOutputTracker lookup of where each bucket lives, dpark/env.py + dpark/tracker.py): after
+ * dpk_partition the rows bound for one peer are ONE contiguous block of the bucket-major buffer.
+ * Copies nseg segments in one launch: nbytes[s] bytes from the device address src_ptrs[s] to
+ * dst_ptrs[s] (all three are DEVICE arrays, so the table can be computed from the gathered counts
+ * without a host sync).  Destinations may be peer-GPU memory mapped over NVLink.  Work items
+ * rotate over the segments so that all peers receive at the same time.  nseg <= 1024; addresses
+ * and sizes of any alignment (16/8/4/1-byte accesses are chosen per item). */
+int dpk_copy_segments(const uint64_t *src_ptrs, const uint64_t *dst_ptrs, const int64_t *nbytes,
+                      int32_t nseg, dpk_stream_t stream);
 
 /* ---- a9: reduce side, DiskHashMerger._merge (dpark/shuffle.py:600-608) ----
  * combined[k] = op(combined[k], v) over the n rows fetched for the nparts reduce

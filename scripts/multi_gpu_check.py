@@ -33,7 +33,7 @@ def main():
     px = None
     try:
         from dpark_b200 import peer
-        px = peer.PeerExchange(2 * n + 4096, torch.int64, torch.int64, dev)
+        px = peer.PeerExchange(world * n + 4096, torch.int64, torch.int64, dev)   # P=1: one rank receives everything
     except Exception as e:
         if rank == 0:
             print("peer exchange unavailable:", type(e).__name__, e)
@@ -57,10 +57,14 @@ def main():
             rx_peer = peer.map_side_push(px, kd, vd, P, None, sb_eff, unordered=False)   # stable mode: bit-comparable
             same = (torch.equal(rx_nccl.keys, rx_peer.keys) and torch.equal(rx_nccl.vals, rx_peer.vals)
                     and torch.equal(rx_nccl.seg, rx_peer.seg) and rx_nccl.part_first == rx_peer.part_first)
+            # ... and so must the block push (local scatter + dpk_copy_segments)
+            rx_push = peer.exchange_push(px, shuffle.map_side(kd, vd, P, None, False, sb_eff))
+            same = (same and torch.equal(rx_nccl.keys, rx_push.keys) and torch.equal(rx_nccl.vals, rx_push.vals)
+                    and torch.equal(rx_nccl.seg, rx_push.seg) and rx_nccl.nparts == rx_push.nparts)
             flags = [None] * world
             dist.all_gather_object(flags, bool(same))
             if rank == 0:
-                print("case %-14s peer-memory push == NCCL alltoallv on every rank: %s" % (case, all(flags)))
+                print("case %-14s fused scatter == block push == NCCL alltoallv on every rank: %s" % (case, all(flags)))
                 ok_all &= all(flags)
         gathered = [None] * world
         dist.all_gather_object(gathered, mine)

@@ -1,0 +1,105 @@
+"""Host-buffer entry points (what bench.py's e2e leg times): HostShuffle.run and the
+pipelined HostShuffleStream.submit/collect must return exactly the reference's
+reduceByKey result (dpark/rdd.py:303-327 over task.py:209-226 + shuffle.py:600-608).  -m gpu."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(parts, want, P):
+    seen = set()
+    for p, k, v in parts:
+        seen.add(p)
+        k, v = k.numpy(), v.numpy()
+        o1, o2 = np.argsort(k), np.argsort(want[p][0])
+        assert np.array_equal(k[o1], want[p][0][o2])
+        assert np.array_equal(v[o1], want[p][1][o2])
+    assert seen == set(range(P))
+
+
+def _batch(seed, n, hi):
+    rng = np.random.default_rng(seed)
+    return rng.integers(-hi, hi, n, dtype=np.int64), rng.integers(-1000, 1000, n, dtype=np.int64)
+
+
+@pytest.mark.parametrize("P,splits,hi", [(8, 4, 2 ** 31), (3, 1, 5000), (1, 5, 100)])
+def test_host_shuffle_run_matches_oracle(P, splits, hi):
+    from dpark_b200 import shuffle
+    n = 300_000
+    k, v = _batch(P, n, hi)
+    hs = shuffle.HostShuffle(n, torch.int64, torch.int64, P, "sum", splits=splits)
+    hs.h_keys.copy_(torch.from_numpy(k))
+    hs.h_vals.copy_(torch.from_numpy(v))
+    want = orc.reduce_by_key(np.array_split(k, splits), np.array_split(v, splits), P, "sum")
+    for _ in range(2):                      # buffers are reused between runs
+        _check(hs.run(), want, P)
+
+
+@pytest.mark.parametrize("depth", [1, 2, 3])
+def test_host_shuffle_stream_pipelined_batches_keep_their_own_results(depth):
+    from dpark_b200 import shuffle
+    n, P, nb = 250_000, 8, 7
+    st = shuffle.HostShuffleStream(n, torch.int64, torch.int64, P, "sum", splits=4, depth=depth)
+    batches = []
+    for b in range(nb):                     # every batch differs, so a slot mix-up cannot pass
+        k, v = _batch(100 + b, n, 3000 * (b + 1))
+        batches.append((torch.from_numpy(k).pin_memory(), torch.from_numpy(v).pin_memory(),
+                        orc.reduce_by_key(np.array_split(k, 4), np.array_split(v, 4), P, "sum")))
+    inflight, done = [], 0
+    for b in range(nb):
+        if len(inflight) == depth:
+            _check(st.collect(), batches[inflight.pop(0)][2], P)
+            done += 1
+        st.submit(batches[b][0], batches[b][1])
+        inflight.append(b)
+    while inflight:
+        _check(st.collect(), batches[inflight.pop(0)][2], P)
+        done += 1
+    assert done == nb
+    assert st.h2d_bytes == n * 16
+
+
+def test_host_shuffle_stream_refuses_overrun_and_underrun():
+    from dpark_b200 import shuffle
+    n = 1000
+    st = shuffle.HostShuffleStream(n, torch.int64, torch.int64, 2, depth=1)
+    with pytest.raises(RuntimeError):
+        st.collect()
+    k = torch.arange(n, dtype=torch.int64).pin_memory()
+    st.submit(k, k)
+    with pytest.raises(RuntimeError):
+        st.submit(k, k)
+    parts = st.collect()
+    assert sum(int(kk.numel()) for _, kk, _ in parts) == n
+
+
+def test_copy_segments_moves_every_byte_at_any_alignment():
+    """dpk_copy_segments (the exchange as block pushes): segments of very different sizes and
+    16/8/4/1-byte alignments land exactly, and bytes outside the segments stay untouched."""
+    from dpark_b200 import _native as nv
+    rng = np.random.default_rng(5)
+    total = 6_000_000
+    src = torch.from_numpy(rng.integers(0, 256, total, dtype=np.uint8)).cuda()
+    dst = torch.full((total,), 7, dtype=torch.uint8, device="cuda")
+    #        src_off   dst_off   bytes
+    segs = [(0,        16,       1_000_000),      # 16-byte aligned
+            (1_000_008, 1_100_008, 800_000),      # 8-byte
+            (2_000_004, 2_100_012, 70_004),       # 4-byte
+            (2_500_001, 2_600_003, 33_333),       # bytes
+            (3_000_000, 3_000_000, 0),            # empty
+            (3_100_000, 3_200_000, 2_500_000),    # much larger than the others
+            (5_900_000, 5_900_016, 16)]
+    so = torch.tensor([src.data_ptr() + a for a, _, _ in segs], dtype=torch.int64, device="cuda")
+    do = torch.tensor([dst.data_ptr() + b for _, b, _ in segs], dtype=torch.int64, device="cuda")
+    nb = torch.tensor([c for _, _, c in segs], dtype=torch.int64, device="cuda")
+    nv.copy_segments(so, do, nb)
+    want = np.full(total, 7, dtype=np.uint8)
+    h = src.cpu().numpy()
+    for a, b, c in segs:
+        want[b:b + c] = h[a:a + c]
+    assert np.array_equal(dst.cpu().numpy(), want)
+    nv.copy_segments(so[:0], do[:0], nb[:0])      # empty table is a no-op
