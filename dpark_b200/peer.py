@@ -46,6 +46,23 @@ class PeerExchange(object):
         self.hk.barrier()
 
 
+def push_plan(all_counts, blocks, rank):
+    """Segment table of one rank's pushes, in rows (pure tensor arithmetic, any device).
+    all_counts[s][b] = rows source s holds for fine bucket b; blocks[d]..blocks[d+1] = the buckets
+    destination d owns.  Returns (send_first[d], dst_first[d], rows[d], recv_total[d]):
+    my block for d starts at row send_first[d] of my bucket-major buffer, holds rows[d] rows, and
+    lands at row dst_first[d] of d's receive buffer (source-rank-major: after the blocks of the
+    lower ranks); recv_total[d] = rows d receives from everyone."""
+    G, F = all_counts.shape
+    csum = torch.zeros(G, F + 1, dtype=torch.int64, device=all_counts.device)
+    csum[:, 1:] = torch.cumsum(all_counts, 1)
+    bidx = torch.tensor(blocks, dtype=torch.int64, device=all_counts.device)
+    edge = csum[:, bidx]                                              # [s][d]: first row of d's block at source s
+    R = edge[:, 1:] - edge[:, :-1]                                    # rows s sends to d
+    src_base = torch.cumsum(R, 0) - R                                 # rows of lower sources inside d's buffer
+    return edge[rank, :-1].contiguous(), src_base[rank].contiguous(), R[rank].contiguous(), R.sum(0)
+
+
 def exchange_push(px, mo):
     """shuffle.exchange() over peer memory: the bucket-major map output `mo` stays local, and ONE
     launch of dpk_copy_segments pushes each peer's contiguous block (keys and values) into that
@@ -59,23 +76,17 @@ def exchange_push(px, mo):
     dist.all_gather_into_tensor(all_counts, counts, group=px.group)   # the MapOutputTracker
     all_counts = all_counts.view(G, F)
     blocks = [b << sb for b in owner_blocks(P, G)]
-    csum = torch.zeros(G, F + 1, dtype=torch.int64, device=dev)
-    csum[:, 1:] = torch.cumsum(all_counts, 1)
-    bidx = torch.tensor(blocks, dtype=torch.int64, device=dev)
-    edge = csum[:, bidx]                                              # [s][d]: first row of d's block at source s
-    R = edge[:, 1:] - edge[:, :-1]                                    # rows s sends to d
-    src_base = torch.cumsum(R, 0) - R                                 # rows of earlier sources inside d's buffer
-    recv_rows = R.sum(0).cpu().tolist()                               # the one host read
+    send_first, dst_first, rows, recv_total = push_plan(all_counts, blocks, rank)
+    recv_rows = recv_total.cpu().tolist()                             # the one host read
     need, nrecv = max(recv_rows), recv_rows[rank]
     if need > px.capacity:
         raise RuntimeError("peer receive buffer too small: need %d rows, capacity %d" % (need, px.capacity))
-    ksz = mo.keys.element_size()
-    cols = [(mo.keys.data_ptr(), px.key_base, ksz)]
+    cols = [(mo.keys.data_ptr(), px.key_base, mo.keys.element_size())]
     if mo.vals is not None:
         cols.append((mo.vals.data_ptr(), px.val_base, mo.vals.element_size()))
-    src = torch.cat([a + edge[rank, :-1] * sz for a, _, sz in cols])
-    dst = torch.cat([base + src_base[rank] * sz for _, base, sz in cols])
-    nby = torch.cat([R[rank] * sz for _, _, sz in cols])
+    src = torch.cat([a + send_first * sz for a, _, sz in cols])
+    dst = torch.cat([base + dst_first * sz for _, base, sz in cols])
+    nby = torch.cat([rows * sz for _, _, sz in cols])
     px.barrier()                                                      # nobody still reads the buffers of the last step
     nv.copy_segments(src.contiguous(), dst.contiguous(), nby.contiguous())
     px.barrier()                                                      # every peer's stores have landed

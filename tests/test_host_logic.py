@@ -254,3 +254,31 @@ def test_device_bisect_and_sub_buckets_on_cpu():
         assert b.min() >= 0 and b.max() < (P << sb)
         cnt = np.bincount(b & ((1 << sb) - 1), minlength=1 << sb)
         assert cnt.min() > 0.5 * len(h) / (1 << sb)                 # sub-bucket bits are well mixed
+
+
+@pytest.mark.parametrize("G,P,sb", [(2, 8, 0), (3, 5, 1), (8, 5, 2), (4, 1, 3), (8, 64, 0)])
+def test_push_plan_reproduces_the_alltoallv_layout(G, P, sb):
+    """peer.push_plan (segment table of the block-push exchange) against a direct construction of
+    what shuffle.exchange delivers: source-rank-major, bucket-major inside, empty owners included."""
+    import torch
+    from dpark_b200 import peer, shuffle
+    rng = np.random.default_rng(G * 100 + P)
+    F = P << sb
+    counts = rng.integers(0, 7, (G, F))
+    counts[rng.random((G, F)) < 0.2] = 0
+    blocks = [b << sb for b in shuffle.owner_blocks(P, G)]
+    # rows tagged (source, bucket, position) so that any misplacement shows
+    bufs = [np.concatenate([np.array([s * 10 ** 6 + b * 1000 + i for i in range(counts[s, b])], dtype=np.int64)
+                            for b in range(F)] + [np.zeros(0, np.int64)]) for s in range(G)]
+    want = [np.concatenate([bufs[s][counts[s, :blocks[d]].sum():counts[s, :blocks[d + 1]].sum()] for s in range(G)])
+            for d in range(G)]
+    got = [np.full(len(want[d]), -1, dtype=np.int64) for d in range(G)]
+    ac = torch.from_numpy(counts.astype(np.int64))
+    for s in range(G):
+        send_first, dst_first, rows, recv_total = peer.push_plan(ac, blocks, s)
+        assert recv_total.tolist() == [len(w) for w in want]
+        for d in range(G):
+            a, b, c = int(send_first[d]), int(dst_first[d]), int(rows[d])
+            got[d][b:b + c] = bufs[s][a:a + c]
+    for d in range(G):
+        assert np.array_equal(got[d], want[d])
