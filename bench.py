@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--sub-bits", type=int, default=-1, help="override the sub-bucket bits (default: auto)")
     ap.add_argument("--agg-target-rows", type=int, default=0, help="override rows per fine bucket (dpk_set_option)")
     ap.add_argument("--count-mode", type=int, default=1, help="A/B switch of the histogram pass (dpk_set_option)")
+    ap.add_argument("--agg-wide", type=int, default=-1, help="A/B: 128-bit slot CAS in the reduce-side merge (0|1)")
     ap.add_argument("--scatter-items", type=int, default=0, help="A/B: rows per thread and tile of the multisplit (8|16)")
     ap.add_argument("--exchange", default="push", choices=["push", "fused", "peer", "nccl"],
                     help="N>1: push = local scatter, then one kernel pushing each peer's block over NVLink; "
@@ -271,6 +272,8 @@ def run_ours(args):
     nv.set_option("count_mode", args.count_mode)
     if args.scatter_items:
         nv.set_option("scatter_items", args.scatter_items)
+    if args.agg_wide >= 0:
+        nv.set_option("agg_wide", args.agg_wide)
 
     ex_events = []
     # exchange: "peer" = the scatter kernel stores rows straight into the owning GPU's receive buffer

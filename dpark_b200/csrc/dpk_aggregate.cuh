@@ -46,6 +46,16 @@ __device__ __forceinline__ long long sm_cas(uint32_t a, long long cmp, long long
     asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "r"(a), "l"(cmp), "l"(val) : "memory");
     return old;
 }
+// 128-bit compare-and-swap on a whole {key, accumulator} slot (native ATOMS.CAS.128 on sm_100): a row
+// that finds a free slot claims it AND deposits its value in one atomic; returns the old key word.
+__device__ __forceinline__ long long sm_cas_slot(uint32_t a, long long ckey, long long cacc, long long nkey, long long nacc) {
+    long long olo, ohi;
+    asm volatile("{\n\t.reg .b128 c, s, o;\n\tmov.b128 c, {%3, %4};\n\tmov.b128 s, {%5, %6};\n\t"
+                 "atom.shared.cas.b128 o, [%2], c, s;\n\tmov.b128 {%0, %1}, o;\n\t}"
+                 : "=l"(olo), "=l"(ohi) : "r"(a), "l"(ckey), "l"(cacc), "l"(nkey), "l"(nacc) : "memory");
+    (void)ohi;
+    return olo;
+}
 // 64-bit integer add into shared memory.  sm_100 has no native 64-bit shared-memory add
 // (red.shared.add.u64 compiles to an ATOMS.CAST.SPIN.64 retry loop), so the add is done on
 // the two 32-bit halves with native atomics: the low half returns its old value, from which
@@ -105,10 +115,10 @@ struct AgShared {
 
 // insert the rows [r0, r1) whose pass id matches (m, r).  Whole warps walk the rows together
 // (predicated on validity) so the claim ballot below is always converged.
-template <typename KeyT, typename ValT, typename AccT>
+template <typename KeyT, typename ValT, typename AccT, bool WIDE>
 __device__ __forceinline__ void ag_insert_rows(const KeyT *__restrict__ keys, const ValT *__restrict__ vals,
-                                               int64_t r0, int64_t r1, int m, int r, int op, uint32_t key_base,
-                                               uint32_t acc_base, long long *s_acc, uint16_t *s_list, AgShared &sh) {
+                                               int64_t r0, int64_t r1, int m, int r, int op, long long ident,
+                                               uint32_t tab_base, long long *s_tab, uint16_t *s_list, AgShared &sh) {
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     const int64_t step = (int64_t)AG_THREADS * AG_UNROLL;
@@ -137,17 +147,29 @@ __device__ __forceinline__ void ag_insert_rows(const KeyT *__restrict__ keys, co
                 bool placed = false;
 #pragma unroll 1
                 for (int steps = 0; steps < AG_MAX_PROBE; steps++) {
-                    const uint32_t ka = key_base + h * 8u;
+                    const uint32_t ka = tab_base + h * 16u;
                     long long cur = sm_ld_volatile(ka);
-                    if (cur == kEmpty) {
-                        cur = sm_cas(ka, kEmpty, kb);  // old value: kEmpty = we claimed it, kb = a peer did
+                    if (cur == kEmpty) {  // old value: kEmpty = we claimed it, kb = a peer did
+                        if constexpr (WIDE) {
+                            // the first value of a key IS its combiner (createCombiner = identity function,
+                            // dpark/rdd.py:303-327): claim the slot and deposit the value in one atomic
+                            long long first;
+                            if constexpr (std::is_same<AccT, double>::value) first = __double_as_longlong((double)vreg[u]);
+                            else first = (long long)vreg[u];
+                            cur = sm_cas_slot(ka, kEmpty, ident, kb, first);
+                        } else {
+                            cur = sm_cas(ka, kEmpty, kb);
+                        }
                         claimed = cur == kEmpty;
                     }
                     if (cur == kb || claimed) { placed = true; break; }
                     h = (h + 1) & (AG_CAP - 1);
                 }
-                if (placed) sm_apply<AccT>(op, acc_base + h * 8u, s_acc + h, (AccT)vreg[u]);
-                else sh.overflow = 1;  // table too full for this pass: it will be split
+                if (placed) {
+                    if (!(WIDE && claimed)) sm_apply<AccT>(op, tab_base + h * 16u + 8u, s_tab + 2 * h + 1, (AccT)vreg[u]);
+                } else {
+                    sh.overflow = 1;  // table too full for this pass: it will be split
+                }
             }
             // ---- append the newly claimed slots to the claim list (one atomic per warp)
             const unsigned cm = __ballot_sync(0xffffffffu, claimed);
@@ -168,23 +190,22 @@ __device__ __forceinline__ void ag_insert_rows(const KeyT *__restrict__ keys, co
     }
 }
 
-template <typename KeyT, typename ValT, typename AccT>
+template <typename KeyT, typename ValT, typename AccT, bool WIDE>
 __global__ void __launch_bounds__(AG_THREADS)
 k_smem_aggregate(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, int op, int64_t ident,
                  const int64_t *__restrict__ fine_off, int32_t nfine, int32_t fine_per_part,
                  const int64_t *__restrict__ part_offsets, KeyT *__restrict__ out_keys,
                  int64_t *__restrict__ out_vals, unsigned long long *__restrict__ out_counts,
                  unsigned long long *__restrict__ fb_state, int *__restrict__ work_counter) {
-    extern __shared__ __align__(16) long long s_dyn[];  // [AG_CAP] keys | [AG_CAP] accumulators | [AG_CAP] u16 claim list
-    long long *s_key = s_dyn;
-    long long *s_acc = s_dyn + AG_CAP;
+    extern __shared__ __align__(16) long long s_dyn[];  // [AG_CAP] {key, accumulator} slots | [AG_CAP] u16 claim list
+    longlong2 *s_slot = reinterpret_cast<longlong2 *>(s_dyn);
     uint16_t *s_list = reinterpret_cast<uint16_t *>(s_dyn + 2 * AG_CAP);
-    const uint32_t key_base = (uint32_t)__cvta_generic_to_shared(s_key);
-    const uint32_t acc_base = (uint32_t)__cvta_generic_to_shared(s_acc);
+    const uint32_t tab_base = (uint32_t)__cvta_generic_to_shared(s_dyn);
+    const longlong2 kFree = make_longlong2(kEmpty, ident);
     __shared__ AgShared sh;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // the table is kept clean between fine buckets: writing a bucket out resets exactly the slots it touched
-    for (int i = threadIdx.x; i < AG_CAP; i += AG_THREADS) { s_key[i] = kEmpty; s_acc[i] = ident; }
+    for (int i = threadIdx.x; i < AG_CAP; i += AG_THREADS) s_slot[i] = kFree;
     if (threadIdx.x == 0) { sh.overflow = 0; sh.side_used = 0; sh.side_acc = ident; sh.nclaim = 0; }
     for (;;) {
         if (threadIdx.x == 0) sh.fb = atomicAdd(work_counter, 1);  // in-order hand-out
@@ -197,7 +218,7 @@ k_smem_aggregate(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, i
         const int64_t pbase = part_offsets[p];
 
         // ---- fast path: one pass over all rows
-        ag_insert_rows<KeyT, ValT, AccT>(keys, vals, r0, r1, 1, 0, op, key_base, acc_base, s_acc, s_list, sh);
+        ag_insert_rows<KeyT, ValT, AccT, WIDE>(keys, vals, r0, r1, 1, 0, op, ident, tab_base, s_dyn, s_list, sh);
         __syncthreads();                                            // (B)
         if (sh.overflow == 0) {                                     // uniform
             const int cnt = sh.nclaim, side = sh.side_used ? 1 : 0;
@@ -214,10 +235,10 @@ k_smem_aggregate(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, i
             const int64_t obase = pbase + (int64_t)sh.excl;
             for (int j = threadIdx.x; j < cnt; j += AG_THREADS) {   // coalesced: list order is output order
                 const int s = s_list[j];
-                out_keys[obase + j] = key_from_bits<KeyT>(s_key[s]);
-                out_vals[obase + j] = s_acc[s];
-                s_key[s] = kEmpty;
-                s_acc[s] = ident;
+                const longlong2 e = s_slot[s];
+                out_keys[obase + j] = key_from_bits<KeyT>(e.x);
+                out_vals[obase + j] = e.y;
+                s_slot[s] = kFree;
             }
             if (threadIdx.x == 0) {
                 if (side) {
@@ -241,9 +262,9 @@ k_smem_aggregate(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, i
             const int m = sh.stack_m[sh.sp - 1], r = sh.stack_r[sh.sp - 1];
             __syncthreads();
             if (threadIdx.x == 0) { sh.sp--; sh.overflow = 0; sh.side_used = 0; sh.side_acc = ident; sh.nclaim = 0; }
-            for (int i = threadIdx.x; i < AG_CAP; i += AG_THREADS) { s_key[i] = kEmpty; s_acc[i] = ident; }
+            for (int i = threadIdx.x; i < AG_CAP; i += AG_THREADS) s_slot[i] = kFree;
             __syncthreads();
-            ag_insert_rows<KeyT, ValT, AccT>(keys, vals, r0, r1, m, r, op, key_base, acc_base, s_acc, s_list, sh);
+            ag_insert_rows<KeyT, ValT, AccT, WIDE>(keys, vals, r0, r1, m, r, op, ident, tab_base, s_dyn, s_list, sh);
             __syncthreads();
             if (sh.overflow) {  // uniform after the barrier: split this pass in two and retry
                 if (threadIdx.x == 0 && sh.sp + 2 <= AG_STACK) {
@@ -266,8 +287,9 @@ k_smem_aggregate(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, i
             const int64_t obase = pbase + (int64_t)(excl + written);
             for (int j = threadIdx.x; j < cnt; j += AG_THREADS) {
                 const int s = s_list[j];
-                out_keys[obase + j] = key_from_bits<KeyT>(s_key[s]);
-                out_vals[obase + j] = s_acc[s];
+                const longlong2 e = s_slot[s];
+                out_keys[obase + j] = key_from_bits<KeyT>(e.x);
+                out_vals[obase + j] = e.y;
             }
             if (side && threadIdx.x == 0) {
                 out_keys[obase + cnt] = key_from_bits<KeyT>(kEmpty);
@@ -277,7 +299,7 @@ k_smem_aggregate(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, i
             __syncthreads();
         }
         // leave the table clean and publish the inclusive value
-        for (int i = threadIdx.x; i < AG_CAP; i += AG_THREADS) { s_key[i] = kEmpty; s_acc[i] = ident; }
+        for (int i = threadIdx.x; i < AG_CAP; i += AG_THREADS) s_slot[i] = kFree;
         if (warp == 0) {
             unsigned long long e = have_excl ? excl : ag_look_back(fb_state, first_fb, fb);
             if (lane == 0) {

@@ -439,6 +439,7 @@ static inline int grid_cap(int64_t items, int per_cta, int waves) {
 int g_reduce_impl = 2;  // dpk_set_option("reduce_impl", 0|1|2)
 
 constexpr int AG_MAX_SB2 = 10;       // at most 1024 fine buckets per first-level bucket
+int g_agg_wide = 1;
 int g_agg_target_rows = 2048;        // rows per fine bucket the split aims for (table load <= 0.5)
 
 static inline int choose_sb2(int64_t n, int32_t F) {
@@ -488,7 +489,8 @@ static int dispatch_op(const Ctx &c) {
         const int32_t nfine = c.F * S2;
         int grid = sm_count() * 8;
         if (grid > nfine) grid = nfine;
-        auto agg = k_smem_aggregate<KeyT, ValT, AccT>;
+        // dpk_set_option("agg_wide"): 1 = claim a slot and deposit the first value with one 128-bit CAS
+        auto agg = g_agg_wide ? k_smem_aggregate<KeyT, ValT, AccT, true> : k_smem_aggregate<KeyT, ValT, AccT, false>;
         const int agg_smem = AG_CAP * 16 + AG_CAP * 2;  // keys | accumulators | claim list
         DPK_CUDA_TRY(cudaFuncSetAttribute(agg, cudaFuncAttributeMaxDynamicSharedMemorySize, agg_smem));
         DPK_CUDA_TRY(cudaMemsetAsync(c.fb_state, 0, (size_t)nfine * 8, c.st));
@@ -577,6 +579,11 @@ int dpk_set_option(const char *name, int64_t value) {
     if (strcmp(name, "reduce_impl") == 0) {
         if (value < 0 || value > 2) return fail(DPK_ERR_INVALID, "reduce_impl must be 0, 1 or 2");
         g_reduce_impl = (int)value;
+        return DPK_OK;
+    }
+    if (strcmp(name, "agg_wide") == 0) {
+        if (value != 0 && value != 1) return fail(DPK_ERR_INVALID, "agg_wide must be 0 or 1");
+        g_agg_wide = (int)value;
         return DPK_OK;
     }
     if (strcmp(name, "scatter_items") == 0) {

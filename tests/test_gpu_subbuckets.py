@@ -162,3 +162,36 @@ def test_choose_sub_bits_bounds():
         for P in (1, 4, 8, 64, 1000, 4096):
             sb = shuffle.choose_sub_bits(n, P)
             assert (P << sb) <= max(P, 1024)
+
+
+@pytest.mark.parametrize("wide", [0, 1])
+@pytest.mark.parametrize("op", ["sum", "min", "max"])
+@pytest.mark.parametrize("vkind", ["i64", "f64"])
+def test_slot_claim_variants_agree_with_the_oracle(wide, op, vkind):
+    """dpk_set_option("agg_wide"): claiming a shared-memory slot and depositing the first value with one
+    128-bit CAS (1) or with a 64-bit key CAS followed by an atomic on the accumulator (0) must both give
+    the reference's createCombiner/mergeValue result (dpark/rdd.py:303-327) for every op and value kind,
+    with negative values (high half of the 64-bit add) and mostly-distinct as well as repeated keys."""
+    from dpark_b200 import shuffle
+    rng = np.random.default_rng(5 + wide)
+    n, P = 700_000, 3
+    k = rng.integers(-2 ** 40, 2 ** 40, n, dtype=np.int64)
+    k[: n // 4] = rng.integers(0, 300, n // 4)
+    if vkind == "i64":
+        v = rng.integers(-2 ** 40, 2 ** 40, n, dtype=np.int64)
+    else:
+        v = rng.standard_normal(n) * 1e6
+    nv().set_option("agg_wide", wide)
+    try:
+        res = shuffle.reduce_by_key([dev(k[: n // 2]), dev(k[n // 2:])], [dev(v[: n // 2]), dev(v[n // 2:])], P, op)
+    finally:
+        nv().set_option("agg_wide", 1)
+    want = orc.reduce_by_key([k[: n // 2], k[n // 2:]], [v[: n // 2], v[n // 2:]], P, op)
+    for p, gk, gv in res:
+        gk, gv = gk.cpu().numpy(), gv.cpu().numpy()
+        o1, o2 = np.argsort(gk), np.argsort(want[p][0])
+        assert np.array_equal(gk[o1], want[p][0][o2])
+        if vkind == "i64" or op != "sum":
+            assert np.array_equal(gv[o1], want[p][1][o2])
+        else:   # float sums: accumulation order differs; tolerance 1e-9 * sum|v| (DESIGN.md §7)
+            assert np.allclose(gv[o1], want[p][1][o2], rtol=0, atol=1e-9 * np.abs(v).sum())
