@@ -14,7 +14,7 @@
 // the 4096 slots, no block scan) and only the touched slots are reset for the next bucket.
 //
 // Output placement without atomics on the critical path: fine buckets are handed out
-// in order (atomic work counter, fetched one bucket ahead), and the position of a fine bucket's output inside its
+// in order (atomic work counter), and the position of a fine bucket's output inside its
 // partition is the running sum of the distinct counts of the fine buckets before it --
 // a chained scan with decoupled look-back over fb_state[] (AGGREGATE then INCLUSIVE
 // words, 2 flag bits + 62 value bits).  The partition's final count is the inclusive
@@ -107,124 +107,91 @@ __device__ __forceinline__ unsigned long long ag_look_back(const unsigned long l
 }
 
 struct AgShared {
-    int fb_next, overflow, side_used, sp;
-    int nclaim[2];  // claim-list length, indexed by the parity of the CTA's bucket sequence number
+    int fb, overflow, side_used, sp, nclaim;
     long long side_acc;
     unsigned long long excl;
     int stack_m[AG_STACK], stack_r[AG_STACK];
 };
 
-// AG_UNROLL rows per thread: rows base + u*AG_THREADS + tid, all loads in flight together
-template <typename KeyT, typename ValT>
-__device__ __forceinline__ void ag_load(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, int64_t base,
-                                        int64_t r1, KeyT (&kreg)[AG_UNROLL], ValT (&vreg)[AG_UNROLL]) {
-#pragma unroll
-    for (int u = 0; u < AG_UNROLL; u++) {
-        const int64_t i = base + u * AG_THREADS + threadIdx.x;
-        if (i < r1) { kreg[u] = keys[i]; vreg[u] = vals[i]; }
-    }
-}
-
-// insert the AG_UNROLL rows a thread holds in registers (pass id (m, r)).  Whole warps walk the rows
-// together (predicated on validity) so the claim ballot is always converged.
-template <typename KeyT, typename ValT, typename AccT, bool WIDE>
-__device__ __forceinline__ void ag_insert_regs(const KeyT (&kreg)[AG_UNROLL], const ValT (&vreg)[AG_UNROLL], int64_t base,
-                                               int64_t r1, int m, int r, int op, long long ident, uint32_t tab_base,
-                                               long long *s_tab, uint16_t *s_list, int *nclaim, AgShared &sh) {
-    const int lane = threadIdx.x & 31;
-    const unsigned lt = (1u << lane) - 1u;
-#pragma unroll
-    for (int u = 0; u < AG_UNROLL; u++) {
-        const int64_t i = base + u * AG_THREADS + threadIdx.x;
-        const int64_t kb = i < r1 ? key_bits<KeyT>(kreg[u]) : 0;
-        const uint64_t mx = mix64((uint64_t)kb);
-        bool live = i < r1 && (m == 1 || (int)((mx >> 40) & (uint64_t)(m - 1)) == r);
-        if (live && kb == kEmpty) {  // the key whose bits equal the free-slot marker: side accumulator
-            sh.side_used = 1;
-            Acc<AccT>::apply(op, (int64_t *)&sh.side_acc, (AccT)vreg[u]);
-            live = false;
-        }
-        bool claimed = false;
-        uint32_t h = (uint32_t)mx & (AG_CAP - 1);
-        if (live) {
-            bool placed = false;
-#pragma unroll 1
-            for (int steps = 0; steps < AG_MAX_PROBE; steps++) {
-                const uint32_t ka = tab_base + h * 16u;
-                long long cur = sm_ld_volatile(ka);
-                if (cur == kEmpty) {  // old value: kEmpty = we claimed it, kb = a peer did
-                    if constexpr (WIDE) {
-                        // the first value of a key IS its combiner (createCombiner = identity function,
-                        // dpark/rdd.py:303-327): claim the slot and deposit the value in one atomic
-                        long long first;
-                        if constexpr (std::is_same<AccT, double>::value) first = __double_as_longlong((double)vreg[u]);
-                        else first = (long long)vreg[u];
-                        cur = sm_cas_slot(ka, kEmpty, ident, kb, first);
-                    } else {
-                        cur = sm_cas(ka, kEmpty, kb);
-                    }
-                    claimed = cur == kEmpty;
-                }
-                if (cur == kb || claimed) { placed = true; break; }
-                h = (h + 1) & (AG_CAP - 1);
-            }
-            if (placed) {
-                if (!(WIDE && claimed)) sm_apply<AccT>(op, tab_base + h * 16u + 8u, s_tab + 2 * h + 1, (AccT)vreg[u]);
-            } else {
-                sh.overflow = 1;  // table too full for this pass: it will be split
-            }
-        }
-        // ---- append the newly claimed slots to the claim list (one atomic per warp)
-        const unsigned cm = __ballot_sync(0xffffffffu, claimed);
-        if (cm) {
-            const int leader = __ffs(cm) - 1;
-            int pos = 0;
-            if (lane == leader) pos = atomicAdd(nclaim, __popc(cm));
-            pos = __shfl_sync(0xffffffffu, pos, leader);
-            if (claimed) {
-                const int at = pos + __popc(cm & lt);
-                if (at < AG_CAP) s_list[at] = (uint16_t)h;
-            }
-            if (pos + __popc(cm) > AG_LIMIT) sh.overflow = 1;
-        }
-    }
-}
-
-// insert the rows [r0, r1) of pass (m, r).  If use_pre, the first AG_UNROLL*AG_THREADS rows are already in
-// (pk, pv) -- prefetched while the previous fine bucket was being written out.
+// insert the rows [r0, r1) whose pass id matches (m, r).  Whole warps walk the rows together
+// (predicated on validity) so the claim ballot below is always converged.
 template <typename KeyT, typename ValT, typename AccT, bool WIDE>
 __device__ __forceinline__ void ag_insert_rows(const KeyT *__restrict__ keys, const ValT *__restrict__ vals,
                                                int64_t r0, int64_t r1, int m, int r, int op, long long ident,
-                                               uint32_t tab_base, long long *s_tab, uint16_t *s_list, int *nclaim,
-                                               AgShared &sh, bool use_pre, const KeyT (&pk)[AG_UNROLL],
-                                               const ValT (&pv)[AG_UNROLL]) {
+                                               uint32_t tab_base, long long *s_tab, uint16_t *s_list, AgShared &sh) {
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
     const int64_t step = (int64_t)AG_THREADS * AG_UNROLL;
-    int64_t base = r0;
-    if (use_pre && base < r1) {
-        ag_insert_regs<KeyT, ValT, AccT, WIDE>(pk, pv, base, r1, m, r, op, ident, tab_base, s_tab, s_list, nclaim, sh);
-        base += step;
-        if (__any_sync(0xffffffffu, *(volatile int *)&sh.overflow != 0)) return;
-    }
-    for (; base < r1; base += step) {
+    for (int64_t base = r0; base < r1; base += step) {
         KeyT kreg[AG_UNROLL];
         ValT vreg[AG_UNROLL];
-        ag_load<KeyT, ValT>(keys, vals, base, r1, kreg, vreg);
-        ag_insert_regs<KeyT, ValT, AccT, WIDE>(kreg, vreg, base, r1, m, r, op, ident, tab_base, s_tab, s_list, nclaim, sh);
-        // warp-uniform exit (the ballots need whole warps)
+#pragma unroll
+        for (int u = 0; u < AG_UNROLL; u++) {  // AG_UNROLL independent loads in flight per thread
+            const int64_t i = base + u * AG_THREADS + threadIdx.x;
+            if (i < r1) { kreg[u] = keys[i]; vreg[u] = vals[i]; }
+        }
+#pragma unroll
+        for (int u = 0; u < AG_UNROLL; u++) {
+            const int64_t i = base + u * AG_THREADS + threadIdx.x;
+            const int64_t kb = i < r1 ? key_bits<KeyT>(kreg[u]) : 0;
+            const uint64_t mx = mix64((uint64_t)kb);
+            bool live = i < r1 && (m == 1 || (int)((mx >> 40) & (uint64_t)(m - 1)) == r);
+            if (live && kb == kEmpty) {  // the key whose bits equal the free-slot marker: side accumulator
+                sh.side_used = 1;
+                Acc<AccT>::apply(op, (int64_t *)&sh.side_acc, (AccT)vreg[u]);
+                live = false;
+            }
+            bool claimed = false;
+            uint32_t h = (uint32_t)mx & (AG_CAP - 1);
+            if (live) {
+                bool placed = false;
+#pragma unroll 1
+                for (int steps = 0; steps < AG_MAX_PROBE; steps++) {
+                    const uint32_t ka = tab_base + h * 16u;
+                    long long cur = sm_ld_volatile(ka);
+                    if (cur == kEmpty) {  // old value: kEmpty = we claimed it, kb = a peer did
+                        if constexpr (WIDE) {
+                            // the first value of a key IS its combiner (createCombiner = identity function,
+                            // dpark/rdd.py:303-327): claim the slot and deposit the value in one atomic
+                            long long first;
+                            if constexpr (std::is_same<AccT, double>::value) first = __double_as_longlong((double)vreg[u]);
+                            else first = (long long)vreg[u];
+                            cur = sm_cas_slot(ka, kEmpty, ident, kb, first);
+                        } else {
+                            cur = sm_cas(ka, kEmpty, kb);
+                        }
+                        claimed = cur == kEmpty;
+                    }
+                    if (cur == kb || claimed) { placed = true; break; }
+                    h = (h + 1) & (AG_CAP - 1);
+                }
+                if (placed) {
+                    if (!(WIDE && claimed)) sm_apply<AccT>(op, tab_base + h * 16u + 8u, s_tab + 2 * h + 1, (AccT)vreg[u]);
+                } else {
+                    sh.overflow = 1;  // table too full for this pass: it will be split
+                }
+            }
+            // ---- append the newly claimed slots to the claim list (one atomic per warp)
+            const unsigned cm = __ballot_sync(0xffffffffu, claimed);
+            if (cm) {
+                const int leader = __ffs(cm) - 1;
+                int pos = 0;
+                if (lane == leader) pos = atomicAdd(&sh.nclaim, __popc(cm));
+                pos = __shfl_sync(0xffffffffu, pos, leader);
+                if (claimed) {
+                    const int at = pos + __popc(cm & lt);
+                    if (at < AG_CAP) s_list[at] = (uint16_t)h;
+                }
+                if (pos + __popc(cm) > AG_LIMIT) sh.overflow = 1;
+            }
+        }
+        // warp-uniform exit (the ballots above need whole warps)
         if (__any_sync(0xffffffffu, *(volatile int *)&sh.overflow != 0)) return;
     }
 }
 
-// Software pipeline of one CTA over its fine buckets (sequence number q, parity par = q & 1):
-//   top       thread 0 issues the hand-out atomic of the NEXT bucket (its ~1 us round trip hides behind the inserts)
-//   inserts   first rows come from registers (prefetched), the rest are loaded
-//   barrier B inserts done, next bucket id visible
-//   prefetch  every thread issues the loads of the next bucket's first rows -- they fly during the rest
-//   look-back EVERY warp computes the output offset on its own (no barrier, no broadcast through shared memory)
-//   write-out claim-list order, resets the touched slots
-//   barrier A table clean
 template <typename KeyT, typename ValT, typename AccT, bool WIDE>
-__global__ void __launch_bounds__(AG_THREADS, 3)
+__global__ void __launch_bounds__(AG_THREADS)
 k_smem_aggregate(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, int op, int64_t ident,
                  const int64_t *__restrict__ fine_off, int32_t nfine, int32_t fine_per_part,
                  const int64_t *__restrict__ part_offsets, KeyT *__restrict__ out_keys,
@@ -239,74 +206,53 @@ k_smem_aggregate(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, i
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // the table is kept clean between fine buckets: writing a bucket out resets exactly the slots it touched
     for (int i = threadIdx.x; i < AG_CAP; i += AG_THREADS) s_slot[i] = kFree;
-    if (threadIdx.x == 0) {
-        sh.overflow = 0; sh.side_used = 0; sh.side_acc = ident; sh.nclaim[0] = 0; sh.nclaim[1] = 0;
-        sh.fb_next = atomicAdd(work_counter, 1);  // in-order hand-out
-    }
-    __syncthreads();
-    int fb = sh.fb_next;
-    int64_t r0 = 0, r1 = 0;
-    KeyT pk[AG_UNROLL];
-    ValT pv[AG_UNROLL];
-    if (fb < nfine) {
-        r0 = fine_off[fb]; r1 = fine_off[fb + 1];
-        ag_load<KeyT, ValT>(keys, vals, r0, r1, pk, pv);
-    }
-    __syncthreads();  // everyone has read fb_next before thread 0 overwrites it
-    for (int par = 0; fb < nfine; par ^= 1) {
-        int nxt = 0;
-        if (threadIdx.x == 0) {
-            nxt = atomicAdd(work_counter, 1);  // next bucket: consumed only at the store before barrier (B)
-            sh.nclaim[par ^ 1] = 0;            // its readers (previous bucket) are all past barrier (A)
-        }
+    if (threadIdx.x == 0) { sh.overflow = 0; sh.side_used = 0; sh.side_acc = ident; sh.nclaim = 0; }
+    for (;;) {
+        if (threadIdx.x == 0) sh.fb = atomicAdd(work_counter, 1);  // in-order hand-out
+        __syncthreads();                                            // (A) also: previous write-out finished, table clean
+        const int fb = sh.fb;
+        if (fb >= nfine) break;
+        const int64_t r0 = fine_off[fb], r1 = fine_off[fb + 1];
         const int p = fb / fine_per_part;
         const int first_fb = p * fine_per_part;
         const int64_t pbase = part_offsets[p];
-        int *nclaim = &sh.nclaim[par];
 
         // ---- fast path: one pass over all rows
-        ag_insert_rows<KeyT, ValT, AccT, WIDE>(keys, vals, r0, r1, 1, 0, op, ident, tab_base, s_dyn, s_list, nclaim, sh,
-                                              true, pk, pv);
-        if (threadIdx.x == 0) sh.fb_next = nxt;
+        ag_insert_rows<KeyT, ValT, AccT, WIDE>(keys, vals, r0, r1, 1, 0, op, ident, tab_base, s_dyn, s_list, sh);
         __syncthreads();                                            // (B)
-        const int fbn = sh.fb_next;
-        const int64_t cur_r0 = r0, cur_r1 = r1;
-        if (fbn < nfine) {                                          // prefetch: in flight during look-back + write-out
-            r0 = fine_off[fbn]; r1 = fine_off[fbn + 1];
-            ag_load<KeyT, ValT>(keys, vals, r0, r1, pk, pv);
-        }
         if (sh.overflow == 0) {                                     // uniform
-            const int cnt = *nclaim;
-            int side = 0;
-            if (threadIdx.x == 0) {
-                side = sh.side_used ? 1 : 0;
-                atomicExch(&fb_state[fb], AG_FLAG_AGG | (unsigned long long)(cnt + side));
+            const int cnt = sh.nclaim, side = sh.side_used ? 1 : 0;
+            if (warp == 0) {
+                if (lane == 0) atomicExch(&fb_state[fb], AG_FLAG_AGG | (unsigned long long)(cnt + side));
+                const unsigned long long e = ag_look_back(fb_state, first_fb, fb);
+                if (lane == 0) {
+                    sh.excl = e;
+                    atomicExch(&fb_state[fb], AG_FLAG_INC | (e + (unsigned long long)(cnt + side)));
+                    if (fb == first_fb + fine_per_part - 1) out_counts[p] = e + (unsigned long long)(cnt + side);
+                }
             }
-            const unsigned long long e = ag_look_back(fb_state, first_fb, fb);  // per warp
-            if (threadIdx.x == 0) {
-                atomicExch(&fb_state[fb], AG_FLAG_INC | (e + (unsigned long long)(cnt + side)));
-                if (fb == first_fb + fine_per_part - 1) out_counts[p] = e + (unsigned long long)(cnt + side);
-            }
-            const int64_t obase = pbase + (int64_t)e;
+            __syncthreads();                                        // (D)
+            const int64_t obase = pbase + (int64_t)sh.excl;
             for (int j = threadIdx.x; j < cnt; j += AG_THREADS) {   // coalesced: list order is output order
                 const int s = s_list[j];
-                const longlong2 ent = s_slot[s];
-                out_keys[obase + j] = key_from_bits<KeyT>(ent.x);
-                out_vals[obase + j] = ent.y;
+                const longlong2 e = s_slot[s];
+                out_keys[obase + j] = key_from_bits<KeyT>(e.x);
+                out_vals[obase + j] = e.y;
                 s_slot[s] = kFree;
             }
-            if (threadIdx.x == 0 && side) {
-                out_keys[obase + cnt] = key_from_bits<KeyT>(kEmpty);
-                out_vals[obase + cnt] = sh.side_acc;
-                sh.side_used = 0;
-                sh.side_acc = ident;
+            if (threadIdx.x == 0) {
+                if (side) {
+                    out_keys[obase + cnt] = key_from_bits<KeyT>(kEmpty);
+                    out_vals[obase + cnt] = sh.side_acc;
+                    sh.side_used = 0;
+                    sh.side_acc = ident;
+                }
+                sh.nclaim = 0;
             }
-            __syncthreads();                                        // (A) table clean, list free
-            fb = fbn;
-            continue;
+            continue;  // barrier (A) of the next iteration orders the resets before the next inserts
         }
 
-        // ---- slow path: hash-disjoint passes over [cur_r0, cur_r1), split on demand
+        // ---- slow path: hash-disjoint passes, split on demand
         unsigned long long written = 0, excl = 0;  // uniform
         bool have_excl = false;
         if (threadIdx.x == 0) { sh.stack_m[0] = 2; sh.stack_r[0] = 0; sh.stack_m[1] = 2; sh.stack_r[1] = 1; sh.sp = 2; }
@@ -315,11 +261,10 @@ k_smem_aggregate(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, i
             __syncthreads();  // everyone has seen sp > 0
             const int m = sh.stack_m[sh.sp - 1], r = sh.stack_r[sh.sp - 1];
             __syncthreads();
-            if (threadIdx.x == 0) { sh.sp--; sh.overflow = 0; sh.side_used = 0; sh.side_acc = ident; *nclaim = 0; }
+            if (threadIdx.x == 0) { sh.sp--; sh.overflow = 0; sh.side_used = 0; sh.side_acc = ident; sh.nclaim = 0; }
             for (int i = threadIdx.x; i < AG_CAP; i += AG_THREADS) s_slot[i] = kFree;
             __syncthreads();
-            ag_insert_rows<KeyT, ValT, AccT, WIDE>(keys, vals, cur_r0, cur_r1, m, r, op, ident, tab_base, s_dyn, s_list,
-                                                  nclaim, sh, false, pk, pv);
+            ag_insert_rows<KeyT, ValT, AccT, WIDE>(keys, vals, r0, r1, m, r, op, ident, tab_base, s_dyn, s_list, sh);
             __syncthreads();
             if (sh.overflow) {  // uniform after the barrier: split this pass in two and retry
                 if (threadIdx.x == 0 && sh.sp + 2 <= AG_STACK) {
@@ -329,7 +274,7 @@ k_smem_aggregate(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, i
                 __syncthreads();
                 continue;
             }
-            const int cnt = *nclaim, side = sh.side_used ? 1 : 0;
+            const int cnt = sh.nclaim, side = sh.side_used ? 1 : 0;
             if (!have_excl) {  // multi-pass buckets publish only their inclusive value, at the end
                 if (warp == 0) {
                     const unsigned long long e = ag_look_back(fb_state, first_fb, fb);
@@ -342,9 +287,9 @@ k_smem_aggregate(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, i
             const int64_t obase = pbase + (int64_t)(excl + written);
             for (int j = threadIdx.x; j < cnt; j += AG_THREADS) {
                 const int s = s_list[j];
-                const longlong2 ent = s_slot[s];
-                out_keys[obase + j] = key_from_bits<KeyT>(ent.x);
-                out_vals[obase + j] = ent.y;
+                const longlong2 e = s_slot[s];
+                out_keys[obase + j] = key_from_bits<KeyT>(e.x);
+                out_vals[obase + j] = e.y;
             }
             if (side && threadIdx.x == 0) {
                 out_keys[obase + cnt] = key_from_bits<KeyT>(kEmpty);
@@ -358,12 +303,10 @@ k_smem_aggregate(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, i
         if (warp == 0) {
             unsigned long long e = have_excl ? excl : ag_look_back(fb_state, first_fb, fb);
             if (lane == 0) {
-                sh.overflow = 0; sh.side_used = 0; sh.side_acc = ident;
+                sh.overflow = 0; sh.side_used = 0; sh.side_acc = ident; sh.nclaim = 0;
                 atomicExch(&fb_state[fb], AG_FLAG_INC | (e + written));
                 if (fb == first_fb + fine_per_part - 1) out_counts[p] = e + written;
             }
         }
-        __syncthreads();                                            // (A)
-        fb = fbn;
     }
 }
