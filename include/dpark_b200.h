@@ -164,8 +164,16 @@ int dpk_combine(const void *keys, int key_kind, const int64_t *key_aux, const vo
                 int32_t sub_bits, int32_t part_first, int32_t nparts, int32_t nsrc,
                 const int64_t *seg_rows, void *out_keys, void *out_vals, int64_t *out_offsets,
                 int64_t *out_counts, void *ws, int64_t ws_bytes, dpk_stream_t stream);
-/* options: "reduce_impl" = 1 (default: one thread-block cluster per fine bucket,
- * table life cycle L2-resident) or 0 (three grid-wide passes; kept for A/B runs) */
+/* Process-wide A/B switches (results are identical for every setting; only the speed differs):
+ *   "reduce_impl"     2 (default) second-level split + one CTA per fine bucket merging in a
+ *                     shared-memory table; 1 = per-bucket tables in HBM, one 8-CTA cluster per bucket;
+ *                     0 = three grid-wide passes over global tables
+ *   "agg_wide"        1 (default) claim a table slot and deposit the first value with one 128-bit
+ *                     shared-memory CAS; 0 = 64-bit key CAS, then an atomic on the accumulator
+ *   "agg_target_rows" rows per fine bucket the second-level split aims for (default 2048)
+ *   "count_mode"      1 (default) one shared-memory atomic per row in the histogram pass; 0 = warp
+ *                     peer masks + leader update
+ *   "scatter_items"   16 (default) or 8 rows per thread and tile in the multisplit scatter */
 int dpk_set_option(const char *name, int64_t value);
 
 /* ---- a10: reduce side of groupByKey (dpark/dependency.py:107-118 merged by
