@@ -1,15 +1,22 @@
-"""Fused scatter + exchange over NVLink peer memory.
+"""The exchange over NVLink peer memory: the map side PUSHES.
 
-The reference's reducers PULL every map's bucket over files + HTTP
-(ShuffleFetcher, dpark/shuffle.py:309-420).  shuffle.exchange() replaces that by one NCCL
-alltoallv -- still a separate pass that reads the bucket-major buffer from HBM and writes it
-into the peer's HBM.  Here the map-side scatter kernel PUSHES instead: every rank maps its
-peers' receive buffers into its address space (torch symmetric memory = cuMem allocations
-exchanged between the ranks of one node) and dpk_partition_scatter_ptrs stores each bucket's
-rows straight into the owning GPU's receive buffer while it is partitioning.  The exchange
-costs no extra HBM pass and overlaps with the scatter's own work; what remains of the
-collective is the small all-gather of the counts matrix (the MapOutputTracker) and two
-barriers.
+The reference's reducers PULL every map's bucket over files + HTTP (ShuffleFetcher,
+dpark/shuffle.py:309-420).  shuffle.exchange() replaces that by one NCCL alltoallv.  Here every
+rank maps its peers' receive buffers into its own address space (torch symmetric memory = cuMem
+allocations exchanged between the ranks of one node) and writes into them directly, in one of two
+forms:
+
+  exchange_push   (mode "push", default) the map output stays local and bucket-major -- the rows
+                  bound for one peer are ONE contiguous block -- and a single launch of
+                  dpk_copy_segments pushes every block with full-width stores; the segment table
+                  (push_plan) is computed on the device from the gathered counts matrix.
+  map_side_push   (mode "fused") dpk_partition_scatter_ptrs: the scatter kernel itself stores each
+                  bucket's rows into the owning GPU's buffer while it is partitioning.  No extra
+                  HBM pass, but the stores are the short bucket runs of one tile, which NVLink
+                  carries poorly (measured slower than "push" from 2 GPUs up).
+
+What remains of the collective in both forms is the small all-gather of the counts matrix (the
+MapOutputTracker) and two stream-ordered barriers.
 
 Layout of a receive buffer = what exchange() delivers: source-rank-major, bucket-major inside.
 """
@@ -71,6 +78,11 @@ def exchange_push(px, mo):
     G, rank, dev = px.world, px.rank, px.device
     P, sb = mo.P, mo.sub_bits
     F = P << sb
+    if mo.keys.dtype != px.keys.dtype or (mo.vals is not None and mo.vals.dtype != px.vals.dtype):
+        raise TypeError("receive buffers are (%s, %s) but the map output is (%s, %s): allocate the PeerExchange "
+                        "with the column dtypes that are exchanged (after a map-side combine the value column "
+                        "is the accumulator type)" % (px.keys.dtype, px.vals.dtype, mo.keys.dtype,
+                                                      None if mo.vals is None else mo.vals.dtype))
     counts = (mo.offsets[1:] - mo.offsets[:-1]).contiguous()
     all_counts = torch.empty(G * F, dtype=torch.int64, device=dev)
     dist.all_gather_into_tensor(all_counts, counts, group=px.group)   # the MapOutputTracker

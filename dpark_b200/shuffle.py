@@ -200,8 +200,9 @@ class HostShuffle(object):
     distinct (key, combined) rows.  Buffers are allocated once and reused."""
 
     def __init__(self, n_rows, key_dtype, val_dtype, P, op="sum", splits=8, thresholds=None, group=None,
-                 device=None, sub_bits=None, world=1, peer_exchange=None):
+                 device=None, sub_bits=None, world=1, peer_exchange=None, map_combine=False):
         self.P, self.op, self.splits, self.thresholds, self.group = P, op, splits, thresholds, group
+        self.map_combine = map_combine       # merge the local map output before the exchange (hot keys)
         self.peer_exchange = peer_exchange
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         self.n = n_rows
@@ -226,16 +227,18 @@ class HostShuffle(object):
             self.d_vals[a:b].copy_(self.h_vals[a:b], non_blocking=True)
             kc.append(self.d_keys[a:b])
             vc.append(self.d_vals[a:b])
-        if self.peer_exchange is not None:     # fused scatter + exchange over NVLink peer memory
-            from . import peer
-            if self.peer_exchange.mode == "fused":
-                rx = peer.map_side_push(self.peer_exchange, kc, vc, self.P, self.thresholds, self.sub_bits)
-            else:
-                rx = peer.exchange_push(self.peer_exchange, map_side(kc, vc, self.P, self.thresholds, False,
-                                                                     self.sub_bits, unordered=True))
+        if self.peer_exchange is not None and self.peer_exchange.mode == "fused" and not self.map_combine:
+            from . import peer                 # the scatter kernel stores straight into peer memory
+            rx = peer.map_side_push(self.peer_exchange, kc, vc, self.P, self.thresholds, self.sub_bits)
         else:
             mo = map_side(kc, vc, self.P, self.thresholds, False, self.sub_bits, unordered=True)
-            rx = exchange(mo, self.group)
+            if self.map_combine:
+                mo = combine_map_output(mo, self.op, self.thresholds)
+            if self.peer_exchange is not None:  # block push over NVLink peer memory
+                from . import peer
+                rx = peer.exchange_push(self.peer_exchange, mo)
+            else:
+                rx = exchange(mo, self.group)
         ok, ov, po, cnt = reduce_side(rx, self.op, self.P, self.thresholds)
         po_h, cnt_h = po.cpu().tolist(), cnt.cpu().tolist()      # the one host sync: result sizes
         nrx = int(ok.numel())
@@ -332,7 +335,29 @@ class HostShuffleStream(object):
         return res
 
 
-def reduce_by_key(key_chunks, val_chunks, P, op="sum", thresholds=None, group=None, sub_bits=None):
+def combine_map_output(mo, op, thresholds=None):
+    """Map-side combine: the dict upsert of ShuffleMapTask._run (dpark/task.py:222-226,
+    `buckets[i][k] = mergeValue(buckets[i][k], v)`), which the reference always does so that a key
+    leaves a map task at most once per reducer.  Here it is an OPTION (reduce_by_key(map_combine=True)):
+    with mostly distinct keys it is a wasted merge pass, with hot keys (Zipf, word counts) it shrinks the
+    exchange and takes the skew out of it -- every rank sends ONE row per key it holds, so the rank
+    owning the hottest key receives G rows for it, not a tenth of the data set.
+
+    The rank's whole map output is merged locally (the reduce-side kernels over all P partitions,
+    one "source"), the distinct rows are compacted and partitioned again.  Combining twice with the
+    same op is exact for every op the library has (sum/min/max/prod/and/or/xor are associative and
+    commutative; float sums are order-free up to the tolerance stated in DESIGN.md §7)."""
+    P, sb = mo.P, mo.sub_bits
+    seg = (mo.offsets[1:] - mo.offsets[:-1]).unsqueeze(0)
+    ok, ov, po, cnt = reduce_side(Received(mo.keys, mo.vals, seg, 0, P, sb), op, P, thresholds)
+    po_h, cnt_h = po.cpu().tolist(), cnt.cpu().tolist()           # host read: sizes of the compacted columns
+    keys = torch.cat([ok[a:a + c] for a, c in zip(po_h, cnt_h)])
+    vals = torch.cat([ov[a:a + c] for a, c in zip(po_h, cnt_h)])
+    return map_side([keys], [vals], P, thresholds, False, sb, unordered=True)
+
+
+def reduce_by_key(key_chunks, val_chunks, P, op="sum", thresholds=None, group=None, sub_bits=None,
+                  map_combine=False):
     """Whole hot path for this rank's map splits.  Returns a list of
     (partition id, keys, vals) for the partitions this rank owns (device tensors)."""
     if sub_bits is None:
@@ -340,6 +365,8 @@ def reduce_by_key(key_chunks, val_chunks, P, op="sum", thresholds=None, group=No
         G = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
         sub_bits = choose_sub_bits(sum(int(k.numel()) for k in key_chunks) * G, P)
     mo = map_side(key_chunks, val_chunks, P, thresholds, False, sub_bits, unordered=True)
+    if map_combine:
+        mo = combine_map_output(mo, op, thresholds)
     rx = exchange(mo, group)
     ok, ov, po, cnt = reduce_side(rx, op, P, thresholds)
     po_h, cnt_h = po.cpu().tolist(), cnt.cpu().tolist()

@@ -103,3 +103,26 @@ def test_copy_segments_moves_every_byte_at_any_alignment():
         want[b:b + c] = h[a:a + c]
     assert np.array_equal(dst.cpu().numpy(), want)
     nv.copy_segments(so[:0], do[:0], nb[:0])      # empty table is a no-op
+
+
+@pytest.mark.parametrize("op", ["sum", "max"])
+def test_map_side_combine_gives_the_same_partitions(op):
+    """reduce_by_key(map_combine=True) -- the reference's map-side dict upsert (dpark/task.py:222-226) as a
+    local merge before the exchange -- must not change any partition's result, on a Zipf-like key column
+    (one key holds ~10 % of the rows) with int32 values (the combined column is int64)."""
+    from dpark_b200 import shuffle
+    rng = np.random.default_rng(17)
+    n, P, M = 800_000, 6, 4
+    k = (rng.zipf(1.3, n) % 50_000).astype(np.int64)
+    k[rng.random(n) < 0.1] = 7
+    v = rng.integers(-500, 500, n).astype(np.int32)
+    ks, vs = np.array_split(k, M), np.array_split(v, M)
+    want = orc.reduce_by_key(ks, [x.astype(np.int64) for x in vs], P, op)
+    for mc in (False, True):
+        res = shuffle.reduce_by_key([torch.from_numpy(x).cuda() for x in ks], [torch.from_numpy(x).cuda() for x in vs],
+                                    P, op, map_combine=mc)
+        _check([(p, a.cpu(), b.cpu()) for p, a, b in res], want, P)
+    # the combined map output holds one row per (distinct key): far fewer rows than went in
+    mo = shuffle.map_side([torch.from_numpy(k).cuda()], [torch.from_numpy(v).cuda()], P, sub_bits=2, unordered=True)
+    mc = shuffle.combine_map_output(mo, op)
+    assert int(mc.keys.numel()) == len(np.unique(k)) and int(mc.offsets[-1]) == len(np.unique(k))
