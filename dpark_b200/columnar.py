@@ -117,18 +117,31 @@ def decode_keys(kind, data, offsets=None):
     return [raw[offs[i]:offs[i + 1]].decode("utf-8", "surrogatepass") for i in range(len(offs) - 1)]
 
 
+def _hash_column(keys):
+    """portable_hash of every key of a Python list, evaluated by the CUDA kernels
+    (dpk_hash_keys / dpk_hash_bytes).  Returns an int64 device tensor."""
+    from . import _native as nv
+    kk, kd, ko = _key_column(keys)
+    if not torch.cuda.is_available():
+        raise nv.NativeError("portable_hash needs a CUDA device (no CPU fallback)")
+    dev = torch.device("cuda", torch.cuda.current_device())
+    if kk in (KEY_I64, KEY_F64):
+        return nv.hash_keys(torch.from_numpy(kd).to(dev))
+    data = torch.from_numpy(np.ascontiguousarray(kd) if kd.size else np.zeros(1, np.uint8)).to(dev)
+    return nv.hash_bytes(data, torch.from_numpy(ko).to(dev), nv.STR_UTF8 if kk == KEY_STR else nv.BYTES_SIGNED)
+
+
+def hashes_of_keys(keys):
+    """[portable_hash(k) for k in keys] as a list of Python ints (device-evaluated)."""
+    if not keys:
+        return []
+    return _hash_column(list(keys)).cpu().tolist()
+
+
 def partition_of_key(key, P, thresholds=None):
     """HashPartitioner.getPartition(key) for one Python key, evaluated by the CUDA
     kernels (1-row launch)."""
     from . import _native as nv
-    kk, kd, ko = _key_column([key])
-    dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None
-    if dev is None:
-        raise nv.NativeError("getPartition needs a CUDA device (no CPU fallback)")
-    if kk in (KEY_I64, KEY_F64):
-        h = nv.hash_keys(torch.from_numpy(kd).to(dev))
-    else:
-        data = torch.from_numpy(np.ascontiguousarray(kd) if kd.size else np.zeros(1, np.uint8)).to(dev)
-        h = nv.hash_bytes(data, torch.from_numpy(ko).to(dev), nv.STR_UTF8 if kk == KEY_STR else nv.BYTES_SIGNED)
-    thr = None if thresholds is None else torch.tensor(thresholds, dtype=torch.int64, device=dev)
+    h = _hash_column([key])
+    thr = None if thresholds is None else torch.tensor(thresholds, dtype=torch.int64, device=h.device)
     return int(nv.partition_ids(h, P, thr)[0])

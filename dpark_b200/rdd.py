@@ -10,12 +10,14 @@ operators are plain Python generators, as in the reference; every shuffle runs
 on the GPU through dpark_b200.shuffle -- there is no CPU shuffle.
 """
 import itertools
+import math
 import os
+import random
 import shutil
 
 import numpy as np
 
-from . import columnar, conf, trace
+from . import columnar, conf, quantiles, trace
 from .dependency import Aggregator, GroupByAggregator, HashPartitioner, Partitioner, ShuffleDependency
 from .errors import DparkUserFatalError  # noqa: F401
 
@@ -176,14 +178,38 @@ class RDD(object):
         return None
 
     # ------------------------------------------------------------- the shuffle
+    def sample(self, faction, withReplacement=False, seed=12345):
+        """dpark/rdd.py:267-268."""
+        return SampleRDD(self, faction, withReplacement, seed)
+
+    def percentiles(self, p, sampleRate=1.0, func=None):
+        """dpark/rdd.py:791-814: one t-digest per partition, merged in partition order."""
+        if sampleRate <= 0:
+            raise ValueError("Sample Rate should be positive.")
+        rdd = self if sampleRate >= 1.0 else self.sample(sampleRate)
+        if func:
+            rdd = rdd.map(func)
+        return quantiles.percentiles_of_partitions(self.ctx.runJob(rdd, list), p)
+
+    def _skew_thresholds(self, splits, sampleRate):
+        """Thresholds of combineByKey(fixSkew=sampleRate) (dpark/rdd.py:516-537): approximate percentiles of
+        portable_hash(key) over a sample of the rows.  The sampled keys of every partition are hashed on the
+        device in one launch; the digest arithmetic is the reference's (dpark_b200/quantiles.py)."""
+        rdd = self if sampleRate >= 1.0 else self.sample(sampleRate)
+        hashed = [columnar.hashes_of_keys([row[0] for row in part])
+                  for part in self.ctx.runJob(rdd, list)]
+        return quantiles.skew_thresholds(hashed, splits)
+
     def combineByKey(self, aggregator, splits=None, taskMemory=None, fixSkew=-1, rddconf=None):
-        """dpark/rdd.py:511-541.  `splits` is a partition count or a Partitioner.
-        fixSkew (t-digest thresholds) is not implemented: the
-        flag is accepted and ignored, explicit HashPartitioner(thresholds=...) works."""
+        """dpark/rdd.py:511-541.  `splits` is a partition count or a Partitioner; fixSkew > 0 is the sample
+        rate for balancing the partitions by hash thresholds instead of hash modulo."""
         if splits is None:
             splits = min(self.ctx.defaultMinSplits, len(self))
         if type(splits) is int:
-            splits = HashPartitioner(splits)
+            thresh = None
+            if fixSkew > 0 and splits > 1:
+                thresh, splits = self._skew_thresholds(splits, fixSkew)
+            splits = HashPartitioner(splits, thresholds=thresh)
         return ShuffledRDD(self, aggregator, splits, taskMemory, rddconf=rddconf)
 
     def reduceByKey(self, func, numSplits=None, taskMemory=None, fixSkew=-1, rddconf=None):
@@ -232,6 +258,26 @@ class FlatMappedRDD(MappedRDD):
 class FilteredRDD(MappedRDD):
     def compute(self, split):
         return filter(self.func, self.prev.iterator(split))
+
+
+class SampleRDD(DerivedRDD):
+    """dpark/rdd.py:1379-1397: Bernoulli (or with-replacement) sample, `random.Random(seed + split.index)`
+    per partition -- the same generator and the same draw order, so the same rows are kept."""
+
+    def __init__(self, prev, frac, withReplacement, seed):
+        DerivedRDD.__init__(self, prev)
+        self.frac, self.withReplacement, self.seed = frac, withReplacement, seed
+
+    def compute(self, split):
+        rd = random.Random(self.seed + split.index)
+        if self.withReplacement:
+            rows = list(self.prev.iterator(split))
+            for _ in range(int(math.ceil(len(rows) * self.frac))):
+                yield rd.choice(rows)
+        else:
+            for row in self.prev.iterator(split):
+                if rd.random() <= self.frac:
+                    yield row
 
 
 class GlommedRDD(DerivedRDD):

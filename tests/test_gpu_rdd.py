@@ -171,3 +171,39 @@ def test_unsupported_things_fail_loudly():
         dc.parallelize([(1, 1), 5], 1).reduceByKey(lambda x, y: x + y).collect()
     with pytest.raises(TypeError):
         dc.parallelize([(True, 1)], 1).reduceByKey(lambda x, y: x + y).collect()
+
+
+def test_fix_skew_layout_of_the_reference_test():
+    """tests/test_rdd.py:259-266 of the reference: keys 0..9 once and key 10 five times in 10 input
+    partitions, groupByKey(3, fixSkew=1) -> the t-digest thresholds [5, 10] put {0..4}, {5..9}, {10}
+    into the three partitions (golden glom() output captured from the reference)."""
+    dc = ctx()
+    dsk = list(zip(range(10), range(10))) + [(10, 10)] * 5
+    rdd = dc.makeRDD(dsk, 10).groupByKey(3, fixSkew=1)
+    assert rdd.partitioner.thresholds == [5, 10]
+    out = rdd.map(lambda kv: (kv[0], list(kv[1]))).glom().collect()
+    assert [sorted([[k, sorted(v)] for k, v in part]) for part in out] == SC["fix_skew_test_basic"]
+
+
+def test_fix_skew_balances_a_hot_hash_range_and_keeps_results():
+    """reduceByKey(fixSkew=rate): thresholds come from a seeded sample (random.Random(12345 + split), as the
+    reference's SampleRDD), partitions are balanced by hash range, per-key results are unchanged."""
+    import random
+    dc = ctx()
+    rnd = random.Random(3)
+    rows = [(rnd.randrange(0, 1000) if rnd.random() < 0.7 else rnd.randrange(-10 ** 12, 10 ** 12), 1)
+            for _ in range(20000)]
+    plain = dict(dc.parallelize(rows, 5).reduceByKey(lambda a, b: a + b, 4).collect())
+    skew = dc.parallelize(rows, 5).reduceByKey(lambda a, b: a + b, 4, fixSkew=0.3)
+    thr = skew.partitioner.thresholds
+    assert thr is not None and thr == sorted(thr) and len(thr) == len(skew.splits) - 1
+    parts = skew.glom().collect()
+    assert dict(kv for part in parts for kv in part) == plain
+    import bisect
+    for i, part in enumerate(parts):                  # every key sits where bisect over the thresholds says
+        assert all(bisect.bisect(thr, k if k != -1 else -2) == i for k, _ in part)
+    sizes = [sum(v for _, v in part) for part in parts]
+    assert max(sizes) < 0.5 * len(rows)               # hash % 4 would not help here either; ranges are balanced
+    # percentiles() itself, against exact order statistics of the same numbers
+    p50, p90 = dc.parallelize(list(range(1000)), 4).percentiles([50, 90])
+    assert abs(p50 - 499.5) < 5 and abs(p90 - 899.5) < 5
