@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--parts-per-gpu", type=int, default=8)
     ap.add_argument("--map-splits", type=int, default=8)
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--e2e-depth", type=int, default=2, help="batches in flight in the e2e leg (1 = serial)")
+    ap.add_argument("--e2e-depth", type=int, default=3, help="batches in flight in the e2e leg (1 = serial)")
     ap.add_argument("--cpu-sample-rows", type=int, default=4_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--reduce-impl", type=int, default=2, help="A/B switch of the reduce-side kernel (dpk_set_option)")
@@ -479,7 +479,7 @@ def run_ours(args):
         for _ in range(args.e2e_depth):
             st.collect()
         torch.cuda.synchronize()
-        K2 = max(args.e2e_steps, 2) * 2
+        K2 = max(args.steps, 4 * args.e2e_steps, 12)     # enough batches to amortise the fill and drain of the pipeline
         t0 = time.perf_counter()
         inflight = 0
         for i in range(K2):
