@@ -221,6 +221,48 @@ class RDD(object):
         """dpark/rdd.py:547-550."""
         return self.combineByKey(GroupByAggregator(), numSplits, taskMemory, fixSkew=fixSkew, rddconf=rddconf)
 
+    def groupWith(self, others, numSplits=None, taskMemory=None, fixSkew=-1, rddconf=None):
+        """dpark/rdd.py:686-731: (k, (values of self, values of others[0], ...)) for every key of any input."""
+        if isinstance(others, RDD):
+            others = [others]
+        others = list(others)
+        if numSplits is None:
+            numSplits = self.partitioner.numPartitions if self.partitioner is not None else self.ctx.defaultParallelism
+        thresh = None
+        if fixSkew > 0 and numSplits > 1:
+            thresh, numSplits = self.union(*others)._skew_thresholds(numSplits, fixSkew)
+        return CoGroupedRDD([self] + others, HashPartitioner(numSplits, thresholds=thresh), taskMemory, rddconf=rddconf)
+
+    cogroup = groupWith
+
+    def join(self, other, numSplits=None, taskMemory=None, fixSkew=-1, rddconf=None):
+        """dpark/rdd.py:649-650."""
+        return self._join(other, (), numSplits, taskMemory, fixSkew=fixSkew, rddconf=rddconf)
+
+    def leftOuterJoin(self, other, numSplits=None, taskMemory=None, fixSkew=-1, rddconf=None):
+        return self._join(other, (1,), numSplits, taskMemory, fixSkew=fixSkew, rddconf=rddconf)
+
+    def rightOuterJoin(self, other, numSplits=None, taskMemory=None, fixSkew=-1, rddconf=None):
+        return self._join(other, (2,), numSplits, taskMemory, fixSkew=fixSkew, rddconf=rddconf)
+
+    def outerJoin(self, other, numSplits=None, taskMemory=None, fixSkew=-1, rddconf=None):
+        return self._join(other, (1, 2), numSplits, taskMemory, fixSkew=fixSkew, rddconf=rddconf)
+
+    def _join(self, other, keeps, numSplits=None, taskMemory=None, fixSkew=-1, rddconf=None):
+        """dpark/rdd.py:661-676: the cross product of the two value lists of every key; `keeps` names the sides
+        (1 = left, 2 = right) whose unmatched keys survive, paired with None."""
+        keep_left, keep_right = 1 in keeps, 2 in keeps
+
+        def pairs(row):
+            k, (left, right) = row
+            if not left and keep_right:
+                left = [None]
+            if not right and keep_left:
+                right = [None]
+            return ((k, (a, b)) for a in left for b in right)
+
+        return self.cogroup(other, numSplits, taskMemory, fixSkew=fixSkew, rddconf=rddconf).flatMap(pairs)
+
     def partitionByKey(self, numSplits=None, taskMemory=None, rddconf=None):
         return self.groupByKey(numSplits, taskMemory, rddconf=rddconf).flatMapValue(lambda x: x)
 
@@ -470,6 +512,47 @@ class OutputTextFileRDD(DerivedRDD):
                 f.write(line if line.endswith("\n") else line + "\n")
         os.rename(tmp, path)
         yield path
+
+
+class _TagValue(object):
+    """v -> (input index, v): marks which cogroup input a row came from."""
+
+    def __init__(self, index):
+        self.index = index
+
+    def __call__(self, v):
+        return (self.index, v)
+
+
+class CoGroupedRDD(RDD):
+    """dpark/rdd.py:1264-1376 with the ordered merger (OrderedCoGroupDiskHashMerger, dpark/shuffle.py:683-719):
+    per key one value list per input, each ordered by (map split of that input, position).
+
+    On this path a cogroup IS a group-by: the inputs are concatenated (input 0's splits first, as the reference
+    numbers its dependencies), every value is tagged with its input index, one ordered groupByKey runs on the GPU
+    (values are host objects addressed by row id, dpark_b200/grouping.py), and the tag splits each key's list
+    again -- a stable split, so the (map split, position) order inside every input survives.  Inputs that already
+    share the partitioner are shuffled again rather than read through a narrow dependency
+    (dpark/rdd.py:1280-1293): same result, one avoidable pass."""
+
+    def __init__(self, rdds, partitioner, taskMemory=None, rddconf=None):
+        RDD.__init__(self, rdds[0].ctx)
+        self.size = len(rdds)
+        self.partitioner = partitioner
+        if taskMemory:
+            self.mem = taskMemory
+        tagged = UnionRDD(self.ctx, [MappedValuesRDD(r, _TagValue(i)) for i, r in enumerate(rdds)])
+        self._grouped = ShuffledRDD(tagged, GroupByAggregator(), partitioner, taskMemory, rddconf=rddconf)
+        self.rddconf = self._grouped.rddconf.dup(op=conf.OP_COGROUP)
+        self._splits = self._grouped.splits
+        self._dependencies = self._grouped._dependencies
+
+    def compute(self, split):
+        for k, tagged in self._grouped.iterator(split):
+            groups = tuple([] for _ in range(self.size))
+            for i, v in tagged:
+                groups[i].append(v)
+            yield k, groups
 
 
 class ShuffledRDD(RDD):

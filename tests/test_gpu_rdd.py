@@ -207,3 +207,17 @@ def test_fix_skew_balances_a_hot_hash_range_and_keeps_results():
     # percentiles() itself, against exact order statistics of the same numbers
     p50, p90 = dc.parallelize(list(range(1000)), 4).percentiles([50, 90])
     assert abs(p50 - 499.5) < 5 and abs(p90 - 899.5) < 5
+
+
+# ---- cogroup / join: the same golden cases as tests/test_cogroup_host.py, real engine
+from tests import cogroup_common as _cc  # noqa: E402
+
+
+@pytest.mark.parametrize("case", _cc.COGROUP_CASES, ids=[c["name"] for c in _cc.COGROUP_CASES])
+def test_cogroup_matches_reference_on_the_gpu(case):
+    _cc.check_cogroup(case)
+
+
+@pytest.mark.parametrize("case", _cc.JOIN_CASES, ids=[c["name"] for c in _cc.JOIN_CASES])
+def test_joins_match_reference_on_the_gpu(case):
+    _cc.check_join(case)
