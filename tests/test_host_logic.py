@@ -282,3 +282,29 @@ def test_push_plan_reproduces_the_alltoallv_layout(G, P, sb):
             got[d][b:b + c] = bufs[s][a:a + c]
     for d in range(G):
         assert np.array_equal(got[d], want[d])
+
+
+def test_sample_rdd_draws_like_the_reference():
+    """SampleRDD (dpark/rdd.py:1379-1397): random.Random(seed + split.index), one draw per row, keep if <= frac;
+    with replacement: ceil(len * frac) choices.  Restated here with the stdlib generator the reference uses."""
+    import random
+    import sys
+    sys.argv = [sys.argv[0]]
+    from dpark_b200 import DparkContext
+    dc = DparkContext("local")
+    rows = list(range(1000))
+    rdd = dc.parallelize(rows, 4)
+    parts = rdd.glom().collect()
+    got = rdd.sample(0.3).glom().collect()
+    for i, part in enumerate(parts):
+        rd = random.Random(12345 + i)
+        assert got[i] == [x for x in part if rd.random() <= 0.3]
+    got = rdd.sample(0.1, True, 7).glom().collect()
+    for i, part in enumerate(parts):
+        rd = random.Random(7 + i)
+        assert got[i] == [rd.choice(part) for _ in range(int(np.ceil(len(part) * 0.1)))]
+    # percentiles(): host-side digest over the partitions (no shuffle involved)
+    p = rdd.percentiles([0, 50, 100])
+    assert p[0] == 0.0 and p[2] == 999.0 and abs(p[1] - 499.5) < 5
+    with pytest.raises(ValueError):
+        rdd.percentiles([50], sampleRate=0)
