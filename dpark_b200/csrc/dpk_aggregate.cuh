@@ -49,11 +49,11 @@ __device__ __forceinline__ long long sm_cas(uint32_t a, long long cmp, long long
 // 128-bit compare-and-swap on a whole {key, accumulator} slot (native ATOMS.CAS.128 on sm_100): a row
 // that finds a free slot claims it AND deposits its value in one atomic; returns the old key word.
 __device__ __forceinline__ long long sm_cas_slot(uint32_t a, long long ckey, long long cacc, long long nkey, long long nacc) {
-    long long olo, ohi;
+    long long olo;
+    [[maybe_unused]] long long ohi;  // the old accumulator word: not needed, the key word tells who owns the slot
     asm volatile("{\n\t.reg .b128 c, s, o;\n\tmov.b128 c, {%3, %4};\n\tmov.b128 s, {%5, %6};\n\t"
                  "atom.shared.cas.b128 o, [%2], c, s;\n\tmov.b128 {%0, %1}, o;\n\t}"
                  : "=l"(olo), "=l"(ohi) : "r"(a), "l"(ckey), "l"(cacc), "l"(nkey), "l"(nacc) : "memory");
-    (void)ohi;
     return olo;
 }
 // 64-bit integer add into shared memory.  sm_100 has no native 64-bit shared-memory add

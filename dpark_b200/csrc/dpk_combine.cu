@@ -2,22 +2,26 @@
 // (dpark/shuffle.py:600-608): combined[k] = mergeCombiners(combined[k], v) over
 // every row fetched for the reduce partitions this GPU owns.
 //
-// Design: open addressing in HBM with 16-byte slots {key bits, accumulator} (a
-// probe + update touches one 32 B sector), ONE TABLE REGION PER FINE BUCKET.
-// The map side already grouped rows by fine bucket (partition x 2^sub_bits), so
-// rows that are adjacent in memory hit the same small region: with ~0.5 M rows per
-// bucket the region (~12 MB) lives in the 126 MB L2 while it is being filled and
-// the atomics run at L2 speed instead of one random DRAM sector per row.
-//   k_tbl_plan    : per-bucket region offsets (1.5 x rows) + per-partition output offsets
-//   k_tbl_init    : slots <- {EMPTY, identity(op)}
-//   k_tbl_insert  : per row: bucket from the key's hash, claim a slot with atomicCAS
-//                   on the key word (linear probing inside the region), then one
-//                   native atomic on the accumulator.
-//   k_tbl_compact : per occupied slot: recompute its partition, reserve an output
-//                   index inside that partition's range (CTA-aggregated), write.
-// Accumulators: int64 for integer values (exact while |sum| < 2^63, as the
-// reference's big ints), float64 for float values (the reference adds Python
-// floats).  Algorithmic bytes: (K+V) * (rows + distinct).
+// Three implementations behind dpk_combine (dpk_set_option "reduce_impl"), all bit-identical:
+//
+//   2 (default)  second-level split + shared-memory merge.  Every first-level bucket of the received
+//      rows is split once more by further hash bits (seg_multisplit, dpk_partition.cu) into fine
+//      buckets of <= ~2 k rows; k_smem_aggregate (dpk_aggregate.cuh) merges one fine bucket per CTA in
+//      a 4096-slot shared-memory table and writes its distinct rows straight into the partition's
+//      output range (chained look-back for the offset).  Probes cost ~30 cycles instead of an L2 round
+//      trip; DRAM traffic = the algorithmic (K+V) * (rows + distinct) plus the split's 2 * (K+V) * rows.
+//   1  one thread-block cluster of 8 CTAs per first-level bucket (k_bucket_reduce): the bucket's
+//      table region in HBM is initialised, filled and compacted while it is L2-resident.
+//   0  three grid-wide passes over per-bucket table regions in HBM:
+//        k_tbl_init    : slots <- {EMPTY, identity(op)}
+//        k_tbl_insert  : per row: bucket from the key's hash, claim a slot with atomicCAS on the key
+//                        word (linear probing inside the region), then one native atomic on the accumulator
+//        k_tbl_compact : per occupied slot: recompute its partition, reserve an output index inside
+//                        that partition's range (CTA-aggregated), write.
+// Common to all: 16-byte slots {key bits, accumulator}; k_tbl_plan computes per-bucket region offsets
+// (1.5 x rows), per-partition output offsets and the first row of every (source, bucket) segment.
+// Accumulators: int64 for integer values (exact while |sum| < 2^63, as the reference's big ints),
+// float64 for float values (the reference adds Python floats).
 #include "dpk_common.cuh"
 #include <cooperative_groups.h>
 #include <type_traits>

@@ -8,14 +8,20 @@
 // buffer (buckets owned by one peer are adjacent).
 //
 // Kernels (HBM-bound integer work, no tensor cores):
-//   k_part_count   : each CTA owns one contiguous row range ("chunk" of the grid),
-//                    hashes keys, counts rows per bucket -> tile_counts[P][T].
+//   k_part_count   : each CTA owns one contiguous row range of the grid, hashes keys, counts rows per
+//                    bucket (warp-private shared-memory histograms) -> tile_counts[P][T].
 //   k_part_scan    : per bucket, exclusive scan over the T CTAs.
-//   k_part_scatter : each CTA re-reads its range tile by tile (4096 rows): fused
-//                    hash -> pid -> warp-level match ranks -> block multisplit in
-//                    shared memory -> coalesced run-wise stores to HBM.
-// Algorithmic bytes: 2*(K+V) per row (read once, write once); this two-pass
-// form re-reads K once more for the histogram (not credited).
+//   k_part_scatter : each CTA re-reads its range tile by tile (4096 rows): fused hash -> bucket ->
+//                    rank inside the tile -> block multisplit in shared memory -> run-wise coalesced
+//                    stores to HBM.  Ranking is STABLE by default (warp match + leader: rows of a bucket
+//                    stay in input order, what groupByKey and the LSD radix passes need) or, with
+//                    DPK_K_UNORDERED, one native shared-memory atomic per row (reduceByKey paths).
+// Modes of the same kernels: plain (one chunk of rows -> bucket-major output), pointer (every bucket has
+// its own destination address, possibly peer-GPU memory: dpk_partition_scatter_ptrs), segmented (the grid
+// runs over a device-built chunk table and splits every first-level bucket again: seg_multisplit, the
+// first stage of the reduce side), radix digit (dpk_radix_pass).
+// Algorithmic bytes: 2*(K+V) per row (read once, write once); this two-pass form re-reads K once more
+// for the histogram (not credited).
 #include "dpk_common.cuh"
 
 namespace dpk {

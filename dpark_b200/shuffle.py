@@ -3,7 +3,8 @@ columnar partitions held as torch CUDA tensors.
 
 Mirrors, for the hot path only:
   ShuffleMapTask._run          dpark/task.py:197-255      -> map_side()
-  ShuffleFetcher.fetch         dpark/shuffle.py:309-420   -> exchange()  (one NCCL alltoallv)
+  ShuffleFetcher.fetch         dpark/shuffle.py:309-420   -> exchange()  (one NCCL alltoallv; the NVLink
+                                                             peer-memory forms live in dpark_b200/peer.py)
   DiskHashMerger._merge        dpark/shuffle.py:600-608   -> reduce_side()
   MapOutputTracker             dpark/shuffle.py:809-826   -> the counts matrix
 
@@ -11,8 +12,8 @@ Layout.  The map side writes ONE bucket-major buffer per rank.  Buckets are the
 reference's P reduce partitions, each refined into 2^sub_bits sub-buckets by
 other hash bits (dpk_partition, include/dpark_b200.h): partition p is the
 concatenation of its sub-buckets, so everything the reference defines (which
-keys a partition owns, row order inside a bucket) is unchanged, while the
-reduce side gets L2-sized working sets.
+keys a partition owns, row order inside a bucket where it is observable) is
+unchanged, while the reduce side gets bounded working sets.
 
 Ownership across G ranks: reduce partition r lives on rank r // ceil(P/G)
 (contiguous blocks), so what a rank sends to one peer is one contiguous range of
@@ -24,7 +25,7 @@ import torch
 from . import _native as nv
 
 # rows per first-level bucket the reduce side aims for: it splits every bucket once
-# more into <= 256 fine buckets of ~2 k rows that are merged in shared memory
+# more (<= 1024-way) into fine buckets of <= ~2 k rows that are merged in shared memory
 # (dpk_combine.cu, implementation 2), so 2^19 rows per bucket is the upper end
 TARGET_BUCKET_ROWS = 1 << 19
 
