@@ -308,3 +308,26 @@ def test_sample_rdd_draws_like_the_reference():
     assert p[0] == 0.0 and p[2] == 999.0 and abs(p[1] - 499.5) < 5
     with pytest.raises(ValueError):
         rdd.percentiles([50], sampleRate=0)
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to ours): exactly one JSON line on stdout
+    with the contract's keys, measured on the oracle's CPython port (bounded sample so this stays quick)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--cpu-sample-rows", "8000"], capture_output=True, text=True, timeout=300,
+                         cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    b = json.loads(lines[0])
+    assert b["impl"] == "reference" and b["unit"] == "rows/s" and b["higher_is_better"] is True
+    assert b["metric"] == "shuffled rows/sec (reduceByKey end-to-end)"
+    assert b["value"] > 0 and b["n_gpus"] == 1 and b["scaling"] == "weak" and b["dtype"] == "int64"
+    assert b["cpu_baseline"]["kind"] == "port" and b["cpu_baseline"]["cores"] >= 1
+    assert b["cpu_baseline"]["value"] == b["value"]
+    assert b["e2e"] == {"value": b["value"], "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in b["config"]
