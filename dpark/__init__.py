@@ -6,5 +6,5 @@ import sys as _sys
 import dpark_b200 as _impl
 
 _sys.modules[__name__] = _impl
-for _name in ("conf", "rdd", "context", "dependency"):
+for _name in ("conf", "rdd", "context", "dependency", "bagel", "accumulator"):
     _sys.modules[__name__ + "." + _name] = __import__("dpark_b200." + _name, fromlist=["_"])

@@ -124,6 +124,11 @@ class DparkContext(object):
     def makeRDD(self, seq, numSlices=None):
         return self.parallelize(seq, numSlices)
 
+    def accumulator(self, init=0, param=None):
+        """dpark/context.py:364-365."""
+        from .accumulator import Accumulator
+        return Accumulator(init, param)
+
     def parallelizeColumns(self, keys, values, numSlices=None):
         """Extension: a (k, v) RDD from two columns (numpy arrays or torch tensors,
         host or cuda) -- rows never become Python tuples on the way to the shuffle."""

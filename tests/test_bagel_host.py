@@ -1,0 +1,92 @@
+"""Bagel (dpark_b200/bagel.py) against results captured from the reference's Bagel on the same jobs
+(tests/golden/make_bagel_golden.py, tests/bagel_jobs.py).  CPU: the two shuffles of every superstep
+(combineByKey of the messages, groupWith of vertices and messages) go through a stand-in engine built from the
+oracle's hash/partition functions; the loop, the accumulators, the aggregator plumbing and the termination rule
+are the code under test.  PageRank values are float sums whose order the reference does not fix: tolerance
+1e-12 relative."""
+import sys
+
+import pytest
+
+from oracle import oracle as orc
+from tests import bagel_jobs
+from tests.golden_util import load
+
+CASES = load("bagel_cases.json")["cases"]
+
+
+@pytest.fixture
+def standin_engine(monkeypatch):
+    from dpark_b200 import columnar, engine
+
+    def run_shuffle(srdd):
+        P, thr = srdd.partitioner.numPartitions, srdd.partitioner.thresholds
+        agg = srdd.aggregator
+        buckets = [dict() for _ in range(P)]
+        for sp in srdd.parent.splits:
+            for k, v in srdd.parent.iterator(sp):
+                b = buckets[orc.get_partition(k, P, thr)]
+                if srdd.kind == "group":
+                    b.setdefault(k, []).append(v)
+                else:
+                    b[k] = agg.mergeValue(b[k], v) if k in b else agg.createCombiner(v)
+        res = engine.ShuffleResult(P)
+        for p, b in enumerate(buckets):
+            res.parts[p] = (list(b.keys()), list(b.values()))
+        return res
+
+    monkeypatch.setattr(engine, "run_shuffle", run_shuffle)
+    monkeypatch.setattr(columnar, "hashes_of_keys", lambda keys: [orc.portable_hash(k) for k in keys])
+
+
+def _ctx():
+    sys.argv = [sys.argv[0]]
+    from dpark_b200 import DparkContext
+    return DparkContext("local")
+
+
+@pytest.mark.parametrize("case", [c for c in CASES if c["job"] == "pagerank"], ids=lambda c: c["name"])
+def test_pagerank_matches_the_reference(case, standin_engine):
+    from dpark_b200 import bagel
+    got = bagel_jobs.run_pagerank(_ctx(), bagel, case["graph"], case["parts"])
+    want = {k: float.fromhex(v) for k, v in case["values"].items()}
+    assert sorted(got) == sorted(want)
+    for k in want:
+        assert abs(got[k] - want[k]) <= 1e-12 * abs(want[k])
+    assert abs(sum(got.values()) - sum(want.values())) < 1e-12
+
+
+@pytest.mark.parametrize("case", [c for c in CASES if c["job"] == "maxprop"], ids=lambda c: c["name"])
+def test_max_propagation_with_aggregator_matches_the_reference(case, standin_engine):
+    from dpark_b200 import bagel
+    got = bagel_jobs.run_maxprop(_ctx(), bagel, [[v, ts] for v, ts in case["graph"]], case["parts"])
+    assert {str(k): v for k, v in got.items()} == case["values"]
+
+
+def test_bagel_surface_and_termination(standin_engine):
+    from dpark_b200 import bagel
+    from dpark_b200.accumulator import Accumulator, listAcc
+    dc = _ctx()
+    calls = []
+
+    def compute(vert, inbox):                      # two-argument form through addAggregatorArg
+        calls.append(vert.id)
+        return bagel.Vertex(vert.id, vert.value + 1, [], False), []
+
+    verts = dc.parallelize([(i, bagel.Vertex(i, 0, [], True)) for i in range(4)], 2)
+    out = bagel.Bagel.run(dc, verts, dc.parallelize([], 2), bagel.Bagel.addAggregatorArg(compute))
+    assert sorted((k, v.value, v.active) for k, v in out.collect()) == [(i, 1, False) for i in range(4)]
+    # maxSuperstep bounds the loop even when vertices stay active
+    def forever(vert, inbox, agg, step):
+        return bagel.Vertex(vert.id, step, [], True), []
+    out = bagel.Bagel.run(dc, verts, dc.parallelize([], 2), forever, maxSuperstep=3)
+    assert set(v.value for _, v in out.collect()) == {2}
+    # combiners the GPU shuffle cannot express are refused when the job is declared
+    with pytest.raises(NotImplementedError):
+        bagel.Bagel.run(dc, verts, dc.parallelize([(0, 1)], 2), forever, combiner=bagel.DefaultListCombiner(),
+                        maxSuperstep=1)
+    acc = Accumulator([], listAcc)
+    acc.add([1])
+    acc.add([2])
+    assert acc.value == [1, 2] and acc.reset() == [1, 2] and acc.value == []
+    assert dc.accumulator(5).value == 5
