@@ -4,7 +4,6 @@
 straight into the destination GPU's receive buffer over NVLink?  Run under torchrun."""
 import os
 import sys
-import time
 
 import torch
 import torch.distributed as dist

@@ -1,7 +1,6 @@
 """Two Bagel jobs used by the golden generator (run on the reference) and by the tests (run on this package):
 the module that provides Vertex / Edge / Bagel / BasicCombiner / Aggregator is passed in, so the same job
 text drives both implementations."""
-import operator
 
 
 def random_graph(rnd, nv, deg, ring=False, int_ids=False):
