@@ -528,31 +528,53 @@ class CoGroupedRDD(RDD):
     """dpark/rdd.py:1264-1376 with the ordered merger (OrderedCoGroupDiskHashMerger, dpark/shuffle.py:683-719):
     per key one value list per input, each ordered by (map split of that input, position).
 
-    On this path a cogroup IS a group-by: the inputs are concatenated (input 0's splits first, as the reference
-    numbers its dependencies), every value is tagged with its input index, one ordered groupByKey runs on the GPU
-    (values are host objects addressed by row id, dpark_b200/grouping.py), and the tag splits each key's list
-    again -- a stable split, so the (map split, position) order inside every input survives.  Inputs that already
-    share the partitioner are shuffled again rather than read through a narrow dependency
-    (dpark/rdd.py:1280-1293): same result, one avoidable pass."""
+    On this path a cogroup IS a group-by: the inputs that need a shuffle are concatenated (in dependency order),
+    every value is tagged with its input index, one ordered groupByKey runs on the GPU (values are host objects
+    addressed by row id, dpark_b200/grouping.py), and the tag splits each key's list again -- a stable split, so
+    the (map split, position) order inside every input survives.
+
+    An input that is already partitioned by the same partitioner is NOT shuffled (the reference's narrow
+    dependency, dpark/rdd.py:1280-1293): its partition j is read as is and merged into partition j of the result,
+    values in the partition's own iteration order.  Iterative jobs live on this -- in Bagel both inputs of the
+    superstep's groupWith (the vertices of the previous superstep, the combined messages) carry the partitioner."""
 
     def __init__(self, rdds, partitioner, taskMemory=None, rddconf=None):
         RDD.__init__(self, rdds[0].ctx)
         self.size = len(rdds)
+        self.rdds = list(rdds)
         self.partitioner = partitioner
         if taskMemory:
             self.mem = taskMemory
-        tagged = UnionRDD(self.ctx, [MappedValuesRDD(r, _TagValue(i)) for i, r in enumerate(rdds)])
-        self._grouped = ShuffledRDD(tagged, GroupByAggregator(), partitioner, taskMemory, rddconf=rddconf)
-        self.rddconf = self._grouped.rddconf.dup(op=conf.OP_COGROUP)
-        self._splits = self._grouped.splits
-        self._dependencies = self._grouped._dependencies
+        self.narrow = [i for i, r in enumerate(rdds) if r.partitioner == partitioner]
+        moved = [i for i in range(self.size) if i not in self.narrow]
+        self._grouped = None
+        if moved:
+            tagged = UnionRDD(self.ctx, [MappedValuesRDD(rdds[i], _TagValue(i)) for i in moved])
+            self._grouped = ShuffledRDD(tagged, GroupByAggregator(), partitioner, taskMemory, rddconf=rddconf)
+            self._dependencies = self._grouped._dependencies
+        self.set_rddconf(rddconf)
+        self.rddconf = self.rddconf.dup(op=conf.OP_COGROUP)
+        self._splits = [Split(i) for i in range(partitioner.numPartitions)]
 
     def compute(self, split):
-        for k, tagged in self._grouped.iterator(split):
-            groups = tuple([] for _ in range(self.size))
-            for i, v in tagged:
-                groups[i].append(v)
-            yield k, groups
+        merged = {}
+
+        def lists_of(k):
+            groups = merged.get(k)
+            if groups is None:
+                groups = merged[k] = tuple([] for _ in range(self.size))
+            return groups
+
+        if self._grouped is not None:
+            for k, tagged in self._grouped.iterator(self._grouped.splits[split.index]):
+                groups = lists_of(k)
+                for i, v in tagged:
+                    groups[i].append(v)
+        for i in self.narrow:
+            rdd = self.rdds[i]
+            for k, v in rdd.iterator(rdd.splits[split.index]):
+                lists_of(k)[i].append(v)
+        return iter(merged.items())
 
 
 class ShuffledRDD(RDD):

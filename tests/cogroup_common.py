@@ -28,7 +28,13 @@ def inputs_of(dc, case):
 def check_cogroup(case):
     dc = ctx()
     rdds = inputs_of(dc, case)
+    if case["op"] == "cogroup_prepartitioned":      # as the generator: the left input already has the partitioner
+        from dpark_b200 import HashPartitioner
+        rdds[0] = rdds[0].groupByKey(case["P"]).flatMapValue(lambda x: x)
+        assert rdds[0].partitioner == HashPartitioner(case["P"])
     out = rdds[0].groupWith(rdds[1:], case["P"], fixSkew=case.get("fixSkew", -1))
+    if case["op"] == "cogroup_prepartitioned":
+        assert out.narrow == [0]
     if "thresholds" in case:
         assert out.partitioner.thresholds == case["thresholds"]
     parts = out.glom().collect()

@@ -8,35 +8,11 @@ import sys
 
 import pytest
 
-from oracle import oracle as orc
 from tests import bagel_jobs
+from tests.standin import standin_engine  # noqa: F401  (fixture)
 from tests.golden_util import load
 
 CASES = load("bagel_cases.json")["cases"]
-
-
-@pytest.fixture
-def standin_engine(monkeypatch):
-    from dpark_b200 import columnar, engine
-
-    def run_shuffle(srdd):
-        P, thr = srdd.partitioner.numPartitions, srdd.partitioner.thresholds
-        agg = srdd.aggregator
-        buckets = [dict() for _ in range(P)]
-        for sp in srdd.parent.splits:
-            for k, v in srdd.parent.iterator(sp):
-                b = buckets[orc.get_partition(k, P, thr)]
-                if srdd.kind == "group":
-                    b.setdefault(k, []).append(v)
-                else:
-                    b[k] = agg.mergeValue(b[k], v) if k in b else agg.createCombiner(v)
-        res = engine.ShuffleResult(P)
-        for p, b in enumerate(buckets):
-            res.parts[p] = (list(b.keys()), list(b.values()))
-        return res
-
-    monkeypatch.setattr(engine, "run_shuffle", run_shuffle)
-    monkeypatch.setattr(columnar, "hashes_of_keys", lambda keys: [orc.portable_hash(k) for k in keys])
 
 
 def _ctx():

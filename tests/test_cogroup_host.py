@@ -4,28 +4,8 @@ the oracle's hash/partition functions that honours the same contract (per partit
 (map split, position) order).  The same cases run through the real engine in tests/test_gpu_rdd.py."""
 import pytest
 
-from oracle import oracle as orc
 from tests import cogroup_common as cc
-
-
-@pytest.fixture
-def standin_engine(monkeypatch):
-    from dpark_b200 import columnar, engine
-
-    def run_shuffle(srdd):
-        assert srdd.kind == "group"
-        P, thr = srdd.partitioner.numPartitions, srdd.partitioner.thresholds
-        buckets = [dict() for _ in range(P)]
-        for sp in srdd.parent.splits:
-            for k, v in srdd.parent.iterator(sp):
-                buckets[orc.get_partition(k, P, thr)].setdefault(k, []).append(v)
-        res = engine.ShuffleResult(P)
-        for p, b in enumerate(buckets):
-            res.parts[p] = (list(b.keys()), list(b.values()))
-        return res
-
-    monkeypatch.setattr(engine, "run_shuffle", run_shuffle)
-    monkeypatch.setattr(columnar, "hashes_of_keys", lambda keys: [orc.portable_hash(k) for k in keys])
+from tests.standin import standin_engine  # noqa: F401  (fixture)
 
 
 @pytest.mark.parametrize("case", cc.COGROUP_CASES, ids=[c["name"] for c in cc.COGROUP_CASES])
@@ -48,3 +28,31 @@ def test_group_with_accepts_one_rdd_or_a_list_and_defaults(standin_engine):
     assert len(a.groupWith(b).splits) == dc.defaultParallelism
     assert dict(a.join(b).collect()) == {2: ("b", "x")}
     assert sorted(a.leftOuterJoin(b).collect()) == [(1, ("a", None)), (2, ("b", "x"))]
+
+
+def test_co_partitioned_inputs_are_not_shuffled_again(standin_engine):
+    """dpark/rdd.py:1280-1293: inputs that already carry the partitioner are read through narrow dependencies.
+    When every input does, the cogroup is a per-partition merge with no shuffle at all (Bagel's steady state)."""
+    import random
+    dc = cc.ctx()
+    rnd = random.Random(9)
+    ra = [(rnd.randrange(40), rnd.randrange(100)) for _ in range(300)]
+    rb = [(rnd.randrange(20, 60), rnd.randrange(100)) for _ in range(200)]
+    a = dc.parallelize(ra, 4).groupByKey(3).flatMapValue(lambda vs: vs)
+    b = dc.parallelize(rb, 2).reduceByKey(lambda x, y: x + y, 3)
+    out = a.groupWith(b)                                  # numSplits defaults to a's partitioner
+    assert out.narrow == [0, 1] and out._grouped is None and len(out.splits) == 3
+    plain = dc.parallelize(ra, 4).groupWith(dc.parallelize(rb, 2).reduceByKey(lambda x, y: x + y, 3), 3)
+    assert plain.narrow == [1] and plain._grouped is not None
+    canon = lambda rdd: [sorted((k, sorted(g0), sorted(g1)) for k, (g0, g1) in part) for part in rdd.glom().collect()]
+    assert canon(out) == canon(plain)
+    want = {}
+    for k, v in ra:
+        want.setdefault(k, ([], []))[0].append(v)
+    sums = {}
+    for k, v in rb:
+        sums[k] = sums.get(k, 0) + v
+    for k, v in sums.items():
+        want.setdefault(k, ([], []))[1].append(v)
+    got = dict((k, (sorted(g0), sorted(g1))) for k, (g0, g1) in out.collect())
+    assert got == dict((k, (sorted(g0), sorted(g1))) for k, (g0, g1) in want.items())
