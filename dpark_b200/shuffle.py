@@ -267,6 +267,9 @@ class HostShuffleStream(object):
         s.submit(h_keys, h_vals)            # pinned host columns; returns immediately
         s.submit(h_keys2, h_vals2)
         parts = s.collect()                 # result of the OLDEST batch: [(partition, keys, vals)] pinned host
+
+    The tensors collect() returns are views of the slot's pinned output buffers: they stay valid until
+    that slot is collected again, i.e. for the next `depth - 1` collect() calls; copy what must live longer.
     """
 
     class _Slot(object):
