@@ -263,6 +263,28 @@ class RDD(object):
 
         return self.cogroup(other, numSplits, taskMemory, fixSkew=fixSkew, rddconf=rddconf).flatMap(pairs)
 
+    def uniq(self, numSplits=None, taskMemory=None, rddconf=None):
+        """dpark/rdd.py:383-385: the distinct elements, partitioned by their hash.  The reference merges `None`
+        values with `lambda x, y: None`; the GPU shuffle needs a recognised op, so the placeholder value is 0
+        merged with `or` -- the keys and their partitions are the same."""
+        import operator
+        return self.map(lambda x: (x, 0)).reduceByKey(operator.or_, numSplits, taskMemory, rddconf=rddconf) \
+                   .map(lambda kv: kv[0])
+
+    def top(self, n=10, key=None, reverse=False):
+        """dpark/rdd.py:387-394: the n largest (smallest with reverse) elements; per partition, then overall."""
+        import heapq
+        pick = heapq.nsmallest if reverse else heapq.nlargest
+        best = []
+        for part in self.ctx.runJob(self, lambda it: pick(n, it, key)):
+            best.extend(part)
+        return pick(n, best, key)
+
+    def hot(self, n=10, numSplits=None, taskMemory=None, rddconf=None):
+        """dpark/rdd.py:396-398: the n most frequent elements with their counts."""
+        counts = self.map(lambda x: (x, 1)).reduceByKey(lambda a, b: a + b, numSplits, taskMemory, rddconf=rddconf)
+        return counts.top(n, key=lambda kv: kv[1])
+
     def partitionByKey(self, numSplits=None, taskMemory=None, rddconf=None):
         return self.groupByKey(numSplits, taskMemory, rddconf=rddconf).flatMapValue(lambda x: x)
 

@@ -56,3 +56,25 @@ def test_co_partitioned_inputs_are_not_shuffled_again(standin_engine):
         want.setdefault(k, ([], []))[1].append(v)
     got = dict((k, (sorted(g0), sorted(g1))) for k, (g0, g1) in out.collect())
     assert got == dict((k, (sorted(g0), sorted(g1))) for k, (g0, g1) in want.items())
+
+
+def test_uniq_top_hot(standin_engine):
+    """dpark/rdd.py:383-398 over the shuffle: uniq keeps one of each element in the partition its hash selects;
+    hot = counts + top."""
+    import collections
+    import random
+    from oracle import oracle as orc
+    dc = cc.ctx()
+    rnd = random.Random(1)
+    xs = [rnd.randrange(-30, 30) for _ in range(500)] + ["w%d" % rnd.randrange(9) for _ in range(0)]
+    parts = dc.parallelize(xs, 5).uniq(4).glom().collect()
+    assert sorted(x for p in parts for x in p) == sorted(set(xs))
+    assert all(orc.get_partition(x, 4) == i for i, p in enumerate(parts) for x in p)
+    words = ["w%d" % int(rnd.paretovariate(1.2)) for _ in range(800)]
+    hot = dc.parallelize(words, 3).hot(5, 2)
+    want = collections.Counter(words).most_common()
+    assert [c for _, c in hot] == [c for _, c in want[:5]]
+    assert all(dict(want)[w] == c for w, c in hot)
+    nums = dc.parallelize(list(range(100)), 7)
+    assert nums.top(3) == [99, 98, 97] and nums.top(2, reverse=True) == [0, 1]
+    assert nums.top(2, key=lambda x: -abs(x - 50)) == [50, 49]
