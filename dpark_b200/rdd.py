@@ -285,6 +285,23 @@ class RDD(object):
         counts = self.map(lambda x: (x, 1)).reduceByKey(lambda a, b: a + b, numSplits, taskMemory, rddconf=rddconf)
         return counts.top(n, key=lambda kv: kv[1])
 
+    def topByKey(self, top_n, order_func=None, reverse=False, num_splits=None, task_memory=None, fixSkew=-1):
+        """dpark/rdd.py:552-594: per key the top_n values by `order_func` (the value itself when None), ascending,
+        or the top_n largest in descending order with reverse=True; values that compare equal keep the order in
+        which they were met -- (input partition, position) -- and the oldest ones win.
+
+        The reference keeps a bounded heap per key on both sides of the shuffle (HeapAggregator,
+        dpark/dependency.py:164-193) over (order, partition, sequence, value) tuples.  The GPU group-by already
+        delivers every key's values in (partition, position) order, so the same answer is a stable sort of that
+        list (Python's sort is stable for reverse=True as well) cut at top_n."""
+        if top_n <= 0:
+            raise AssertionError("top_n must be positive")
+
+        def best(values):
+            return sorted(values, key=order_func, reverse=reverse)[:top_n]
+
+        return self.groupByKey(num_splits, task_memory, fixSkew=fixSkew).mapValue(best)
+
     def partitionByKey(self, numSplits=None, taskMemory=None, rddconf=None):
         return self.groupByKey(numSplits, taskMemory, rddconf=rddconf).flatMapValue(lambda x: x)
 

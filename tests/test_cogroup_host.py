@@ -78,3 +78,21 @@ def test_uniq_top_hot(standin_engine):
     nums = dc.parallelize(list(range(100)), 7)
     assert nums.top(3) == [99, 98, 97] and nums.top(2, reverse=True) == [0, 1]
     assert nums.top(2, key=lambda x: -abs(x - 50)) == [50, 49]
+
+
+TOPK = __import__("tests.golden_util", fromlist=["load"]).load("topbykey_cases.json")["cases"]
+TOPK_ORDER = {"none": None, "first": lambda x: x[0], "mod7": lambda x: x % 7, "neg": lambda x: -x}
+
+
+@pytest.mark.parametrize("case", TOPK, ids=[c["name"] for c in TOPK])
+def test_top_by_key_matches_reference(case, standin_engine):
+    """topByKey against the reference's outputs (its own test inputs, tests/test_rdd.py:353-374, and seeded rows
+    with many ties): bounded-heap semantics = stable sort of the (partition, position)-ordered group, cut."""
+    import json
+    from tests.golden.make_golden import enc
+    from tests.golden_util import dec
+    dc = cc.ctx()
+    rows = [(dec(k), dec(v)) for k, v in case["rows"]]
+    out = dc.makeRDD(rows, case["M"]).topByKey(case["top_n"], TOPK_ORDER[case["order"]], case["reverse"], case["P"])
+    got = [sorted(([enc(k), enc(list(v))] for k, v in part), key=json.dumps) for part in out.glom().collect()]
+    assert got == case["parts"]
