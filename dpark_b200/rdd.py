@@ -21,6 +21,8 @@ from . import columnar, conf, quantiles, trace
 from .dependency import Aggregator, GroupByAggregator, HashPartitioner, Partitioner, ShuffleDependency
 from .errors import DparkUserFatalError  # noqa: F401
 
+_enumerate = enumerate      # RDD.enumerate shadows the builtin inside the class body
+
 
 class Split(object):
     def __init__(self, index):
@@ -301,6 +303,101 @@ class RDD(object):
             return sorted(values, key=order_func, reverse=reverse)[:top_n]
 
         return self.groupByKey(num_splits, task_memory, fixSkew=fixSkew).mapValue(best)
+
+    def groupBy(self, f, numSplits=None, rddconf=None):
+        """dpark/rdd.py:298-301."""
+        if numSplits is None:
+            numSplits = min(self.ctx.defaultMinSplits, len(self))
+        return self.map(lambda x: (f(x), x)).groupByKey(numSplits, rddconf=rddconf)
+
+    def update(self, other, replace_only=False, numSplits=None, taskMemory=None, fixSkew=-1, rddconf=None):
+        """dpark/rdd.py:599-624: this (k, v) RDD with the values `other` holds for the same keys put in their
+        place; keys only `other` has are added unless replace_only.
+
+        The reference folds (value, origin bit) pairs with an order-sensitive lambda, which the GPU shuffle cannot
+        express as one of its ops; the same table falls out of a cogroup: a key's new value is the first one
+        `other` holds for it in (input partition, position) order, else its first old value -- the outcome the
+        reference's fold gives when it meets the rows in that order."""
+        def pick(groups):
+            old, new = groups
+            return new[0] if new else old[0]
+
+        both = self.groupWith(other, numSplits, taskMemory, fixSkew=fixSkew, rddconf=rddconf)
+        if replace_only:
+            both = both.filter(lambda kv: bool(kv[1][0]))
+        return both.mapValue(pick)
+
+    def innerJoin(self, smallRdd):
+        """dpark/rdd.py:626-647: join against a small RDD held as a dict on the host (no shuffle)."""
+        import collections
+        table = collections.defaultdict(list)
+        for k, v in smallRdd.collect():
+            table[k].append(v)
+
+        def matches(kv):
+            k, v = kv
+            return [(k, (v, w)) for w in table.get(k, ())]
+
+        return self.flatMap(matches)
+
+    def percentilesByKey(self, p, sampleRate=1.0, func=None, numSplits=None, taskMemory=None, fixSkew=-1):
+        """dpark/rdd.py:815-850: per key the requested percentiles of its values (t-digest).  The reference builds
+        one digest per key and map task and merges them on the reduce side in fetch order; here the values of a key
+        arrive grouped and ordered by (input partition, position), each carries its partition index, and the same
+        digests are built and merged in partition order -- one of the orders the reference may take."""
+        if sampleRate <= 0:
+            raise ValueError("Sample Rate should be positive.")
+        rdd = self if sampleRate >= 1.0 else self.sample(sampleRate)
+        if func:
+            rdd = rdd.mapValue(func)
+
+        def quantiles_of(tagged):
+            merged, current, digest = None, None, None
+            for part, x in tagged:
+                if part != current:
+                    if digest is not None:
+                        merged = digest if merged is None else merged.absorb(digest)
+                        merged.compress()
+                    current, digest = part, quantiles.MergingDigest()
+                digest.add(x)
+            if digest is not None:
+                merged = digest if merged is None else merged.absorb(digest)
+                merged.compress()
+            return [merged.quantile(pp / 100.) for pp in p]
+
+        tagged = rdd.mapPartitionWithIndex(lambda i, it: ((k, (i, v)) for k, v in it))
+        return tagged.groupByKey(numSplits, taskMemory, fixSkew=fixSkew).mapValue(quantiles_of)
+
+    def fold(self, zero, f):
+        """dpark/rdd.py:400-408."""
+        import copy
+        import functools
+        return functools.reduce(f, self.ctx.runJob(self, lambda it: functools.reduce(f, it, copy.copy(zero))), zero)
+
+    def aggregate(self, zero, seqOp, combOp):
+        """dpark/rdd.py:410-422."""
+        import copy
+        import functools
+        return functools.reduce(combOp, self.ctx.runJob(self, lambda it: functools.reduce(seqOp, it, copy.copy(zero))),
+                                zero)
+
+    def toList(self):
+        return self.collect()
+
+    def foreachPartition(self, f):
+        list(self.ctx.runJob(self, f))
+
+    def enumeratePartition(self):
+        """dpark/rdd.py:326-327: (partition index, element)."""
+        return self.mapPartitionWithIndex(lambda i, it: ((i, x) for x in it))
+
+    def enumerate(self):
+        """dpark/rdd.py:329-345: (global position, element), positions counted partition after partition."""
+        sizes = list(self.ctx.runJob(self, lambda it: sum(1 for _ in it))) if len(self) > 1 else [0]
+        starts = [0]
+        for c in sizes[:-1]:
+            starts.append(starts[-1] + c)
+        return self.mapPartitionWithIndex(lambda i, it: ((starts[i] + j, x) for j, x in _enumerate(it)))
 
     def partitionByKey(self, numSplits=None, taskMemory=None, rddconf=None):
         return self.groupByKey(numSplits, taskMemory, rddconf=rddconf).flatMapValue(lambda x: x)
