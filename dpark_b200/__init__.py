@@ -11,7 +11,7 @@ See DESIGN.md and INTEGRATION.md.
 from .errors import DparkUserFatalError  # noqa: F401
 from .context import DparkContext, parser as optParser  # noqa: F401
 from .dependency import (Aggregator, AddAggregator, GroupByAggregator, HashPartitioner,  # noqa: F401
-                         MergeAggregator)
+                         MergeAggregator, RangePartitioner)
 from . import conf  # noqa: F401
 
 __all__ = ["DparkContext", "optParser", "DparkUserFatalError"]

@@ -86,6 +86,33 @@ class HashPartitioner(Partitioner):
         return hash((self.partitions, None if self.thresholds is None else tuple(self.thresholds)))
 
 
+class RangePartitioner(Partitioner):
+    """dpark/dependency.py:242-258: partition = number of bounds <= key (mirrored when reverse).  Evaluated on the
+    host: `RDD.sort` routes every element to its range first and shuffles on the range index."""
+
+    def __init__(self, keys, reverse=False):
+        self.keys = sorted(keys)
+        self.reverse = reverse
+
+    @property
+    def numPartitions(self):
+        return len(self.keys) + 1
+
+    def getPartition(self, key):
+        import bisect
+        idx = bisect.bisect(self.keys, key)
+        return len(self.keys) - idx if self.reverse else idx
+
+    def __eq__(self, other):
+        return isinstance(other, RangePartitioner) and other.keys == self.keys and other.reverse == self.reverse
+
+    def __ne__(self, other):
+        return not self.__eq__(other)
+
+    def __hash__(self):
+        return hash((tuple(self.keys), self.reverse))
+
+
 class ShuffleDependency(object):
     """dpark/dependency.py:67-75."""
 

@@ -18,7 +18,8 @@ import shutil
 import numpy as np
 
 from . import columnar, conf, quantiles, trace
-from .dependency import Aggregator, GroupByAggregator, HashPartitioner, Partitioner, ShuffleDependency
+from .dependency import (Aggregator, GroupByAggregator, HashPartitioner, Partitioner, RangePartitioner,
+                         ShuffleDependency)
 from .errors import DparkUserFatalError  # noqa: F401
 
 _enumerate = enumerate      # RDD.enumerate shadows the builtin inside the class body
@@ -303,6 +304,25 @@ class RDD(object):
             return sorted(values, key=order_func, reverse=reverse)[:top_n]
 
         return self.groupByKey(num_splits, task_memory, fixSkew=fixSkew).mapValue(best)
+
+    def sort(self, key=lambda x: x, reverse=False, numSplits=None, taskMemory=None, rddconf=None):
+        """dpark/rdd.py:273-287: a globally sorted RDD.  Range bounds come from the first elements of every
+        partition exactly as in the reference (every 10th of the sorted sample, offset 5); each element is routed to
+        its range on the host (RangePartitioner) and the shuffle runs on the GPU keyed by the RANGE INDEX --
+        portable_hash(i) % P == i for 0 <= i < P, so HashPartitioner(P) reproduces the reference's layout -- then
+        every partition is sorted."""
+        if not len(self):
+            return self
+        if len(self) == 1:
+            return self.mapPartitions(lambda it: sorted(it, key=key, reverse=reverse))
+        if numSplits is None:
+            numSplits = min(self.ctx.defaultMinSplits, len(self))
+        n = max(numSplits * 10 // len(self), 1)
+        samples = self.mapPartitions(lambda it: itertools.islice(it, n)).map(key).collect()
+        ranges = RangePartitioner(sorted(samples, reverse=reverse)[5::10][:numSplits - 1], reverse=reverse)
+        routed = self.map(lambda x: (ranges.getPartition(key(x)), x)) \
+                     .groupByKey(ranges.numPartitions, taskMemory, rddconf=rddconf)
+        return routed.flatMap(lambda kv: kv[1]).mapPartitions(lambda it: sorted(it, key=key, reverse=reverse))
 
     def groupBy(self, f, numSplits=None, rddconf=None):
         """dpark/rdd.py:298-301."""
