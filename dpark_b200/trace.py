@@ -153,6 +153,26 @@ def _is_identity(f):
         return False
 
 
+def _builds_lists(create, merge_value, merge_combiners):
+    """True for the list-collecting aggregator written by hand -- createCombiner(v) == [v], mergeValue appends,
+    mergeCombiners concatenates (e.g. dpark.bagel.DefaultListCombiner, or the usual
+    `combineByKey(lambda v: [v], lambda c, v: c + [v], lambda a, b: a + b)`): that is a groupByKey, whose GPU
+    path yields every key's values as a list in (map split, position) order -- the list these functions build
+    when they meet the rows in that order."""
+    a, b, c, d = object(), object(), object(), object()
+    try:
+        one = create(a)
+        if type(one) is not list or len(one) != 1 or one[0] is not a:
+            return False
+        two = merge_value([a], b)
+        if type(two) is not list or len(two) != 2 or two[0] is not a or two[1] is not b:
+            return False
+        four = merge_combiners([a, b], [c, d])
+        return type(four) is list and len(four) == 4 and all(x is y for x, y in zip(four, (a, b, c, d)))
+    except Exception:
+        return False
+
+
 def recognize_aggregator(agg):
     """-> ("reduce", op) | ("group", None) for an Aggregator-like object
     (dpark/dependency.py:107-161), else NotImplementedError."""
@@ -166,6 +186,8 @@ def recognize_aggregator(agg):
     mc = getattr(agg, "mergeCombiners", None)
     if create is None or mv is None or mc is None:
         raise NotImplementedError("aggregator %r lacks createCombiner/mergeValue/mergeCombiners" % (agg,))
+    if _builds_lists(create, mv, mc):
+        return "group", None
     if not _is_identity(create):
         raise NotImplementedError(
             "createCombiner of %r is not the identity; only reduce-style aggregators (identity, f, f) and the "

@@ -58,11 +58,50 @@ def test_bagel_surface_and_termination(standin_engine):
     out = bagel.Bagel.run(dc, verts, dc.parallelize([], 2), forever, maxSuperstep=3)
     assert set(v.value for _, v in out.collect()) == {2}
     # combiners the GPU shuffle cannot express are refused when the job is declared
+    class SetCombiner(bagel.Combiner):
+        def createCombiner(self, msg):
+            return {msg}
+
+        def mergeValue(self, combiner, msg):
+            return combiner | {msg}
+
+        def mergeCombiners(self, a, b):
+            return a | b
+
     with pytest.raises(NotImplementedError):
-        bagel.Bagel.run(dc, verts, dc.parallelize([(0, 1)], 2), forever, combiner=bagel.DefaultListCombiner(),
-                        maxSuperstep=1)
+        bagel.Bagel.run(dc, verts, dc.parallelize([(0, 1)], 2), forever, combiner=SetCombiner(), maxSuperstep=1)
     acc = Accumulator([], listAcc)
     acc.add([1])
     acc.add([2])
     assert acc.value == [1, 2] and acc.reset() == [1, 2] and acc.value == []
     assert dc.accumulator(5).value == 5
+
+
+def test_list_collecting_combiners_run_as_group_by(standin_engine):
+    """An aggregator that builds lists by hand is recognised as a group-by (trace._builds_lists): Bagel's
+    DefaultListCombiner and the usual three-lambda combineByKey give every key its values in (split, position)
+    order; an aggregator that builds something else is still refused."""
+    from dpark_b200 import bagel, trace
+    from dpark_b200.dependency import Aggregator
+    assert trace.recognize_aggregator(bagel.DefaultListCombiner()) == ("group", None)
+    lists = Aggregator(lambda v: [v], lambda c, v: c + [v], lambda a, b: a + b)
+    assert trace.recognize_aggregator(lists) == ("group", None)
+    dc = _ctx()
+    rows = [(i % 4, i) for i in range(20)]
+    got = dict(dc.parallelize(rows, 3).combineByKey(lists, 2).collect())
+    assert got == {k: [i for i in range(20) if i % 4 == k] for k in range(4)}
+    for bad in (Aggregator(lambda v: [v, v], lambda c, v: c + [v], lambda a, b: a + b),      # not [v]
+                Aggregator(lambda v: [v], lambda c, v: [v] + c, lambda a, b: a + b),          # prepends
+                Aggregator(lambda v: {v}, lambda c, v: c | {v}, lambda a, b: a | b)):         # sets
+        with pytest.raises(NotImplementedError):
+            trace.recognize_aggregator(bad)
+
+    def compute(vert, inbox, agg, step):          # inbox = [list of messages] with the list combiner
+        seen = sorted(inbox[0]) if inbox else []
+        out = [(e.target_id, vert.id) for e in vert.outEdges] if step == 0 else []
+        return bagel.Vertex(vert.id, seen, vert.outEdges, step == 0), out
+
+    verts = dc.parallelize([(i, bagel.Vertex(i, None, [bagel.Edge((i + 1) % 3), bagel.Edge((i + 2) % 3)], True))
+                            for i in range(3)], 2)
+    out = bagel.Bagel.run(dc, verts, dc.parallelize([], 2), compute, combiner=bagel.DefaultListCombiner())
+    assert dict((k, v.value) for k, v in out.collect()) == {0: [1, 2], 1: [0, 2], 2: [0, 1]}
