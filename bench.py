@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--count-mode", type=int, default=1, help="A/B switch of the histogram pass (dpk_set_option)")
     ap.add_argument("--agg-wide", type=int, default=-1, help="A/B: 128-bit slot CAS in the reduce-side merge (0|1)")
     ap.add_argument("--scatter-items", type=int, default=0, help="A/B: rows per thread and tile of the multisplit (8|16)")
+    ap.add_argument("--scatter-bulk", type=int, default=-1, help="A/B: TMA bulk-store multisplit kernel (0|1)")
+    ap.add_argument("--agg-impl", type=int, default=-1, help="A/B: reduce-side merge kernel (0 = round 1, 1 = row-index tags)")
     ap.add_argument("--exchange", default="push", choices=["push", "fused", "peer", "nccl"],
                     help="N>1: push = local scatter, then one kernel pushing each peer's block over NVLink; "
                          "fused (alias peer) = the scatter kernel stores into peer memory; nccl = alltoallv")
@@ -274,6 +276,10 @@ def run_ours(args):
         nv.set_option("scatter_items", args.scatter_items)
     if args.agg_wide >= 0:
         nv.set_option("agg_wide", args.agg_wide)
+    if args.scatter_bulk >= 0:
+        nv.set_option("scatter_bulk", args.scatter_bulk)
+    if args.agg_impl >= 0:
+        nv.set_option("agg_impl", args.agg_impl)
 
     ex_events = []
     # exchange: "peer" = the scatter kernel stores rows straight into the owning GPU's receive buffer

@@ -1,0 +1,322 @@
+// dpk_aggregate2.cuh -- reduce-side implementation 2, final stage, round-2 form (included by
+// dpk_combine.cu after dpk_aggregate.cuh; the round-1 kernel k_smem_aggregate stays selectable with
+// dpk_set_option("agg_impl", 0) as the A/B baseline and parity cross-check).
+//
+// One CTA merges one fine bucket (~1.5 k rows after the second-level split) at a time.  What changed,
+// and the B200 measurements behind it (scripts/microbench/smem_ops.cu, profiles/r02_microbench.md):
+//
+//   * The rows of the bucket are STAGED in shared memory (key bits + accumulator, 8 B each, row-linear),
+//     and the hash table holds only a 32-bit TAG per slot: staged row index + 1 of the row that claimed
+//     the slot (0 = free).  A claim is one atom.shared.cas.b32 (5.5 cycles per warp instruction against
+//     24 for the round-1 128-bit {key, accumulator} claim), no key value is reserved as "empty" marker
+//     (no side slot), and the claiming row's staged value IS the key's accumulator: rows that claim
+//     (97.7 % of C2's rows) touch no accumulator at all; later rows of a key compare with the claimer's
+//     staged key and add into its staged accumulator with native shared atomics.
+//   * Output positions come from the claim ballots (row-index order: coalesced stores), summed per warp
+//     and item into 64 counters that warp 0 scans while it does the decoupled look-back; no claim list,
+//     no atomic on a CTA-wide counter.  The distinct rows are written from registers (key) and the
+//     staged accumulator (conflict-free linear LDS).
+//   * The tag table (16 KB) is cleared with 128-bit stores instead of one random reset per claimed row.
+//   * 48 KB of shared memory per CTA instead of 72: four CTAs per SM.
+//
+// Buckets that do not fit one staging window (more than AG2_CAP rows: hot keys) take the general path:
+// windows of rows are staged behind the RESIDENT distinct rows found so far (claimed rows are compacted
+// to the front and re-tagged after every window), so a bucket of any size with up to ~AG2_CAP distinct
+// keys is one pass; more distinct keys than that split the bucket into hash-disjoint passes (m, r).
+// Splitting stops at AG2_MAX_M; a bucket that still overflows marks its partition as failed
+// (out_counts[p] = -1, surfaced as DPK error by the caller) instead of dropping rows silently.
+#pragma once
+
+constexpr int AG2_THREADS = 256;
+constexpr int AG2_WARPS = AG2_THREADS / 32;
+constexpr int AG2_TAGS = 4096;
+constexpr int AG2_CAP = 2048;                       // staged rows per window
+constexpr int AG2_ITEMS = AG2_CAP / AG2_THREADS;    // 8 rows per thread and window
+constexpr int AG2_GEN_ITEMS = 4;                    // general path: rows per thread and window (register pressure)
+constexpr int AG2_MINW = 256;                       // a window smaller than this is not worth a round: split the pass
+constexpr int AG2_MAX_M = 1 << 16;                  // hash-disjoint passes use hash bits 12..27
+constexpr int AG2_STACK = 40;
+
+struct Ag2Shared {
+    int fb, sp, overflow, nres;
+    unsigned long long excl;
+    int wcnt[AG2_ITEMS * AG2_WARPS];   // claims per (item, warp), then their exclusive prefix
+    int total;
+    int stack_m[AG2_STACK], stack_r[AG2_STACK];
+};
+
+__device__ __forceinline__ uint32_t sm_ld_u32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t sm_cas_u32(uint32_t a, uint32_t cmp, uint32_t val) {
+    uint32_t old;
+    asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "r"(a), "r"(cmp), "r"(val) : "memory");
+    return old;
+}
+__device__ __forceinline__ long long sm_ld_s64(uint32_t a) {
+    long long v;
+    asm volatile("ld.volatile.shared.b64 %0, [%1];" : "=l"(v) : "r"(a) : "memory");
+    return v;
+}
+
+// Insert the staged rows [lo, hi) of the window (staged index = lo + j * THREADS + tid) into the tag table.
+// Returns the bit mask of the items this thread claimed.  Per item the claim ballot gives the number of claims
+// of the warp (lane j keeps item j's count in *lane_cnt) and this lane's rank among them (8 bits per item in
+// offs[2]); SLOTS: remember the slot of every claimed item (12 bits each in slots[3]) for re-tagging.
+// (m, r): hash-disjoint pass filter.  Whole warps run the loop together (ballots).
+template <typename AccT, bool SLOTS, int NI>
+__device__ __forceinline__ unsigned ag2_insert(int lo, int hi, int m, int r, int op, uint32_t tag_base, uint32_t key_base,
+                                               uint32_t acc_base, long long *s_acc, uint32_t (&offs)[2], int *lane_cnt,
+                                               uint32_t (&slots)[3]) {
+    unsigned mine = 0;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    offs[0] = offs[1] = 0;
+    if constexpr (SLOTS) slots[0] = slots[1] = slots[2] = 0;
+    int lc = 0;
+#pragma unroll
+    for (int j = 0; j < NI; j++) {
+        const int idx = lo + j * AG2_THREADS + (int)threadIdx.x;
+        bool claimed = false;
+        if (idx < hi) {
+            const long long k = sm_ld_s64(key_base + (uint32_t)idx * 8u);
+            const uint32_t hs = slot_hash32((uint64_t)k);
+            if (m == 1 || (int)((hs >> 12) & (uint32_t)(m - 1)) == r) {
+                uint32_t h = hs & (AG2_TAGS - 1);
+                for (;;) {
+                    uint32_t t = sm_ld_u32(tag_base + h * 4u);
+                    if (t == 0u) {
+                        t = sm_cas_u32(tag_base + h * 4u, 0u, (uint32_t)idx + 1u);
+                        if (t == 0u) { claimed = true; break; }
+                    }
+                    if (sm_ld_s64(key_base + (t - 1u) * 8u) == k) {   // a row of the same key owns the slot: add into its accumulator
+                        const long long mv = sm_ld_s64(acc_base + (uint32_t)idx * 8u);
+                        if constexpr (std::is_same<AccT, double>::value)
+                            sm_apply<double>(op, acc_base + (t - 1u) * 8u, s_acc + (t - 1u), __longlong_as_double(mv));
+                        else
+                            sm_apply<int64_t>(op, acc_base + (t - 1u) * 8u, s_acc + (t - 1u), (int64_t)mv);
+                        break;
+                    }
+                    h = (h + 1u) & (AG2_TAGS - 1);
+                }
+                if constexpr (SLOTS) {
+                    if (claimed) {   // 12 bits per item: items 0..7 at bit 12*j of the 96-bit word slots[0..2]
+                        const int bit = 12 * j;
+                        slots[bit >> 5] |= h << (bit & 31);
+                        if ((bit & 31) > 20) slots[(bit >> 5) + 1] |= h >> (32 - (bit & 31));
+                    }
+                }
+            }
+        }
+        const unsigned cmj = __ballot_sync(0xffffffffu, claimed);
+        if (lane == j) lc = __popc(cmj);
+        offs[j >> 2] |= (uint32_t)__popc(cmj & lt) << (8 * (j & 3));
+        if (claimed) mine |= 1u << j;
+    }
+    *lane_cnt = lc;
+    return mine;
+}
+__device__ __forceinline__ int ag2_off(const uint32_t (&offs)[2], int j) { return (int)((offs[j >> 2] >> (8 * (j & 3))) & 0xffu); }
+__device__ __forceinline__ uint32_t ag2_slot(const uint32_t (&slots)[3], int j) {
+    const int bit = 12 * j;
+    uint32_t v = slots[bit >> 5] >> (bit & 31);
+    if ((bit & 31) > 20) v |= slots[(bit >> 5) + 1] << (32 - (bit & 31));
+    return v & 0xfffu;
+}
+
+template <typename KeyT, typename ValT, typename AccT>
+__global__ void __launch_bounds__(AG2_THREADS, 3)
+k_smem_aggregate2(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, int op,
+                  const int64_t *__restrict__ fine_off, int32_t nfine, int32_t fine_per_part,
+                  const int64_t *__restrict__ part_offsets, KeyT *__restrict__ out_keys,
+                  int64_t *__restrict__ out_vals, long long *__restrict__ out_counts,
+                  unsigned long long *__restrict__ fb_state, int *__restrict__ work_counter,
+                  int *__restrict__ part_err) {
+    extern __shared__ __align__(16) long long s_dyn2[];  // [TAGS] u32 tags | [CAP] key bits | [CAP] accumulators
+    uint32_t *s_tag = reinterpret_cast<uint32_t *>(s_dyn2);
+    long long *s_key = s_dyn2 + AG2_TAGS / 2;
+    long long *s_acc = s_key + AG2_CAP;
+    const uint32_t tag_base = (uint32_t)__cvta_generic_to_shared(s_tag);
+    const uint32_t key_base = (uint32_t)__cvta_generic_to_shared(s_key);
+    const uint32_t acc_base = (uint32_t)__cvta_generic_to_shared(s_acc);
+    __shared__ Ag2Shared sh;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    auto clear_tags = [&]() {
+        uint4 *t4 = reinterpret_cast<uint4 *>(s_tag);
+#pragma unroll
+        for (int i = 0; i < AG2_TAGS / 4 / AG2_THREADS; i++) t4[i * AG2_THREADS + threadIdx.x] = make_uint4(0, 0, 0, 0);
+    };
+    // stage the rows [g0, g0 + w) of the input at staged indices [at, at + w)
+    auto stage = [&](int64_t g0, int w, int at, auto ni_tag) {
+        constexpr int NI = decltype(ni_tag)::value;
+        KeyT kr[NI];
+        ValT vr[NI];
+#pragma unroll
+        for (int j = 0; j < NI; j++) {
+            const int i = j * AG2_THREADS + (int)threadIdx.x;
+            if (i < w) { kr[j] = keys[g0 + i]; vr[j] = vals[g0 + i]; }
+        }
+#pragma unroll
+        for (int j = 0; j < NI; j++) {
+            const int i = j * AG2_THREADS + (int)threadIdx.x;
+            if (i < w) {
+                s_key[at + i] = key_bits<KeyT>(kr[j]);
+                if constexpr (std::is_same<AccT, double>::value) s_acc[at + i] = __double_as_longlong((double)vr[j]);
+                else s_acc[at + i] = (long long)vr[j];
+            }
+        }
+    };
+    // warp 0: exclusive prefix of the (item, warp) claim counts in place, total -> sh.total
+    auto scan_claims = [&]() {
+        constexpr int N = AG2_ITEMS * AG2_WARPS;   // 64
+        int a = sh.wcnt[lane], b = sh.wcnt[lane + 32];
+        int ia = a, ib = b;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int ta = __shfl_up_sync(0xffffffffu, ia, d), tb = __shfl_up_sync(0xffffffffu, ib, d);
+            if (lane >= d) { ia += ta; ib += tb; }
+        }
+        const int suma = __shfl_sync(0xffffffffu, ia, 31);
+        sh.wcnt[lane] = ia - a;
+        sh.wcnt[lane + 32] = suma + ib - b;
+        if (lane == 31) sh.total = suma + ib;
+        static_assert(N == 64, "scan_claims handles 64 counters");
+    };
+
+    clear_tags();
+    for (;;) {
+        if (threadIdx.x == 0) sh.fb = atomicAdd(work_counter, 1);  // in-order hand-out (what the chained look-back relies on)
+        __syncthreads();                                            // (A) also: previous write-out and tag clear finished
+        const int fb = sh.fb;
+        if (fb >= nfine) break;
+        const int64_t r0 = fine_off[fb], r1 = fine_off[fb + 1];
+        const int p = fb / fine_per_part;
+        const int first_fb = p * fine_per_part;
+        const bool last_fb = fb == first_fb + fine_per_part - 1;
+        const int64_t pbase = part_offsets[p];
+        uint32_t offs[2], slots[3];
+        int lane_cnt;
+
+        if (r1 - r0 <= AG2_CAP) {
+            // ================= fast path: the whole bucket is one window, one pass
+            const int n = (int)(r1 - r0);
+            stage(r0, n, 0, std::integral_constant<int, AG2_ITEMS>());
+            __syncthreads();                                        // (S) rows staged
+            const unsigned mine = ag2_insert<AccT, false, AG2_ITEMS>(0, n, 1, 0, op, tag_base, key_base, acc_base, s_acc, offs, &lane_cnt, slots);
+            if (lane < AG2_ITEMS) sh.wcnt[lane * AG2_WARPS + warp] = lane_cnt;
+            __syncthreads();                                        // (B) inserts done, claim counts written
+            if (warp == 0) {
+                scan_claims();
+                __syncwarp();
+                const unsigned long long cnt = (unsigned long long)sh.total;
+                if (lane == 0) atomicExch(&fb_state[fb], AG_FLAG_AGG | cnt);
+                const unsigned long long e = ag_look_back(fb_state, first_fb, fb);
+                if (lane == 0) {
+                    sh.excl = e;
+                    atomicExch(&fb_state[fb], AG_FLAG_INC | (e + cnt));
+                    if (last_fb) out_counts[p] = *(volatile int *)&part_err[p] ? -1ll : (long long)(e + cnt);
+                }
+            }
+            __syncthreads();                                        // (D) offsets known
+            const int64_t obase = pbase + (int64_t)sh.excl;
+#pragma unroll
+            for (int j = 0; j < AG2_ITEMS; j++) {
+                if (mine & (1u << j)) {
+                    const int idx = j * AG2_THREADS + (int)threadIdx.x;
+                    const int64_t o = obase + sh.wcnt[j * AG2_WARPS + warp] + ag2_off(offs, j);
+                    out_keys[o] = key_from_bits<KeyT>(s_key[idx]);
+                    out_vals[o] = s_acc[idx];
+                }
+            }
+            clear_tags();
+            continue;  // barrier (A) of the next iteration orders the reads and the clear before the next staging
+        }
+
+        // ================= general path: windows behind resident distinct rows, hash-disjoint passes on overflow
+        unsigned long long written = 0, excl = 0;  // uniform
+        bool have_excl = false, failed = false;
+        if (threadIdx.x == 0) { sh.stack_m[0] = 1; sh.stack_r[0] = 0; sh.sp = 1; }
+        __syncthreads();
+        while (sh.sp > 0) {
+            const int m = sh.stack_m[sh.sp - 1], r = sh.stack_r[sh.sp - 1];
+            __syncthreads();
+            if (threadIdx.x == 0) { sh.sp--; sh.overflow = 0; sh.nres = 0; }
+            __syncthreads();
+            int64_t cursor = r0;
+            int nres = 0;
+            bool ok = true;
+            while (cursor < r1) {
+                const int room = AG2_CAP - nres;
+                if (room < AG2_MINW) { ok = false; break; }          // too many distinct keys for one pass
+                const int w = (int)min((int64_t)min(room, AG2_GEN_ITEMS * AG2_THREADS), r1 - cursor);
+                stage(cursor, w, nres, std::integral_constant<int, AG2_GEN_ITEMS>());
+                __syncthreads();
+                const unsigned mine = ag2_insert<AccT, true, AG2_GEN_ITEMS>(nres, nres + w, m, r, op, tag_base, key_base, acc_base, s_acc, offs, &lane_cnt, slots);
+                if (lane < AG2_ITEMS) sh.wcnt[lane * AG2_WARPS + warp] = lane_cnt;
+                __syncthreads();
+                // compact the claimed rows behind the residents and re-tag their slots
+                long long kv[AG2_GEN_ITEMS], av[AG2_GEN_ITEMS];
+#pragma unroll
+                for (int j = 0; j < AG2_GEN_ITEMS; j++)
+                    if (mine & (1u << j)) {
+                        kv[j] = s_key[nres + j * AG2_THREADS + (int)threadIdx.x];
+                        av[j] = s_acc[nres + j * AG2_THREADS + (int)threadIdx.x];
+                    }
+                if (warp == 0) scan_claims();
+                __syncthreads();
+#pragma unroll
+                for (int j = 0; j < AG2_GEN_ITEMS; j++) {
+                    if (mine & (1u << j)) {
+                        const int ni = nres + sh.wcnt[j * AG2_WARPS + warp] + ag2_off(offs, j);
+                        s_key[ni] = kv[j];
+                        s_acc[ni] = av[j];
+                        s_tag[ag2_slot(slots, j)] = (uint32_t)ni + 1u;
+                    }
+                }
+                nres += sh.total;
+                cursor += w;
+                __syncthreads();
+            }
+            if (!ok) {  // uniform: split this pass in two, or give up (error flag) when the hash bits are used up
+                if (m * 2 <= AG2_MAX_M && sh.sp + 2 <= AG2_STACK) {
+                    if (threadIdx.x == 0) {
+                        sh.stack_m[sh.sp] = m * 2; sh.stack_r[sh.sp] = r; sh.sp++;
+                        sh.stack_m[sh.sp] = m * 2; sh.stack_r[sh.sp] = r + m; sh.sp++;
+                    }
+                } else {
+                    failed = true;
+                }
+                clear_tags();
+                __syncthreads();
+                continue;
+            }
+            if (!have_excl) {  // multi-pass buckets publish only their inclusive value, at the end
+                if (warp == 0) {
+                    const unsigned long long e = ag_look_back(fb_state, first_fb, fb);
+                    if (lane == 0) sh.excl = e;
+                }
+                __syncthreads();
+                excl = sh.excl;
+                have_excl = true;
+            }
+            const int64_t obase = pbase + (int64_t)(excl + written);
+            for (int i = threadIdx.x; i < nres; i += AG2_THREADS) {
+                out_keys[obase + i] = key_from_bits<KeyT>(s_key[i]);
+                out_vals[obase + i] = s_acc[i];
+            }
+            written += (unsigned long long)nres;
+            clear_tags();
+            __syncthreads();
+        }
+        if (warp == 0) {
+            unsigned long long e = have_excl ? excl : ag_look_back(fb_state, first_fb, fb);
+            if (lane == 0) {
+                if (failed) { atomicExch(&part_err[p], 1); __threadfence(); }
+                atomicExch(&fb_state[fb], AG_FLAG_INC | (e + written));
+                if (last_fb) out_counts[p] = (failed || *(volatile int *)&part_err[p]) ? -1ll : (long long)(e + written);
+            }
+        }
+    }
+}

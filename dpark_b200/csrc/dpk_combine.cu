@@ -413,6 +413,7 @@ k_bucket_reduce(const KeyT *__restrict__ keys, const int64_t *__restrict__ aux, 
 
 // ===== implementation 2: second-level split + shared-memory tables (dpk_aggregate.cuh) =====
 #include "dpk_aggregate.cuh"
+#include "dpk_aggregate2.cuh"
 
 // the key whose bits equal the free-slot marker lives in the side slot: append it
 template <typename KeyT>
@@ -444,6 +445,7 @@ int g_reduce_impl = 2;  // dpk_set_option("reduce_impl", 0|1|2)
 
 constexpr int AG_MAX_SB2 = 10;       // at most 1024 fine buckets per first-level bucket
 int g_agg_wide = 1;
+int g_agg_impl = 1;                  // dpk_set_option("agg_impl"): 1 = k_smem_aggregate2 (row-index tags), 0 = round-1 kernel
 int g_agg_target_rows = 2048;        // rows per fine bucket the split aims for (table load <= 0.5)
 
 static inline int choose_sb2(int64_t n, int32_t F) {
@@ -456,6 +458,7 @@ struct Ctx {
     int key_kind, val_bytes;
     int64_t *fine_off;
     unsigned long long *fb_state;
+    int *part_err;
     void *seg_ws;
     int64_t seg_ws_bytes;
     const void *keys, *vals;
@@ -484,7 +487,7 @@ static int dispatch_op(const Ctx &c) {
         const int sb2 = choose_sb2(c.n, c.F);
         const int32_t S2 = 1 << sb2;
         PartFn fine = c.f;
-        fine.mode = 5; fine.P = S2; fine.shift = 64 - c.f.sub_bits - sb2; fine.sub_bits = 0; fine.row_hash = c.aux;
+        fine.mode = 5; fine.P = S2; fine.shift = 32 - c.f.sub_bits - sb2; fine.sub_bits = 0; fine.row_hash = c.aux;
         KeyT *rekeys = (KeyT *)c.table;
         ValT *revals = (ValT *)((char *)c.table + (size_t)c.n * 8);
         int rc = seg_multisplit(c.keys, c.key_kind, c.vals, (int32_t)sizeof(ValT), c.n, fine, c.F, c.nsrc, c.seg_start,
@@ -498,6 +501,16 @@ static int dispatch_op(const Ctx &c) {
         const int agg_smem = AG_CAP * 16 + AG_CAP * 2;  // keys | accumulators | claim list
         DPK_CUDA_TRY(cudaFuncSetAttribute(agg, cudaFuncAttributeMaxDynamicSharedMemorySize, agg_smem));
         DPK_CUDA_TRY(cudaMemsetAsync(c.fb_state, 0, (size_t)nfine * 8, c.st));
+        if (g_agg_impl == 1) {
+            auto agg2 = k_smem_aggregate2<KeyT, ValT, AccT>;
+            const int smem2 = AG2_TAGS * 4 + AG2_CAP * 16;
+            DPK_CUDA_TRY(cudaFuncSetAttribute(agg2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+            DPK_CUDA_TRY(cudaMemsetAsync(c.part_err, 0, (size_t)c.nparts * 4, c.st));
+            DPK_LAUNCH("smem_aggregate", c.st, agg2<<<grid, AG2_THREADS, smem2, c.st>>>(
+                rekeys, revals, c.op, c.fine_off, nfine, (1 << c.f.sub_bits) * S2, c.part_off,
+                (KeyT *)c.out_keys, c.out_vals, (long long *)c.out_counts, c.fb_state, c.bucket_counter, c.part_err));
+            return DPK_OK;
+        }
         DPK_LAUNCH("smem_aggregate", c.st, agg<<<grid, AG_THREADS, agg_smem, c.st>>>(
             rekeys, revals, c.op, ident, c.fine_off, nfine, (1 << c.f.sub_bits) * S2, c.part_off,
             (KeyT *)c.out_keys, c.out_vals, c.out_counts, c.fb_state, c.bucket_counter));
@@ -558,7 +571,8 @@ static int run_combine(Ctx &c, int val_kind, int64_t *out_offsets, void *ws) {
     c.fine_off = seg_start + (int64_t)c.nsrc * c.F + 2;
     const int sb2 = choose_sb2(c.n, c.F);
     c.fb_state = (unsigned long long *)(c.fine_off + ((int64_t)c.F << sb2) + 2);
-    c.seg_ws = (void *)(((uintptr_t)(c.fb_state + ((int64_t)c.F << sb2) + 2) + 255) & ~(uintptr_t)255);
+    c.part_err = (int *)(c.fb_state + ((int64_t)c.F << sb2) + 2);
+    c.seg_ws = (void *)(((uintptr_t)(c.part_err + c.F + 2) + 255) & ~(uintptr_t)255);
     c.seg_ws_bytes = seg_multisplit_ws_bytes(c.n, c.F, 1 << sb2, c.nsrc);
     // side slot: free marker + identity are written by the init below; flags cleared here
     DPK_CUDA_TRY(cudaMemsetAsync(c.side_used, 0, 16, c.st));
@@ -585,6 +599,11 @@ int dpk_set_option(const char *name, int64_t value) {
         g_reduce_impl = (int)value;
         return DPK_OK;
     }
+    if (strcmp(name, "agg_impl") == 0) {
+        if (value != 0 && value != 1) return fail(DPK_ERR_INVALID, "agg_impl must be 0 or 1");
+        g_agg_impl = (int)value;
+        return DPK_OK;
+    }
     if (strcmp(name, "agg_wide") == 0) {
         if (value != 0 && value != 1) return fail(DPK_ERR_INVALID, "agg_wide must be 0 or 1");
         g_agg_wide = (int)value;
@@ -593,6 +612,11 @@ int dpk_set_option(const char *name, int64_t value) {
     if (strcmp(name, "scatter_items") == 0) {
         if (value != 8 && value != 16) return fail(DPK_ERR_INVALID, "scatter_items must be 8 or 16");
         g_scatter_items = (int)value;
+        return DPK_OK;
+    }
+    if (strcmp(name, "scatter_bulk") == 0) {
+        if (value != 0 && value != 1) return fail(DPK_ERR_INVALID, "scatter_bulk must be 0 or 1");
+        g_scatter_bulk = (int)value;
         return DPK_OK;
     }
     if (strcmp(name, "count_mode") == 0) {
@@ -614,7 +638,7 @@ int64_t dpk_combine_workspace_bytes(int64_t n, int32_t nbuckets, int32_t nsrc) {
     if (nsrc < 1) nsrc = 1;
     return (max_slots_for(n, nbuckets) + 2) * (int64_t)sizeof(Slot) +
            ((int64_t)nbuckets + 4 + (int64_t)nbuckets * nsrc) * 8 + 64 +
-           (((int64_t)nbuckets << choose_sb2(n, nbuckets)) + 4) * 16 + 512 +
+           (((int64_t)nbuckets << choose_sb2(n, nbuckets)) + 4) * 16 + 512 + ((int64_t)nbuckets + 2) * 4 +
            seg_multisplit_ws_bytes(n, nbuckets, 1 << choose_sb2(n, nbuckets), nsrc);
 }
 

@@ -31,6 +31,7 @@ int fail(int code, const char *fmt, ...);
 int sm_count();
 extern int g_scatter_items;  // dpk_partition.cu, rows per thread and tile of the scatter (16 or 8)
 extern int g_count_mode;  // dpk_partition.cu, A/B switch of the histogram pass
+extern int g_scatter_bulk;  // dpk_partition.cu, 1 = unordered multisplits use the TMA bulk-store kernel
 
 // every kernel launch goes through DPK_LAUNCH: counts it and, when profiling
 // is on, brackets it with CUDA events on the launching stream.
@@ -55,6 +56,7 @@ constexpr uint64_t kPyMod = (1ull << 61) - 1;  // CPython _PyHASH_MODULUS
 // hash(int) for an int64 value -- dpark/portable_hash.pyx:61-62 (CPython
 // long_hash: sign * (|x| mod 2^61-1); -1 -> -2).
 DPK_HD int64_t hash_i64(int64_t x) {
+    if ((uint64_t)x < kPyMod) return x;                      // 0 <= x < 2^61-1 hashes to itself (the common case)
     uint64_t a = x < 0 ? 0ull - (uint64_t)x : (uint64_t)x;  // |INT64_MIN| = 2^63 ok
     uint64_t r = (a & kPyMod) + (a >> 61);                   // hi <= 4
     if (r >= kPyMod) r -= kPyMod;
@@ -156,17 +158,22 @@ struct PartFn {
         // mode 4 (radix pass of the group-by sort): digit `shift` of the raw key bits, P = 2^bits
         if (mode == 4) return (int32_t)(((uint64_t)h >> shift) & (uint64_t)(P - 1));
         // mode 5 (second-level split on the reduce side): the P = 2^k bits of the same mixed
-        // hash that follow the first-level sub-bucket bits (shift = 64 - sub_bits_1 - k)
-        if (mode == 5) return P == 1 ? 0 : (int32_t)((mixed(h) >> shift) & (uint64_t)(P - 1));
+        // hash that follow the first-level sub-bucket bits (shift = 32 - sub_bits_1 - k)
+        if (mode == 5) return P == 1 ? 0 : (int32_t)((mixed(h) >> shift) & (uint32_t)(P - 1));
         int32_t p = (*this)(h);
         if (sub_bits == 0) return p;
-        return (p << sub_bits) | (int32_t)(mixed(h) >> (64 - sub_bits));
+        return (p << sub_bits) | (int32_t)(mixed(h) >> (32 - sub_bits));
     }
-    static DPK_HD uint64_t mixed(int64_t h) {
-        uint64_t m = (uint64_t)h * 0x9E3779B97F4A7C15ull;
-        m ^= m >> 29;
-        m *= 0xBF58476D1CE4E5B9ull;
-        return m;
+    // 32 well-mixed bits of the hash for the LAYOUT-ONLY sub-bucket levels (first level: the top sub_bits
+    // bits, second level: the bits below them; at most 12 + 10).  Both halves of the hash enter through
+    // odd multipliers, then the lowbias32 finaliser; five 32-bit multiplies/xorshifts instead of the two
+    // 64-bit multiplies of a splitmix step (the multisplit kernels are issue-bound).
+    static DPK_HD uint32_t mixed(int64_t h) {
+        uint32_t x = (uint32_t)(uint64_t)h * 0x9E3779B1u + (uint32_t)((uint64_t)h >> 32) * 0x85EBCA77u;
+        x ^= x >> 16; x *= 0x21F0AAADu;
+        x ^= x >> 15; x *= 0x735A2D97u;
+        x ^= x >> 15;
+        return x;
     }
 
     DPK_HD int32_t operator()(int64_t h) const {
@@ -207,11 +214,20 @@ int seg_multisplit(const void *keys, int key_kind, const void *vals, int32_t val
                    const int64_t *seg_rows, void *out_keys, void *out_vals, int64_t *fine_off, void *ws,
                    int64_t ws_bytes, cudaStream_t st);
 
-// murmur3 fmix64 -- slot hash for the reduce-side tables (not part of the
+// murmur3 fmix64 -- slot hash for the reduce-side tables in HBM (implementations 0/1; not part of the
 // reference semantics; only spreads keys over table slots)
 DPK_HD uint64_t mix64(uint64_t x) {
     x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull;
     return x ^ (x >> 33);
+}
+// 32-bit slot hash of 64 key bits for the shared-memory merge (implementation 2): independent of
+// PartFn::mixed (all rows of a fine bucket agree in those bits), murmur3 fmix32 after folding the halves
+DPK_HD uint32_t slot_hash32(uint64_t kb) {
+    uint32_t x = (uint32_t)kb * 0xCC9E2D51u + (uint32_t)(kb >> 32) * 0x1B873593u + 0x7F4A7C15u;
+    x ^= x >> 16; x *= 0x85EBCA6Bu;
+    x ^= x >> 13; x *= 0xC2B2AE35u;
+    x ^= x >> 16;
+    return x;
 }
 
 }  // namespace dpk

@@ -38,6 +38,9 @@ struct NoVal {};
 // histogram; 0 = warp peer mask + leader update (slower: measured 1.01 ms vs 0.47 ms per 1e8 rows)
 int g_count_mode = 1;
 int g_scatter_items = 16;
+// dpk_set_option("scatter_bulk"): 1 (default) = unordered multisplits run k_part_scatter_bulk (CTA-wide
+// shared-memory ranking + TMA bulk stores of the staged bucket runs); 0 = the round-1 kernel (A/B switch)
+int g_scatter_bulk = 1;
 
 // Segmented mode (second-level split on the reduce side): the grid runs over a
 // device-resident chunk table instead of equal row ranges; every chunk lies inside
@@ -155,7 +158,18 @@ k_part_count(const KeyT *__restrict__ keys, int64_t n, int64_t L, PartFn f,
     const int lane = threadIdx.x & 31;
     int32_t *wh = s_cnt + (priv ? (threadIdx.x >> 5) * P : 0);
     constexpr int U = 8;
-    for (int64_t i0 = beg; i0 < end; i0 += (int64_t)PT_THREADS * U) {
+    int64_t i0 = beg;
+    if (count_mode == 1) {
+        // full blocks of 2048 rows: no bounds predicates (the kernel is issue-bound: hash + one atomic per row)
+        for (; i0 + (int64_t)PT_THREADS * U <= end; i0 += (int64_t)PT_THREADS * U) {
+            KeyT k[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) k[u] = keys[i0 + (int64_t)u * PT_THREADS + threadIdx.x];
+#pragma unroll
+            for (int u = 0; u < U; u++) atomicAdd(&wh[f.bucket(key_hash<KeyT, PRE>(k[u], f))], 1);
+        }
+    }
+    for (; i0 < end; i0 += (int64_t)PT_THREADS * U) {
         KeyT k[U];
         bool ok[U];
 #pragma unroll
@@ -410,6 +424,195 @@ k_part_scatter(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, int
     }
 }
 
+
+// ------------------------------------------------- scatter, TMA bulk-store form
+// Unordered multisplit of one tile at a time (reduceByKey paths: the order of rows inside a bucket is not
+// observable).  Differences to k_part_scatter:
+//   * rank = the value ONE native shared-memory atomic on the tile's bucket counter returns (ATOMS.ADD,
+//     measured 3 cycles per warp instruction at random addresses on B200; MATCH.ANY costs 62): no warp
+//     histograms, no scan over warps, one block barrier less per tile;
+//   * the staged tile leaves through the TMA: every bucket run is written with cp.async.bulk
+//     (shared -> global, UBLKCP.G.S) -- measured 4.1-4.5 TB/s chip-wide at 128-byte runs against 2.1 TB/s for
+//     the per-thread LDS + STG.64 copy-out, and it costs the SM one instruction per run instead of two per row.
+//     Bulk copies need 16-byte aligned addresses and sizes on both sides: the staging position of a run is
+//     shifted by up to 16/size-1 elements so that it has the same alignment phase as its destination, and the
+//     unaligned head/tail elements of a run (at most 16/size-1 each) are stored by the issuing thread;
+//   * the next tile's rows are loaded into the (now free) registers right after the placement, so their DRAM
+//     latency overlaps the barrier, the bulk-store issue and the counter reset.
+// Per tile: rank -> barrier -> aligned scan of the 256..1024 tile counts -> barrier -> placement ->
+// fence.proxy.async -> barrier -> bulk stores (asynchronous; their shared-memory reads are awaited with
+// cp.async.bulk.wait_group.read right before the next placement).
+struct BulkSmem {
+    int64_t key_off, val_off, gpos_off, cnt_off, sk_off, sv_off, total;
+    int32_t key_slots, val_slots;
+};
+static BulkSmem bulk_smem(int kb, int vb, int32_t P, int tile) {
+    BulkSmem s;
+    int64_t o = 0;
+    const int padk = 16 / kb - 1, padv = vb ? 16 / vb - 1 : 0;
+    s.key_slots = tile + P * padk;
+    s.val_slots = vb ? tile + P * padv : 0;
+    s.key_off = o; o += align_up((int64_t)s.key_slots * kb, 128);
+    s.val_off = o; o += align_up((int64_t)s.val_slots * vb, 128);
+    s.gpos_off = o; o += align_up((int64_t)P * 8, 16);
+    s.cnt_off = o; o += align_up((int64_t)P * 4 * 2, 16);    // two alternating count arrays
+    s.sk_off = o; o += align_up((int64_t)P * 4, 16);
+    s.sv_off = o; o += align_up((int64_t)P * 4, 16);
+    s.total = o;
+    return s;
+}
+
+__device__ __forceinline__ void bulk_store_s2g(void *gdst, uint32_t ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
+}
+
+// copy-out of one bucket run of one column: [head: plain stores][aligned middle: one bulk store][tail: plain]
+template <typename T>
+__device__ __forceinline__ void flush_run(T *__restrict__ out, int64_t g, const T *s_col, uint32_t s_col_addr, int s0, int cnt) {
+    constexpr int A = 16 / (int)sizeof(T);
+    T *dst = out + g;
+    int head = (int)(((16u - (uint32_t)((uintptr_t)dst & 15u)) & 15u) / (uint32_t)sizeof(T));
+    if (head > cnt) head = cnt;
+    const int mid = ((cnt - head) / A) * A;
+    for (int i = 0; i < head; i++) dst[i] = s_col[s0 + i];
+    if (mid) bulk_store_s2g(dst + head, s_col_addr + (uint32_t)(s0 + head) * (uint32_t)sizeof(T), (uint32_t)mid * (uint32_t)sizeof(T));
+    for (int i = head + mid; i < cnt; i++) dst[i] = s_col[s0 + i];
+}
+
+template <typename KeyT, typename ValT, int PRE>
+__global__ void __launch_bounds__(PT_THREADS, 2)
+k_part_scatter_bulk(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, int64_t n, int64_t L,
+                    PartFn f, const int32_t *__restrict__ tile_off, int32_t T,
+                    const int64_t *__restrict__ bucket_base, KeyT *__restrict__ out_keys,
+                    ValT *__restrict__ out_vals, BulkSmem lay, SegTab seg) {
+    constexpr bool HAS_VAL = !std::is_same<ValT, NoVal>::value;
+    constexpr int ITEMS = 16;
+    constexpr int TILE = PT_THREADS * ITEMS;
+    constexpr int AK = 16 / (int)sizeof(KeyT);
+    constexpr int AV = HAS_VAL ? 16 / (int)sizeof(typename std::conditional<HAS_VAL, ValT, int64_t>::type) : 1;
+    extern __shared__ __align__(128) unsigned char smem_bulk[];
+    unsigned char *smem = smem_bulk;
+    __shared__ int s_warp[PT_WARPS];
+    KeyT *s_key = reinterpret_cast<KeyT *>(smem + lay.key_off);
+    ValT *s_val = reinterpret_cast<ValT *>(smem + lay.val_off);
+    int64_t *s_gpos = reinterpret_cast<int64_t *>(smem + lay.gpos_off);
+    uint32_t *s_cnt = reinterpret_cast<uint32_t *>(smem + lay.cnt_off);      // [2][P]
+    int32_t *s_sk = reinterpret_cast<int32_t *>(smem + lay.sk_off);          // start of bucket p's key run in the staging tile
+    int32_t *s_sv = reinterpret_cast<int32_t *>(smem + lay.sv_off);
+    const uint32_t key_addr = (uint32_t)__cvta_generic_to_shared(s_key);
+    const uint32_t val_addr = (uint32_t)__cvta_generic_to_shared(s_val);
+
+    const int P = f.nbuckets();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (seg.cbeg != nullptr && (int)blockIdx.x >= *seg.ctotal) return;
+    const int64_t beg = seg.cbeg ? seg.cbeg[blockIdx.x] : ((int64_t)blockIdx.x * L / T) * PT_TILE;
+    const int64_t end = seg.cbeg ? seg.cend[blockIdx.x] : min(n, ((int64_t)(blockIdx.x + 1) * L / T) * PT_TILE);
+    if (seg.cbeg) {
+        for (int p = threadIdx.x; p < P; p += PT_THREADS) s_gpos[p] = seg.chunk_off[(int64_t)blockIdx.x * P + p];
+    } else {
+        for (int p = threadIdx.x; p < P; p += PT_THREADS)
+            s_gpos[p] = bucket_base[p] + (int64_t)tile_off[(int64_t)p * T + blockIdx.x];
+    }
+    for (int p = threadIdx.x; p < 2 * P; p += PT_THREADS) s_cnt[p] = 0;
+    const int E = (P + PT_THREADS - 1) / PT_THREADS;  // buckets per thread in the scan
+
+    KeyT k[ITEMS];
+    ValT v[ITEMS];
+    auto load_tile = [&](int64_t tile) {
+        const int64_t wbase = tile + (int64_t)warp * (32 * ITEMS) + lane;
+        if (tile + TILE <= end) {
+#pragma unroll
+            for (int j = 0; j < ITEMS; j++) k[j] = keys[wbase + j * 32];
+            if constexpr (HAS_VAL) {
+#pragma unroll
+                for (int j = 0; j < ITEMS; j++) v[j] = vals[wbase + j * 32];
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < ITEMS; j++) k[j] = (wbase + j * 32) < end ? keys[wbase + j * 32] : KeyT(0);
+            if constexpr (HAS_VAL) {
+#pragma unroll
+                for (int j = 0; j < ITEMS; j++)
+                    if ((wbase + j * 32) < end) v[j] = vals[wbase + j * 32];
+            }
+        }
+    };
+    if (beg < end) load_tile(beg);
+    __syncthreads();  // s_gpos, s_cnt initialised
+
+    int par = 0;
+    for (int64_t tile = beg; tile < end; tile += TILE, par ^= 1) {
+        uint32_t *cnt = s_cnt + par * P;
+        const int64_t wbase = tile + (int64_t)warp * (32 * ITEMS) + lane;
+        const bool full = tile + TILE <= end;
+        // ---- rank: one shared-memory atomic per row on the tile's bucket counter
+        uint32_t pr[ITEMS];  // bucket << 16 | rank inside the tile (both < 2^16: P <= 4096, TILE = 4096)
+#pragma unroll
+        for (int j = 0; j < ITEMS; j++) {
+            const bool ok = full || (wbase + j * 32) < end;
+            pr[j] = 0xffffffffu;
+            if (ok) {
+                const int p = f.bucket(key_hash<KeyT, PRE>(k[j], f));
+                pr[j] = ((uint32_t)p << 16) | atomicAdd(&cnt[p], 1u);
+            }
+        }
+        // the previous tile's bulk stores must have read the staging tile before it is overwritten
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncthreads();  // (A) counts final
+
+        // ---- starts of the bucket runs in the staging tile: exclusive scan of the counts, every run shifted
+        //      so that it has the alignment phase of its destination
+        {
+            const int b = threadIdx.x * E;
+            int sum = 0;
+            for (int i = b; i < min(b + E, P); i++) sum += (int)cnt[i];
+            int tot;
+            int run = block_excl_scan(sum, s_warp, &tot);
+            for (int i = b; i < min(b + E, P); i++) {
+                const int64_t g = s_gpos[i];
+                const uint32_t gk = (uint32_t)(((uintptr_t)(out_keys + g)) / sizeof(KeyT));
+                const int basek = run + i * (AK - 1);
+                s_sk[i] = basek + (int)((gk - (uint32_t)basek) & (uint32_t)(AK - 1));
+                if constexpr (HAS_VAL) {
+                    const uint32_t gv = (uint32_t)(((uintptr_t)(out_vals + g)) / sizeof(ValT));
+                    const int basev = run + i * (AV - 1);
+                    s_sv[i] = basev + (int)((gv - (uint32_t)basev) & (uint32_t)(AV - 1));
+                }
+                run += (int)cnt[i];
+            }
+        }
+        __syncthreads();  // (B)
+
+        // ---- placement
+#pragma unroll
+        for (int j = 0; j < ITEMS; j++) {
+            if (pr[j] != 0xffffffffu) {
+                const int p = (int)(pr[j] >> 16), r = (int)(pr[j] & 0xffffu);
+                s_key[s_sk[p] + r] = k[j];
+                if constexpr (HAS_VAL) s_val[s_sv[p] + r] = v[j];
+            }
+        }
+        // registers are free: fetch the next tile now, its latency hides behind the barrier and the copy-out
+        if (tile + TILE < end) load_tile(tile + TILE);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the TMA
+        __syncthreads();  // (C)
+
+        // ---- copy-out: bucket runs leave through the TMA
+        for (int p = threadIdx.x; p < P; p += PT_THREADS) {
+            const int c = (int)cnt[p];
+            if (c) {
+                const int64_t g = s_gpos[p];
+                flush_run<KeyT>(out_keys, g, s_key, key_addr, s_sk[p], c);
+                if constexpr (HAS_VAL) flush_run<ValT>(out_vals, g, s_val, val_addr, s_sv[p], c);
+                s_gpos[p] = g + c;
+                cnt[p] = 0;  // this array is used again two tiles from now (barriers A..C of the next tile in between)
+            }
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all stores complete before the CTA's shared memory goes away
+}
+
 // ------------------------------------------------------------ host dispatch
 template <typename KeyT, int PRE>
 static int launch_count(const void *keys, int64_t n, const Plan &pl, const PartFn &f,
@@ -454,9 +657,31 @@ static int launch_scatter_items(const void *keys, const void *vals, int64_t n, c
 }
 
 template <typename KeyT, typename ValT, int PRE>
-static int launch_scatter(const void *keys, const void *vals, int64_t n, const Plan &pl, const PartFn &f,
+static int launch_scatter_bulk(const void *keys, const void *vals, int64_t n, const Plan &pl, const PartFn &f,
+                               const int32_t *tile_off, const int64_t *bucket_base, void *out_keys,
+                               void *out_vals, cudaStream_t st) {
+    constexpr int vb = std::is_same<ValT, NoVal>::value ? 0 : (int)sizeof(ValT);
+    BulkSmem lay = bulk_smem((int)sizeof(KeyT), vb, f.nbuckets(), PT_TILE);
+    auto kern = k_part_scatter_bulk<KeyT, ValT, PRE>;
+    DPK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
+    DPK_LAUNCH(pl.seg.cbeg ? "seg_scatter" : "part_scatter", st,
+               kern<<<pl.T, PT_THREADS, (size_t)lay.total, st>>>((const KeyT *)keys, (const ValT *)vals, n, pl.L, f,
+                                                                tile_off, pl.T, bucket_base, (KeyT *)out_keys,
+                                                                (ValT *)out_vals, lay, pl.seg));
+    return DPK_OK;
+}
+
+template <typename KeyT, typename ValT, int PRE>
+static int launch_scatter(const void *keys, const void *vals, int64_t n, const Plan &pl_in, const PartFn &f,
                           const int32_t *tile_off, const int64_t *bucket_base, void *out_keys,
                           void *out_vals, cudaStream_t st) {
+    Plan pl = pl_in;
+    if (pl.seg.unordered == 2) {  // unordered + plain/segmented destination: the TMA bulk-store kernel
+        constexpr int vb = std::is_same<ValT, NoVal>::value ? 0 : (int)sizeof(ValT);
+        if (bulk_smem((int)sizeof(KeyT), vb, f.nbuckets(), PT_TILE).total <= 110 * 1024)
+            return launch_scatter_bulk<KeyT, ValT, PRE>(keys, vals, n, pl, f, tile_off, bucket_base, out_keys, out_vals, st);
+        pl.seg.unordered = (f.nbuckets() % 2 == 0) ? 1 : 0;  // too many buckets for two resident CTAs: the round-1 kernel
+    }
     // dpk_set_option("scatter_items"): 16 or 8 rows per thread and tile (A/B switch)
     if (g_scatter_items == 8)
         return launch_scatter_items<KeyT, ValT, PRE, 8>(keys, vals, n, pl, f, tile_off, bucket_base, out_keys, out_vals, st);
@@ -483,6 +708,9 @@ static int dispatch_scatter(const void *keys, int key_kind, const void *vals, in
     if (key_kind >= DPK_K_UNORDERED) {  // caller does not need input order inside a bucket
         key_kind -= DPK_K_UNORDERED;
         if (f.nbuckets() % 2 == 0) pl.seg.unordered = 1;  // packed 16-bit counter pairs need an even bucket count
+        if (g_scatter_bulk && pl.seg.key_ptrs == nullptr) pl.seg.unordered = 2;
+    } else if (pl.seg.unordered && g_scatter_bulk && pl.seg.key_ptrs == nullptr) {
+        pl.seg.unordered = 2;  // segmented mode (reduce side): never ordered
     }
     // the scatter only moves bits: 8-byte keys share the int64/uint64/double code
     // paths for hashing, so dispatch on the hash kind
@@ -620,7 +848,7 @@ int seg_multisplit(const void *keys, int key_kind, const void *vals, int32_t val
     pl.T = (int32_t)maxc;
     pl.L = 0;
     // the reduce side never needs the order of rows inside a fine bucket
-    pl.seg = SegTab{cbeg, cend, ctotal, chunk_counts, chunk_off, nullptr, nullptr, (S2 % 2 == 0) ? 1 : 0};
+    pl.seg = SegTab{cbeg, cend, ctotal, chunk_counts, chunk_off, nullptr, nullptr, (S2 % 2 == 0) ? 1 : (g_scatter_bulk ? 2 : 0)};
     int rc = DPK_OK;
     if (n > 0) {
         rc = dispatch_count(keys, key_kind, n, pl, fine, nullptr, st);
