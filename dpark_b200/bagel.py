@@ -91,7 +91,10 @@ class Bagel(object):
     @classmethod
     def run(cls, ctx, verts, msgs, compute, combiner=DefaultValueCombiner, aggregator=None,
             maxSuperstep=sys.maxsize, numSplits=None, checkpointDir=None):
+        # checkpointDir is accepted for signature compatibility and ignored: nothing is written to disk, every
+        # superstep's (vertex, outbox) rows are cached in memory for exactly one superstep (see comp()).
         superstep = 0
+        previous = None
         while superstep < maxSuperstep:
             aggregated = cls.agg(verts, aggregator) if aggregator else None
             inbox = msgs.combineByKey(combiner, numSplits)
@@ -100,7 +103,10 @@ class Bagel(object):
             def step(vert, inbox_values, _agg=aggregated, _n=superstep):
                 return compute(vert, inbox_values, _agg, _n)
 
-            verts, msgs, sent, active = cls.comp(ctx, grouped, step, checkpointDir)
+            verts, msgs, sent, active, moved = cls.comp(ctx, grouped, step, checkpointDir)
+            if previous is not None:
+                previous.uncache()            # the superstep before last is no longer reachable through a cache miss
+            previous = moved
             superstep += 1
             if sent == 0 and active == 0:
                 break
@@ -127,11 +133,14 @@ class Bagel(object):
                 active.add(1)
             return [(vert, outbox)]
 
-        moved = grouped.flatMapValue(advance)
+        # cached: `moved` is read three times (the count below, the next superstep's message shuffle and its
+        # groupWith), and through the narrow dependency of a co-partitioned cogroup every later superstep would
+        # otherwise re-run compute() for all earlier ones (quadratic, and user side effects would re-fire)
+        moved = grouped.flatMapValue(advance).cache()
         verts = moved.mapValue(lambda vert_outbox: vert_outbox[0])
         msgs = moved.flatMap(lambda kv: kv[1][1])
         verts.count()                         # one evaluation of the superstep; the counters are read after it
-        return verts, msgs, sent.value, active.value
+        return verts, msgs, sent.value, active.value, moved
 
     @classmethod
     def addAggregatorArg(cls, compute):

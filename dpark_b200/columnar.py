@@ -52,7 +52,7 @@ def _key_column(keys):
         arr = np.array(keys, dtype=np.float64)
         if np.isnan(arr).any():
             raise TypeError("NaN keys are not supported (CPython hashes NaN by identity)")
-        return KEY_F64, arr, None
+        return KEY_F64, arr + 0.0, None      # -0.0 and 0.0 are ONE dict key in Python: canonical spelling 0.0 on every path
     if t is str or t is bytes:
         blobs = [k.encode("utf-8", "surrogatepass") for k in keys] if t is str else keys
         offs = np.zeros(len(blobs) + 1, dtype=np.int64)
@@ -62,7 +62,7 @@ def _key_column(keys):
     if issubclass(t, np.integer):
         return KEY_I64, np.array(keys, dtype=np.int64), None
     if issubclass(t, np.floating):
-        return KEY_F64, np.array(keys, dtype=np.float64), None
+        return KEY_F64, np.array(keys, dtype=np.float64) + 0.0, None
     if t is bool or t in (list, dict, set, complex):
         raise _unhashable(t)                      # dpark/portable_hash.pyx:70
     if t is tuple or t is type(None):

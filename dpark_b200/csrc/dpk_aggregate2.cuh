@@ -40,6 +40,8 @@ constexpr int AG2_STACK = 40;
 struct Ag2Shared {
     int fb, sp, overflow, nres;
     unsigned long long excl;
+    int next_fb[2];                          // ticket of the next fine bucket (prefetched), by iteration parity
+    long long next_r0[2], next_r1[2];        // ... and its row range
     int wcnt[AG2_ITEMS * AG2_WARPS];   // claims per (item, warp), then their exclusive prefix
     int total;
     int stack_m[AG2_STACK], stack_r[AG2_STACK];
@@ -126,8 +128,16 @@ __device__ __forceinline__ uint32_t ag2_slot(const uint32_t (&slots)[3], int j) 
     return v & 0xfffu;
 }
 
-template <typename KeyT, typename ValT, typename AccT>
-__global__ void __launch_bounds__(AG2_THREADS, 3)
+// CURSOR = true (default): the output range of a fine bucket inside its partition is reserved with ONE
+// atomicAdd on the partition's count (the buckets of a partition come out in any order: a reduce partition is a
+// set).  CURSOR = false: the round-1 scheme, a chained scan with decoupled look-back over fb_state[] (deterministic
+// order).  Measured on B200 (profiles/r02_ncu_findings.md): with ~450 resident CTAs all finishing equal-sized
+// buckets in lockstep, the look-back waits for the SLOWEST of its ~32 nearest predecessors every time -- 24 % of the
+// kernel's stall samples sat at the barrier behind it, ~78 polls per bucket -- and widening the window to 256
+// predecessors made it worse; the atomic costs a fixed L2 round trip, no waiting on other CTAs, and lifts the
+// in-order requirement, so the next ticket and its row range are prefetched a bucket ahead.
+template <typename KeyT, typename ValT, typename AccT, int MINB, bool CURSOR>
+__global__ void __launch_bounds__(AG2_THREADS, MINB)
 k_smem_aggregate2(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, int op,
                   const int64_t *__restrict__ fine_off, int32_t nfine, int32_t fine_per_part,
                   const int64_t *__restrict__ part_offsets, KeyT *__restrict__ out_keys,
@@ -148,8 +158,9 @@ k_smem_aggregate2(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, 
 #pragma unroll
         for (int i = 0; i < AG2_TAGS / 4 / AG2_THREADS; i++) t4[i * AG2_THREADS + threadIdx.x] = make_uint4(0, 0, 0, 0);
     };
-    // stage the rows [g0, g0 + w) of the input at staged indices [at, at + w)
-    auto stage = [&](int64_t g0, int w, int at, auto ni_tag) {
+    // stage the rows [g0, g0 + w) of the input at staged indices [at, at + w); between its loads and its stores
+    // thread 0 runs `between` (the ticket prefetch: its L2 round trip overlaps the row loads)
+    auto stage = [&](int64_t g0, int w, int at, auto ni_tag, auto between) {
         constexpr int NI = decltype(ni_tag)::value;
         KeyT kr[NI];
         ValT vr[NI];
@@ -158,6 +169,7 @@ k_smem_aggregate2(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, 
             const int i = j * AG2_THREADS + (int)threadIdx.x;
             if (i < w) { kr[j] = keys[g0 + i]; vr[j] = vals[g0 + i]; }
         }
+        between();
 #pragma unroll
         for (int j = 0; j < NI; j++) {
             const int i = j * AG2_THREADS + (int)threadIdx.x;
@@ -168,6 +180,7 @@ k_smem_aggregate2(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, 
             }
         }
     };
+    auto nothing = []() {};
     // warp 0: exclusive prefix of the (item, warp) claim counts in place, total -> sh.total
     auto scan_claims = [&]() {
         constexpr int N = AG2_ITEMS * AG2_WARPS;   // 64
@@ -186,39 +199,76 @@ k_smem_aggregate2(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, 
     };
 
     clear_tags();
-    for (;;) {
-        if (threadIdx.x == 0) sh.fb = atomicAdd(work_counter, 1);  // in-order hand-out (what the chained look-back relies on)
+    if (threadIdx.x == 0) {
+        const int t = atomicAdd(work_counter, 1);
+        sh.next_fb[0] = t;
+        if (t < nfine) { sh.next_r0[0] = fine_off[t]; sh.next_r1[0] = fine_off[t + 1]; }
+    }
+    for (int it = 0;; it++) {
         __syncthreads();                                            // (A) also: previous write-out and tag clear finished
-        const int fb = sh.fb;
+        const int fb = sh.next_fb[it & 1];
         if (fb >= nfine) break;
-        const int64_t r0 = fine_off[fb], r1 = fine_off[fb + 1];
+        const int64_t r0 = sh.next_r0[it & 1], r1 = sh.next_r1[it & 1];
         const int p = fb / fine_per_part;
         const int first_fb = p * fine_per_part;
         const bool last_fb = fb == first_fb + fine_per_part - 1;
         const int64_t pbase = part_offsets[p];
         uint32_t offs[2], slots[3];
         int lane_cnt;
+        // next ticket: taken while this bucket's rows are in flight (CURSOR: any order is fine; look-back: the ticket
+        // must not be taken before this bucket is published, so it is taken at the end instead)
+        int nt = 0;
+        long long nr0 = 0, nr1 = 0;
+        auto prefetch_ticket = [&]() {
+            if (CURSOR && threadIdx.x == 0) nt = atomicAdd(work_counter, 1);
+        };
+        auto prefetch_range = [&]() {
+            if (CURSOR && threadIdx.x == 0) {
+                sh.next_fb[(it + 1) & 1] = nt;
+                if (nt < nfine) { nr0 = fine_off[nt]; nr1 = fine_off[nt + 1]; }
+            }
+        };
+        auto publish_range = [&]() {   // before a barrier that precedes (A) of the next iteration
+            if (threadIdx.x == 0) {
+                if (!CURSOR) {
+                    nt = atomicAdd(work_counter, 1);
+                    sh.next_fb[(it + 1) & 1] = nt;
+                    if (nt < nfine) { nr0 = fine_off[nt]; nr1 = fine_off[nt + 1]; }
+                }
+                sh.next_r0[(it + 1) & 1] = nr0;
+                sh.next_r1[(it + 1) & 1] = nr1;
+            }
+        };
 
         if (r1 - r0 <= AG2_CAP) {
             // ================= fast path: the whole bucket is one window, one pass
             const int n = (int)(r1 - r0);
-            stage(r0, n, 0, std::integral_constant<int, AG2_ITEMS>());
+            stage(r0, n, 0, std::integral_constant<int, AG2_ITEMS>(), prefetch_ticket);
+            prefetch_range();
             __syncthreads();                                        // (S) rows staged
             const unsigned mine = ag2_insert<AccT, false, AG2_ITEMS>(0, n, 1, 0, op, tag_base, key_base, acc_base, s_acc, offs, &lane_cnt, slots);
             if (lane < AG2_ITEMS) sh.wcnt[lane * AG2_WARPS + warp] = lane_cnt;
+            if (CURSOR) publish_range();
             __syncthreads();                                        // (B) inserts done, claim counts written
             if (warp == 0) {
                 scan_claims();
                 __syncwarp();
                 const unsigned long long cnt = (unsigned long long)sh.total;
-                if (lane == 0) atomicExch(&fb_state[fb], AG_FLAG_AGG | cnt);
-                const unsigned long long e = ag_look_back(fb_state, first_fb, fb);
-                if (lane == 0) {
-                    sh.excl = e;
-                    atomicExch(&fb_state[fb], AG_FLAG_INC | (e + cnt));
-                    if (last_fb) out_counts[p] = *(volatile int *)&part_err[p] ? -1ll : (long long)(e + cnt);
+                if constexpr (CURSOR) {
+                    if (lane == 0) sh.excl = atomicAdd(reinterpret_cast<unsigned long long *>(&out_counts[p]), cnt);
+                } else {
+                    if (lane == 0) atomicExch(&fb_state[fb], AG_FLAG_AGG | cnt);
+                    const unsigned long long e = ag_look_back(fb_state, first_fb, fb);
+                    if (lane == 0) {
+                        sh.excl = e;
+                        atomicExch(&fb_state[fb], AG_FLAG_INC | (e + cnt));
+                        if (last_fb) out_counts[p] = *(volatile int *)&part_err[p] ? -1ll : (long long)(e + cnt);
+                    }
                 }
+            } else {
+                clear_tags();   // 7 warps x 4 x 16 B per thread cover 14 KB; warp 0 clears its share after the barrier
             }
+            if (!CURSOR) publish_range();
             __syncthreads();                                        // (D) offsets known
             const int64_t obase = pbase + (int64_t)sh.excl;
 #pragma unroll
@@ -230,11 +280,13 @@ k_smem_aggregate2(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, 
                     out_vals[o] = s_acc[idx];
                 }
             }
-            clear_tags();
+            if (warp == 0) clear_tags();
             continue;  // barrier (A) of the next iteration orders the reads and the clear before the next staging
         }
 
         // ================= general path: windows behind resident distinct rows, hash-disjoint passes on overflow
+        prefetch_ticket();
+        prefetch_range();
         unsigned long long written = 0, excl = 0;  // uniform
         bool have_excl = false, failed = false;
         if (threadIdx.x == 0) { sh.stack_m[0] = 1; sh.stack_r[0] = 0; sh.sp = 1; }
@@ -251,7 +303,7 @@ k_smem_aggregate2(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, 
                 const int room = AG2_CAP - nres;
                 if (room < AG2_MINW) { ok = false; break; }          // too many distinct keys for one pass
                 const int w = (int)min((int64_t)min(room, AG2_GEN_ITEMS * AG2_THREADS), r1 - cursor);
-                stage(cursor, w, nres, std::integral_constant<int, AG2_GEN_ITEMS>());
+                stage(cursor, w, nres, std::integral_constant<int, AG2_GEN_ITEMS>(), nothing);
                 __syncthreads();
                 const unsigned mine = ag2_insert<AccT, true, AG2_GEN_ITEMS>(nres, nres + w, m, r, op, tag_base, key_base, acc_base, s_acc, offs, &lane_cnt, slots);
                 if (lane < AG2_ITEMS) sh.wcnt[lane * AG2_WARPS + warp] = lane_cnt;
@@ -292,7 +344,13 @@ k_smem_aggregate2(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, 
                 __syncthreads();
                 continue;
             }
-            if (!have_excl) {  // multi-pass buckets publish only their inclusive value, at the end
+            if constexpr (CURSOR) {
+                if (threadIdx.x == 0)
+                    sh.excl = atomicAdd(reinterpret_cast<unsigned long long *>(&out_counts[p]), (unsigned long long)nres);
+                __syncthreads();
+                excl = sh.excl;
+                written = 0;
+            } else if (!have_excl) {  // multi-pass buckets publish only their inclusive value, at the end
                 if (warp == 0) {
                     const unsigned long long e = ag_look_back(fb_state, first_fb, fb);
                     if (lane == 0) sh.excl = e;
@@ -311,12 +369,23 @@ k_smem_aggregate2(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, 
             __syncthreads();
         }
         if (warp == 0) {
-            unsigned long long e = have_excl ? excl : ag_look_back(fb_state, first_fb, fb);
-            if (lane == 0) {
-                if (failed) { atomicExch(&part_err[p], 1); __threadfence(); }
-                atomicExch(&fb_state[fb], AG_FLAG_INC | (e + written));
-                if (last_fb) out_counts[p] = (failed || *(volatile int *)&part_err[p]) ? -1ll : (long long)(e + written);
+            if constexpr (CURSOR) {
+                if (lane == 0 && failed) atomicExch(&part_err[p], 1);
+            } else {
+                unsigned long long e = have_excl ? excl : ag_look_back(fb_state, first_fb, fb);
+                if (lane == 0) {
+                    if (failed) { atomicExch(&part_err[p], 1); __threadfence(); }
+                    atomicExch(&fb_state[fb], AG_FLAG_INC | (e + written));
+                    if (last_fb) out_counts[p] = (failed || *(volatile int *)&part_err[p]) ? -1ll : (long long)(e + written);
+                }
             }
         }
+        publish_range();
     }
+}
+
+// CURSOR mode: mark the partitions whose merge failed (out_counts = -1), after the merge kernel
+__global__ void k_agg_finalize(const int *__restrict__ part_err, long long *__restrict__ out_counts, int32_t nparts) {
+    for (int p = threadIdx.x; p < nparts; p += blockDim.x)
+        if (part_err[p]) out_counts[p] = -1;
 }

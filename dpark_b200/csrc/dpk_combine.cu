@@ -445,6 +445,8 @@ int g_reduce_impl = 2;  // dpk_set_option("reduce_impl", 0|1|2)
 
 constexpr int AG_MAX_SB2 = 10;       // at most 1024 fine buckets per first-level bucket
 int g_agg_wide = 1;
+int g_agg_ctas = 3;
+int g_agg_cursor = 1;
 int g_agg_impl = 1;                  // dpk_set_option("agg_impl"): 1 = k_smem_aggregate2 (row-index tags), 0 = round-1 kernel
 int g_agg_target_rows = 2048;        // rows per fine bucket the split aims for (table load <= 0.5)
 
@@ -502,13 +504,18 @@ static int dispatch_op(const Ctx &c) {
         DPK_CUDA_TRY(cudaFuncSetAttribute(agg, cudaFuncAttributeMaxDynamicSharedMemorySize, agg_smem));
         DPK_CUDA_TRY(cudaMemsetAsync(c.fb_state, 0, (size_t)nfine * 8, c.st));
         if (g_agg_impl == 1) {
-            auto agg2 = k_smem_aggregate2<KeyT, ValT, AccT>;
+            // dpk_set_option("agg_ctas"): resident CTAs per SM the kernel is compiled for (3: 80 registers, 4: 64)
+            // dpk_set_option("agg_cursor"): 1 = output ranges reserved with one atomicAdd per fine bucket, 0 = chained look-back
+            auto agg2 = g_agg_cursor ? (g_agg_ctas == 4 ? k_smem_aggregate2<KeyT, ValT, AccT, 4, true> : k_smem_aggregate2<KeyT, ValT, AccT, 3, true>)
+                                     : (g_agg_ctas == 4 ? k_smem_aggregate2<KeyT, ValT, AccT, 4, false> : k_smem_aggregate2<KeyT, ValT, AccT, 3, false>);
             const int smem2 = AG2_TAGS * 4 + AG2_CAP * 16;
             DPK_CUDA_TRY(cudaFuncSetAttribute(agg2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
             DPK_CUDA_TRY(cudaMemsetAsync(c.part_err, 0, (size_t)c.nparts * 4, c.st));
             DPK_LAUNCH("smem_aggregate", c.st, agg2<<<grid, AG2_THREADS, smem2, c.st>>>(
                 rekeys, revals, c.op, c.fine_off, nfine, (1 << c.f.sub_bits) * S2, c.part_off,
                 (KeyT *)c.out_keys, c.out_vals, (long long *)c.out_counts, c.fb_state, c.bucket_counter, c.part_err));
+            if (g_agg_cursor)
+                DPK_LAUNCH("agg_finalize", c.st, k_agg_finalize<<<1, 256, 0, c.st>>>(c.part_err, (long long *)c.out_counts, c.nparts));
             return DPK_OK;
         }
         DPK_LAUNCH("smem_aggregate", c.st, agg<<<grid, AG_THREADS, agg_smem, c.st>>>(
@@ -604,6 +611,16 @@ int dpk_set_option(const char *name, int64_t value) {
         g_agg_impl = (int)value;
         return DPK_OK;
     }
+    if (strcmp(name, "agg_cursor") == 0) {
+        if (value != 0 && value != 1) return fail(DPK_ERR_INVALID, "agg_cursor must be 0 or 1");
+        g_agg_cursor = (int)value;
+        return DPK_OK;
+    }
+    if (strcmp(name, "agg_ctas") == 0) {
+        if (value != 3 && value != 4) return fail(DPK_ERR_INVALID, "agg_ctas must be 3 or 4");
+        g_agg_ctas = (int)value;
+        return DPK_OK;
+    }
     if (strcmp(name, "agg_wide") == 0) {
         if (value != 0 && value != 1) return fail(DPK_ERR_INVALID, "agg_wide must be 0 or 1");
         g_agg_wide = (int)value;
@@ -612,6 +629,11 @@ int dpk_set_option(const char *name, int64_t value) {
     if (strcmp(name, "scatter_items") == 0) {
         if (value != 8 && value != 16) return fail(DPK_ERR_INVALID, "scatter_items must be 8 or 16");
         g_scatter_items = (int)value;
+        return DPK_OK;
+    }
+    if (strcmp(name, "scatter_threads") == 0) {
+        if (value != 256 && value != 512) return fail(DPK_ERR_INVALID, "scatter_threads must be 256 or 512");
+        g_scatter_threads = (int)value;
         return DPK_OK;
     }
     if (strcmp(name, "scatter_bulk") == 0) {

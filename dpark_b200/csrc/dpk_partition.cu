@@ -41,6 +41,7 @@ int g_scatter_items = 16;
 // dpk_set_option("scatter_bulk"): 1 (default) = unordered multisplits run k_part_scatter_bulk (CTA-wide
 // shared-memory ranking + TMA bulk stores of the staged bucket runs); 0 = the round-1 kernel (A/B switch)
 int g_scatter_bulk = 1;
+int g_scatter_threads = 512;
 
 // Segmented mode (second-level split on the reduce side): the grid runs over a
 // device-resident chunk table instead of equal row ranges; every chunk lies inside
@@ -64,6 +65,7 @@ struct Plan {
     int32_t T;  // CTAs (row ranges, or the chunk-table upper bound in segmented mode)
     int64_t L;  // rows per CTA, multiple of PT_TILE
     SegTab seg;
+    const char *label_count = nullptr, *label_scatter = nullptr;  // profiling labels (default: part_* / seg_*)
 };
 
 static Plan make_plan(int64_t n) {
@@ -115,6 +117,7 @@ __device__ __forceinline__ unsigned warp_peers(int id, int nbits) {
 
 // exclusive scan of one int per thread over the 256-thread CTA; returns the
 // exclusive prefix, *total gets the CTA sum.  s_warp: >= PT_WARPS ints.
+template <int NW = PT_WARPS>
 __device__ __forceinline__ int block_excl_scan(int v, int *s_warp, int *total) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int inc = v;
@@ -127,7 +130,7 @@ __device__ __forceinline__ int block_excl_scan(int v, int *s_warp, int *total) {
     __syncthreads();
     int base = 0, tot = 0;
 #pragma unroll
-    for (int w = 0; w < PT_WARPS; w++) {
+    for (int w = 0; w < NW; w++) {
         int t = s_warp[w];
         if (w < warp) base += t;
         tot += t;
@@ -479,20 +482,21 @@ __device__ __forceinline__ void flush_run(T *__restrict__ out, int64_t g, const 
     for (int i = head + mid; i < cnt; i++) dst[i] = s_col[s0 + i];
 }
 
-template <typename KeyT, typename ValT, int PRE>
-__global__ void __launch_bounds__(PT_THREADS, 2)
+template <typename KeyT, typename ValT, int PRE, int NT>
+__global__ void __launch_bounds__(NT, 2)
 k_part_scatter_bulk(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, int64_t n, int64_t L,
                     PartFn f, const int32_t *__restrict__ tile_off, int32_t T,
                     const int64_t *__restrict__ bucket_base, KeyT *__restrict__ out_keys,
                     ValT *__restrict__ out_vals, BulkSmem lay, SegTab seg) {
     constexpr bool HAS_VAL = !std::is_same<ValT, NoVal>::value;
-    constexpr int ITEMS = 16;
-    constexpr int TILE = PT_THREADS * ITEMS;
+    constexpr int ITEMS = PT_TILE / NT;   // 16 rows per thread with 256 threads, 8 with 512 (twice the resident warps)
+    constexpr int TILE = PT_TILE;
+    constexpr int NW = NT / 32;
     constexpr int AK = 16 / (int)sizeof(KeyT);
     constexpr int AV = HAS_VAL ? 16 / (int)sizeof(typename std::conditional<HAS_VAL, ValT, int64_t>::type) : 1;
     extern __shared__ __align__(128) unsigned char smem_bulk[];
     unsigned char *smem = smem_bulk;
-    __shared__ int s_warp[PT_WARPS];
+    __shared__ int s_warp[NW];
     KeyT *s_key = reinterpret_cast<KeyT *>(smem + lay.key_off);
     ValT *s_val = reinterpret_cast<ValT *>(smem + lay.val_off);
     int64_t *s_gpos = reinterpret_cast<int64_t *>(smem + lay.gpos_off);
@@ -508,13 +512,13 @@ k_part_scatter_bulk(const KeyT *__restrict__ keys, const ValT *__restrict__ vals
     const int64_t beg = seg.cbeg ? seg.cbeg[blockIdx.x] : ((int64_t)blockIdx.x * L / T) * PT_TILE;
     const int64_t end = seg.cbeg ? seg.cend[blockIdx.x] : min(n, ((int64_t)(blockIdx.x + 1) * L / T) * PT_TILE);
     if (seg.cbeg) {
-        for (int p = threadIdx.x; p < P; p += PT_THREADS) s_gpos[p] = seg.chunk_off[(int64_t)blockIdx.x * P + p];
+        for (int p = threadIdx.x; p < P; p += NT) s_gpos[p] = seg.chunk_off[(int64_t)blockIdx.x * P + p];
     } else {
-        for (int p = threadIdx.x; p < P; p += PT_THREADS)
+        for (int p = threadIdx.x; p < P; p += NT)
             s_gpos[p] = bucket_base[p] + (int64_t)tile_off[(int64_t)p * T + blockIdx.x];
     }
-    for (int p = threadIdx.x; p < 2 * P; p += PT_THREADS) s_cnt[p] = 0;
-    const int E = (P + PT_THREADS - 1) / PT_THREADS;  // buckets per thread in the scan
+    for (int p = threadIdx.x; p < 2 * P; p += NT) s_cnt[p] = 0;
+    const int E = (P + NT - 1) / NT;  // buckets per thread in the scan
 
     KeyT k[ITEMS];
     ValT v[ITEMS];
@@ -567,7 +571,7 @@ k_part_scatter_bulk(const KeyT *__restrict__ keys, const ValT *__restrict__ vals
             int sum = 0;
             for (int i = b; i < min(b + E, P); i++) sum += (int)cnt[i];
             int tot;
-            int run = block_excl_scan(sum, s_warp, &tot);
+            int run = block_excl_scan<NW>(sum, s_warp, &tot);
             for (int i = b; i < min(b + E, P); i++) {
                 const int64_t g = s_gpos[i];
                 const uint32_t gk = (uint32_t)(((uintptr_t)(out_keys + g)) / sizeof(KeyT));
@@ -598,7 +602,7 @@ k_part_scatter_bulk(const KeyT *__restrict__ keys, const ValT *__restrict__ vals
         __syncthreads();  // (C)
 
         // ---- copy-out: bucket runs leave through the TMA
-        for (int p = threadIdx.x; p < P; p += PT_THREADS) {
+        for (int p = threadIdx.x; p < P; p += NT) {
             const int c = (int)cnt[p];
             if (c) {
                 const int64_t g = s_gpos[p];
@@ -618,7 +622,7 @@ template <typename KeyT, int PRE>
 static int launch_count(const void *keys, int64_t n, const Plan &pl, const PartFn &f,
                         int32_t *tile_counts, cudaStream_t st) {
     size_t sh = (size_t)f.nbuckets() * sizeof(int32_t) * (f.nbuckets() <= PT_COUNT_PRIV ? PT_WARPS : 1);
-    DPK_LAUNCH(pl.seg.cbeg ? "seg_count" : "part_count", st, k_part_count<KeyT, PRE><<<pl.T, PT_THREADS, sh, st>>>((const KeyT *)keys, n, pl.L, f, tile_counts, pl.T, pl.seg, g_count_mode));
+    DPK_LAUNCH(pl.label_count ? pl.label_count : (pl.seg.cbeg ? "seg_count" : "part_count"), st, k_part_count<KeyT, PRE><<<pl.T, PT_THREADS, sh, st>>>((const KeyT *)keys, n, pl.L, f, tile_counts, pl.T, pl.seg, g_count_mode));
     return DPK_OK;
 }
 
@@ -649,7 +653,7 @@ static int launch_scatter_items(const void *keys, const void *vals, int64_t n, c
     if (lay.total > 227 * 1024)
         return fail(DPK_ERR_UNSUPPORTED, "%d buckets need %lld B of shared memory", f.nbuckets(), (long long)lay.total);
     DPK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
-    DPK_LAUNCH(pl.seg.cbeg ? "seg_scatter" : "part_scatter", st,
+    DPK_LAUNCH(pl.label_scatter ? pl.label_scatter : (pl.seg.cbeg ? "seg_scatter" : "part_scatter"), st,
                kern<<<pl.T, PT_THREADS, (size_t)lay.total, st>>>((const KeyT *)keys, (const ValT *)vals, n, pl.L, f,
                                                                 tile_off, pl.T, bucket_base, (KeyT *)out_keys,
                                                                 (ValT *)out_vals, lay, pl.seg));
@@ -662,10 +666,12 @@ static int launch_scatter_bulk(const void *keys, const void *vals, int64_t n, co
                                void *out_vals, cudaStream_t st) {
     constexpr int vb = std::is_same<ValT, NoVal>::value ? 0 : (int)sizeof(ValT);
     BulkSmem lay = bulk_smem((int)sizeof(KeyT), vb, f.nbuckets(), PT_TILE);
-    auto kern = k_part_scatter_bulk<KeyT, ValT, PRE>;
+    // dpk_set_option("scatter_threads"): 512 (default; 8 rows per thread, 32 warps per SM) or 256 (16 rows per thread)
+    const int nt = g_scatter_threads;
+    auto kern = nt == 512 ? k_part_scatter_bulk<KeyT, ValT, PRE, 512> : k_part_scatter_bulk<KeyT, ValT, PRE, 256>;
     DPK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
-    DPK_LAUNCH(pl.seg.cbeg ? "seg_scatter" : "part_scatter", st,
-               kern<<<pl.T, PT_THREADS, (size_t)lay.total, st>>>((const KeyT *)keys, (const ValT *)vals, n, pl.L, f,
+    DPK_LAUNCH(pl.label_scatter ? pl.label_scatter : (pl.seg.cbeg ? "seg_scatter" : "part_scatter"), st,
+               kern<<<pl.T, nt, (size_t)lay.total, st>>>((const KeyT *)keys, (const ValT *)vals, n, pl.L, f,
                                                                 tile_off, pl.T, bucket_base, (KeyT *)out_keys,
                                                                 (ValT *)out_vals, lay, pl.seg));
     return DPK_OK;
@@ -974,6 +980,8 @@ int dpk_radix_pass(const int64_t *keys, const void *vals, int32_t val_bytes, int
     int64_t *totals = (int64_t *)((char *)ws + ws_counts_bytes(F));
     int64_t *offsets = (int64_t *)((char *)totals + align_up((int64_t)F * 8, 256));
     Plan pl = make_plan(n);
+    pl.label_count = "radix_count";
+    pl.label_scatter = "radix_scatter";
     rc = dispatch_count(keys, -1, n, pl, f, tile_counts, st);
     if (rc) return rc;
     DPK_LAUNCH("part_scan", st, k_part_scan<<<F, PT_THREADS, 0, st>>>(tile_counts, pl.T, totals));

@@ -87,6 +87,13 @@ def _run_reduce(splits, P, thr, op, dev):
         if vkinds:
             vdt = torch.int64 if vkinds == {columnar.VAL_I64} else torch.float64
             vc = [v.to(vdt) for v in vc]
+        if vkinds == {columnar.VAL_I64} and op == "sum":
+            # the reference adds Python big ints; the device accumulates in int64.  A cheap sufficient check: if the
+            # sum of |v| over the whole shuffle stays below 2^63 no key's sum can wrap
+            bound = sum(float(np.abs(c.vals.astype(np.float64)).sum()) for c in splits if c.n)
+            if bound >= 2.0 ** 63:
+                raise OverflowError("reduceByKey(add): the values' magnitudes sum to %.3g >= 2^63; int64 accumulation on the "
+                                    "B200 path could wrap where the reference's big ints do not" % bound)
         parts = shuffle.reduce_by_key(kc, vc, P, op, thr)
         for p, k, v in parts:
             res.parts[p] = (k.cpu().numpy().tolist(), v.cpu().numpy().tolist())

@@ -15,8 +15,12 @@ forms:
                   HBM pass, but the stores are the short bucket runs of one tile, which NVLink
                   carries poorly (measured slower than "push" from 2 GPUs up).
 
-What remains of the collective in both forms is the small all-gather of the counts matrix (the
-MapOutputTracker) and two stream-ordered barriers.
+What remains of the collective is the small all-gather of the counts matrix (the MapOutputTracker)
+and ONE stream-ordered barrier per step ("every peer's stores have landed"): the receive buffers are
+double-buffered, so the step that overwrites a buffer is two barriers after the step that read it.
+Nothing is read back by the host on this path: receive sizes stay on the device (the reduce side takes
+them from the segment matrix), and a receive buffer that is too small raises a device flag
+(PeerExchange.check(), read together with the result sizes) instead of a per-step host sync.
 
 Layout of a receive buffer = what exchange() delivers: source-rank-major, bucket-major inside.
 """
@@ -28,9 +32,10 @@ from .shuffle import Received, owner_blocks
 
 
 class PeerExchange(object):
-    """Symmetric receive buffers (keys + values) of `capacity` rows on every rank."""
+    """Symmetric receive buffers (keys + values) of `capacity` rows on every rank, two of each
+    (alternating per step)."""
 
-    def __init__(self, capacity, key_dtype, val_dtype, device=None, group=None, mode="push"):
+    def __init__(self, capacity, key_dtype, val_dtype, device=None, group=None, mode="push", buffers=2):
         import torch.distributed._symmetric_memory as symm
         if mode not in ("push", "fused"):
             raise ValueError("mode must be 'push' (scatter locally, then block pushes) or 'fused' "
@@ -41,16 +46,64 @@ class PeerExchange(object):
         self.world = dist.get_world_size(self.group)
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         self.capacity = int(capacity)
-        self.keys = symm.empty(self.capacity, dtype=key_dtype, device=self.device)
-        self.vals = symm.empty(self.capacity, dtype=val_dtype, device=self.device)
+        self.nbuf = max(1, int(buffers))
         name = self.group.group_name
-        self.hk = symm.rendezvous(self.keys, name)
-        self.hv = symm.rendezvous(self.vals, name)
-        self.key_base = torch.tensor([int(p) for p in self.hk.buffer_ptrs], dtype=torch.int64, device=self.device)
-        self.val_base = torch.tensor([int(p) for p in self.hv.buffer_ptrs], dtype=torch.int64, device=self.device)
+        self._keys, self._vals, self._hk, self._hv, self._kb, self._vb = [], [], [], [], [], []
+        for _ in range(self.nbuf):
+            k = symm.empty(self.capacity, dtype=key_dtype, device=self.device)
+            v = symm.empty(self.capacity, dtype=val_dtype, device=self.device)
+            hk, hv = symm.rendezvous(k, name), symm.rendezvous(v, name)
+            self._keys.append(k)
+            self._vals.append(v)
+            self._hk.append(hk)
+            self._hv.append(hv)
+            self._kb.append(torch.tensor([int(p) for p in hk.buffer_ptrs], dtype=torch.int64, device=self.device))
+            self._vb.append(torch.tensor([int(p) for p in hv.buffer_ptrs], dtype=torch.int64, device=self.device))
+        self.step = 0
+        self.err = torch.zeros(1, dtype=torch.int64, device=self.device)   # max rows any rank needed beyond capacity
+        self._closed = False
+
+    # the buffer set of the current step
+    @property
+    def keys(self):
+        return self._keys[self.step % self.nbuf]
+
+    @property
+    def vals(self):
+        return self._vals[self.step % self.nbuf]
+
+    @property
+    def key_base(self):
+        return self._kb[self.step % self.nbuf]
+
+    @property
+    def val_base(self):
+        return self._vb[self.step % self.nbuf]
 
     def barrier(self):
-        self.hk.barrier()
+        self._hk[self.step % self.nbuf].barrier()
+
+    def advance(self):
+        self.step += 1
+
+    def note_need(self, need_rows):
+        """Device-side capacity check: remember by how many rows the largest receive exceeded the buffers."""
+        torch.maximum(self.err, (need_rows - self.capacity).reshape(1), out=self.err)
+
+    def check(self):
+        """Raise if any step since the last check() needed more rows than the receive buffers hold (one host
+        read; call it where the host synchronises anyway, e.g. next to the result sizes)."""
+        over = int(self.err.item())
+        if over > 0:
+            self.err.zero_()
+            raise RuntimeError("peer receive buffer too small: a step needed %d rows, capacity %d (results of that "
+                               "step are invalid)" % (self.capacity + over, self.capacity))
+
+    def close(self):
+        """Drop the symmetric allocations (all ranks must call it)."""
+        if not self._closed:
+            self._closed = True
+            self._keys, self._vals, self._hk, self._hv, self._kb, self._vb = [], [], [], [], [], []
 
 
 def push_plan(all_counts, blocks, rank):
@@ -70,11 +123,13 @@ def push_plan(all_counts, blocks, rank):
     return edge[rank, :-1].contiguous(), src_base[rank].contiguous(), R[rank].contiguous(), R.sum(0)
 
 
-def exchange_push(px, mo):
+def exchange_push(px, mo, need_host_count=False):
     """shuffle.exchange() over peer memory: the bucket-major map output `mo` stays local, and ONE
     launch of dpk_copy_segments pushes each peer's contiguous block (keys and values) into that
     peer's receive buffer with full-width stores.  The segment table is computed on the device from
-    the gathered counts; the only host read is the capacity check."""
+    the gathered counts; no host read (unless need_host_count: the group-by reduce side sizes its
+    sort buffers on the host).  The returned Received views the WHOLE receive buffer (`bound` rows);
+    the rows actually received are what its segment matrix says."""
     G, rank, dev = px.world, px.rank, px.device
     P, sb = mo.P, mo.sub_bits
     F = P << sb
@@ -89,23 +144,27 @@ def exchange_push(px, mo):
     all_counts = all_counts.view(G, F)
     blocks = [b << sb for b in owner_blocks(P, G)]
     send_first, dst_first, rows, recv_total = push_plan(all_counts, blocks, rank)
-    recv_rows = recv_total.cpu().tolist()                             # the one host read
-    need, nrecv = max(recv_rows), recv_rows[rank]
-    if need > px.capacity:
-        raise RuntimeError("peer receive buffer too small: need %d rows, capacity %d" % (need, px.capacity))
+    px.note_need(recv_total.max())
+    # clamp what is pushed to the capacity of the destination (an overflow is reported by check(); never write
+    # past a peer's buffer)
+    room = (px.capacity - dst_first).clamp_(min=0)
+    rows = torch.minimum(rows, room)
     cols = [(mo.keys.data_ptr(), px.key_base, mo.keys.element_size())]
     if mo.vals is not None:
         cols.append((mo.vals.data_ptr(), px.val_base, mo.vals.element_size()))
     src = torch.cat([a + send_first * sz for a, _, sz in cols])
     dst = torch.cat([base + dst_first * sz for _, base, sz in cols])
     nby = torch.cat([rows * sz for _, _, sz in cols])
-    px.barrier()                                                      # nobody still reads the buffers of the last step
     nv.copy_segments(src.contiguous(), dst.contiguous(), nby.contiguous())
     px.barrier()                                                      # every peer's stores have landed
     b0, b1 = blocks[rank], blocks[rank + 1]
     seg = all_counts[:, b0:b1].contiguous()
-    vals = px.vals[:nrecv] if mo.vals is not None else None
-    return Received(px.keys[:nrecv], vals, seg, b0 >> sb, (b1 - b0) >> sb, sb)
+    keys, vals = px.keys, (px.vals if mo.vals is not None else None)
+    px.advance()                                                      # the next step writes the other buffer set
+    if need_host_count:
+        nrecv = min(int(recv_total[rank].item()), px.capacity)
+        return Received(keys[:nrecv], None if vals is None else vals[:nrecv], seg, b0 >> sb, (b1 - b0) >> sb, sb)
+    return Received(keys, vals, seg, b0 >> sb, (b1 - b0) >> sb, sb, bound=True)
 
 
 def map_side_push(px, key_chunks, val_chunks, P, thresholds=None, sub_bits=0, unordered=True):
@@ -126,7 +185,7 @@ def map_side_push(px, key_chunks, val_chunks, P, thresholds=None, sub_bits=0, un
     # rows every source sends to every destination: R[s][d]
     R = torch.stack([all_counts[:, blocks[d]:blocks[d + 1]].sum(1) for d in range(G)], dim=1)   # [G, G]
     src_base = torch.cumsum(R, 0) - R                               # [s][d]: rows of earlier sources at d
-    need = int(R.sum(0).max().item())                               # host read: capacity check + recv sizes
+    need = int(R.sum(0).max().item())                               # host read: capacity check (stores cannot be clamped here)
     if need > px.capacity:
         raise RuntimeError("peer receive buffer too small: need %d rows, capacity %d" % (need, px.capacity))
     # offset of my bucket b inside its owner's buffer
@@ -141,7 +200,6 @@ def map_side_push(px, key_chunks, val_chunks, P, thresholds=None, sub_bits=0, un
     chunk_off = torch.cumsum(cm, 0) - cm                            # rows of earlier local chunks per bucket
     ksz, vsz = key_chunks[0].element_size(), val_chunks[0].element_size()
     kbase, vbase = px.key_base[owner], px.val_base[owner]
-    px.barrier()                                                    # nobody still reads the buffers of the last step
     for m, (k, v) in enumerate(zip(key_chunks, val_chunks)):
         off = dst_off + chunk_off[m]
         nv.partition_scatter_ptrs(k, v, P, (kbase + off * ksz).contiguous(), (vbase + off * vsz).contiguous(),
@@ -150,4 +208,6 @@ def map_side_push(px, key_chunks, val_chunks, P, thresholds=None, sub_bits=0, un
     b0, b1 = blocks[rank], blocks[rank + 1]
     nrecv = int(R[:, rank].sum().item())
     seg = all_counts[:, b0:b1].contiguous()
-    return Received(px.keys[:nrecv], px.vals[:nrecv], seg, b0 >> sub_bits, (b1 - b0) >> sub_bits, sub_bits)
+    keys, vals = px.keys, px.vals
+    px.advance()
+    return Received(keys[:nrecv], vals[:nrecv], seg, b0 >> sub_bits, (b1 - b0) >> sub_bits, sub_bits)

@@ -69,6 +69,11 @@ class RDD(object):
         self.should_cache = True
         return self
 
+    def uncache(self):
+        """Drop the cached partitions (they are recomputed from the lineage if read again)."""
+        self._cache = None
+        return self
+
     def set_rddconf(self, rddconf):
         self.rddconf = conf.default_rddconf.dup() if rddconf is None else rddconf
 

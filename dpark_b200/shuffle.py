@@ -24,10 +24,12 @@ import torch
 
 from . import _native as nv
 
-# rows per first-level bucket the reduce side aims for: it splits every bucket once
-# more (<= 1024-way) into fine buckets of <= ~2 k rows that are merged in shared memory
-# (dpk_combine.cu, implementation 2), so 2^19 rows per bucket is the upper end
-TARGET_BUCKET_ROWS = 1 << 19
+# rows the reduce side wants in a fine bucket (second-level split, merged in shared memory: dpk_combine.cu,
+# implementation 2) and the widest second-level split it can do
+FINE_BUCKET_ROWS = 1536
+MAX_SECOND_LEVEL = 1024
+TARGET_BUCKET_ROWS = FINE_BUCKET_ROWS * MAX_SECOND_LEVEL      # upper end of a first-level bucket (all ranks' rows)
+MAX_FIRST_LEVEL = 512        # map-side bucket runs of a 4096-row tile stay >= 8 rows (64 B); 1024 only when forced
 
 
 def owner_blocks(P, G):
@@ -36,16 +38,56 @@ def owner_blocks(P, G):
     return [min(P, g * per) for g in range(G + 1)]
 
 
-def choose_sub_bits(total_rows, P):
-    """Sub-bucket bits so that a fine bucket holds ~TARGET_BUCKET_ROWS rows of
-    the whole job, capped by the kernel's bucket limit."""
+def choose_sub_bits(rows, P, world=1):
+    """Sub-bucket bits of the map side (first split level) for `rows` rows PER RANK on `world` ranks.
+
+    The job needs rows * world / FINE_BUCKET_ROWS fine buckets in all; they are reached in two levels, the map
+    side's P << sub_bits buckets and the reduce side's second-level split (<= 1024-way).  The levels are balanced
+    (first level ~ sqrt of the total), the first level stays at <= 512 buckets so that the bucket runs of a map-side
+    tile stay long (256 buckets at 1 GPU and 1e8 rows, 512 x 512 at 4 GPUs, 512 x 1024 at 8), and grows to 1024
+    only when the second level could not absorb the rest."""
+    total = float(rows) * max(1, world)
+    nf = total / FINE_BUCKET_ROWS
+    if nf <= P:
+        return 0
+    want = min(float(MAX_FIRST_LEVEL), nf ** 0.5)
     sb = 0
-    while (P << (sb + 1)) <= nv.MAX_PARTITIONS and sb < 12 and total_rows / float(P << sb) > TARGET_BUCKET_ROWS:
+    while sb < 12 and (P << (sb + 1)) <= min(nv.MAX_PARTITIONS, MAX_FIRST_LEVEL) and (P << sb) < want:
         sb += 1
-    # keep the map side's write runs long: at most 1024 buckets
-    while sb > 0 and (P << sb) > 1024:
-        sb -= 1
+    while sb < 12 and (P << (sb + 1)) <= min(nv.MAX_PARTITIONS, 1024) and total / float(P << sb) > TARGET_BUCKET_ROWS:
+        sb += 1
     return sb
+
+
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this process (and with it the pinned host buffers it allocates from now on: first touch) to the CPUs of
+    the NUMA node GPU `local_rank` hangs off.  Eight ranks pulling pinned memory across the socket interconnect
+    measured 1.8x slower per rank than one (round-1 SCALE run: GPU0-3 on node 0, GPU4-7 on node 1).  Returns the
+    node number, or None when the topology cannot be read (nothing is changed then)."""
+    import os
+    try:
+        props = torch.cuda.get_device_properties(local_rank)
+        bus = "%04x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                lo, hi = part.split("-")
+                cpus.update(range(int(lo), int(hi) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
 
 
 class MapOutput(object):
@@ -93,11 +135,14 @@ class Received(object):
     """Rows fetched for the partitions this rank owns.  keys/vals are laid out
     source-rank-major, then bucket-major; seg[s][b] = rows from source s for
     local fine bucket b."""
-    __slots__ = ("keys", "vals", "seg", "part_first", "nparts", "sub_bits")
+    __slots__ = ("keys", "vals", "seg", "part_first", "nparts", "sub_bits", "bound")
 
-    def __init__(self, keys, vals, seg, part_first, nparts, sub_bits):
+    def __init__(self, keys, vals, seg, part_first, nparts, sub_bits, bound=False):
         self.keys, self.vals, self.seg = keys, vals, seg
         self.part_first, self.nparts, self.sub_bits = part_first, nparts, sub_bits
+        # bound: keys/vals are a whole receive buffer (an upper bound of the rows); the rows actually received are
+        # seg.sum() and stay on the device (no host sync on the reduceByKey path)
+        self.bound = bound
 
 
 def exchange(mo, group=None):
@@ -179,8 +224,13 @@ def group_side(rx, P, thresholds=None, key_view=None, row_hash=None):
     partition-major, then CSR.  rx.keys: int64 key bits (for float keys pass
     key_view=torch.float64 so that the partition step hashes them as floats; for
     row-id keys pass row_hash so that the partition step uses the looked-up hash).
-    Returns (group_keys, group_starts, ngroups, values, part_offsets[P+1]); group g
-    holds values[group_starts[g] : group_starts[g+1]], groups are partition-major."""
+    Returns (group_keys, group_starts, ngroups, values, part_offsets[nparts+1]); group g
+    holds values[group_starts[g] : group_starts[g+1]], groups are partition-major; part_offsets are the
+    value-row offsets of the partitions this rank owns."""
+    if rx.bound:   # the sort sizes its buffers on the host
+        nrecv = int(rx.seg.sum().item())
+        rx = Received(rx.keys[:nrecv], None if rx.vals is None else rx.vals[:nrecv], rx.seg, rx.part_first, rx.nparts,
+                      rx.sub_bits)
     k, v = sort_by_key_bits(rx.keys, rx.vals)
     if row_hash is not None:
         # keys are representative row ids: partition by the hash of the key they stand for,
@@ -190,15 +240,28 @@ def group_side(rx, P, thresholds=None, key_view=None, row_hash=None):
     pk = k if key_view is None else k.view(key_view)
     ok, ov, off = nv.partition(pk, v, P, thresholds)
     gk, gs, ng = nv.group_heads(ok.view(torch.int64))
-    return gk, gs, ng, ov, off
+    # offsets of the partitions this rank owns (the others are empty here)
+    return gk, gs, ng, ov, off[rx.part_first:rx.part_first + rx.nparts + 1]
+
+
+def _world(group=None):
+    import torch.distributed as dist
+    return dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+
+
+def check_counts(cnt_h):
+    """out_counts of the reduce side on the host: -1 marks a partition whose merge overflowed beyond recovery
+    (more distinct keys in one fine bucket than its hash bits can split: dpk_aggregate2.cuh)."""
+    if any(c < 0 for c in cnt_h):
+        raise nv.NativeError("reduce side: a fine bucket overflowed its shared-memory table beyond the splittable hash "
+                             "bits; the partition's result is invalid (dpk_combine out_counts = -1)")
 
 
 class HostShuffle(object):
-    """End-to-end reduceByKey for HOST-resident columns: the call a user of the
-    plugin makes when rows arrive from Python / files (SURVEY.md §8b seam 2).
-    Per call: pinned host -> device copy of every map split, map_side,
-    exchange, reduce_side, device -> pinned host copy of every partition's
-    distinct (key, combined) rows.  Buffers are allocated once and reused."""
+    """End-to-end reduceByKey for HOST-resident columns, one batch at a time: the serial form of
+    HostShuffleStream (depth 1).  Per call: pinned host -> device copy of every map split, map_side,
+    exchange, reduce_side, device -> pinned host copy of every partition's distinct (key, combined)
+    rows.  Buffers are allocated once and reused."""
 
     def __init__(self, n_rows, key_dtype, val_dtype, P, op="sum", splits=8, thresholds=None, group=None,
                  device=None, sub_bits=None, world=1, peer_exchange=None, map_combine=False):
@@ -207,7 +270,7 @@ class HostShuffle(object):
         self.peer_exchange = peer_exchange
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         self.n = n_rows
-        self.sub_bits = choose_sub_bits(n_rows * world, P) if sub_bits is None else sub_bits
+        self.sub_bits = choose_sub_bits(n_rows, P, world) if sub_bits is None else sub_bits
         self.h_keys = torch.empty(n_rows, dtype=key_dtype).pin_memory()
         self.h_vals = torch.empty(n_rows, dtype=val_dtype).pin_memory()
         self.d_keys = torch.empty(n_rows, dtype=key_dtype, device=self.device)
@@ -228,73 +291,92 @@ class HostShuffle(object):
             self.d_vals[a:b].copy_(self.h_vals[a:b], non_blocking=True)
             kc.append(self.d_keys[a:b])
             vc.append(self.d_vals[a:b])
-        if self.peer_exchange is not None and self.peer_exchange.mode == "fused" and not self.map_combine:
+        px = self.peer_exchange
+        if px is not None and px.mode == "fused" and not self.map_combine:
             from . import peer                 # the scatter kernel stores straight into peer memory
-            rx = peer.map_side_push(self.peer_exchange, kc, vc, self.P, self.thresholds, self.sub_bits)
+            rx = peer.map_side_push(px, kc, vc, self.P, self.thresholds, self.sub_bits)
         else:
             mo = map_side(kc, vc, self.P, self.thresholds, False, self.sub_bits, unordered=True)
             if self.map_combine:
                 mo = combine_map_output(mo, self.op, self.thresholds)
-            if self.peer_exchange is not None:  # block push over NVLink peer memory
+            if px is not None:                 # block push over NVLink peer memory
                 from . import peer
-                rx = peer.exchange_push(self.peer_exchange, mo)
+                rx = peer.exchange_push(px, mo)
             else:
                 rx = exchange(mo, self.group)
         ok, ov, po, cnt = reduce_side(rx, self.op, self.P, self.thresholds)
         po_h, cnt_h = po.cpu().tolist(), cnt.cpu().tolist()      # the one host sync: result sizes
-        nrx = int(ok.numel())
-        if self.out_keys is None or self.out_keys.numel() < nrx:
-            self.out_keys = torch.empty(nrx, dtype=ok.dtype).pin_memory()
-            self.out_vals = torch.empty(nrx, dtype=ov.dtype).pin_memory()
-        res, d2h = [], 0
+        check_counts(cnt_h)
+        if px is not None:
+            px.check()
+        nout = sum(cnt_h)
+        if self.out_keys is None or self.out_keys.numel() < nout:
+            self.out_keys = torch.empty(max(nout, 1), dtype=ok.dtype).pin_memory()
+            self.out_vals = torch.empty(max(nout, 1), dtype=ov.dtype).pin_memory()
+        res, at = [], 0
         for j in range(rx.nparts):
             a, c = po_h[j], cnt_h[j]
-            self.out_keys[a:a + c].copy_(ok[a:a + c], non_blocking=True)
-            self.out_vals[a:a + c].copy_(ov[a:a + c], non_blocking=True)
-            d2h += c * (ok.element_size() + ov.element_size())
-            res.append((rx.part_first + j, self.out_keys[a:a + c], self.out_vals[a:a + c]))
+            self.out_keys[at:at + c].copy_(ok[a:a + c], non_blocking=True)
+            self.out_vals[at:at + c].copy_(ov[a:a + c], non_blocking=True)
+            res.append((rx.part_first + j, self.out_keys[at:at + c], self.out_vals[at:at + c]))
+            at += c
         torch.cuda.current_stream().synchronize()
-        self.d2h_bytes = d2h
+        self.d2h_bytes = nout * (ok.element_size() + ov.element_size())
         return res
 
 
 class HostShuffleStream(object):
-    """Streaming form of HostShuffle for back-to-back batches on one GPU: `depth` batches are in
-    flight on their own CUDA streams, so the host->device copy of batch i+1 runs while batch i is
-    reduced and its result is copied back (PCIe is full duplex, the copy engines are separate).
+    """Streaming shuffle for back-to-back batches of HOST-resident columns: `depth` batches are in flight on their
+    own CUDA streams, so the host->device copy of batch i+1 runs while batch i is reduced and its result is copied
+    back (PCIe is full duplex, the copy engines are separate).  Works on one GPU and, under torch.distributed, on
+    every rank of the job at once (each slot then owns its PeerExchange: symmetric receive buffers + barrier state,
+    so batches in flight never share a receive buffer; all ranks must submit/collect in the same order).
 
-        s = HostShuffleStream(n, torch.int64, torch.int64, P)
-        s.submit(h_keys, h_vals)            # pinned host columns; returns immediately
+        s = HostShuffleStream(n, torch.int64, torch.int64, P)        # kind="group": groupByKey (CSR result)
+        s.submit(h_keys, h_vals)            # pinned host columns of THIS rank; returns immediately
         s.submit(h_keys2, h_vals2)
-        parts = s.collect()                 # result of the OLDEST batch: [(partition, keys, vals)] pinned host
+        parts = s.collect()                 # result of the OLDEST batch for the partitions this rank owns
 
-    The tensors collect() returns are views of the slot's pinned output buffers: they stay valid until
-    that slot is collected again, i.e. for the next `depth - 1` collect() calls; copy what must live longer.
+    reduce: [(partition, keys, combined values)]; group: [(partition, group keys, group starts, values)] with the
+    values of group g at values[starts[g]:starts[g+1]] in (map split, position) order.  All pinned-host views of the
+    slot's output buffers: valid until that slot is collected again (`depth - 1` further collect() calls).
     """
 
     class _Slot(object):
         pass
 
     def __init__(self, n_rows, key_dtype, val_dtype, P, op="sum", splits=8, thresholds=None, device=None,
-                 sub_bits=None, depth=2):
-        self.P, self.op, self.splits, self.thresholds = P, op, splits, thresholds
+                 sub_bits=None, depth=2, kind="reduce", peer_mode="push", recv_factor=1.25, group=None):
+        if kind not in ("reduce", "group"):
+            raise ValueError("kind must be 'reduce' or 'group'")
+        self.P, self.op, self.splits, self.thresholds, self.kind, self.group = P, op, splits, thresholds, kind, group
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         self.n = n_rows
-        self.sub_bits = choose_sub_bits(n_rows, P) if sub_bits is None else sub_bits
+        self.world = _world(group)
+        self.sub_bits = choose_sub_bits(n_rows, P, self.world) if sub_bits is None else sub_bits
+        cap = n_rows if self.world == 1 else int(n_rows * recv_factor) + (1 << 16)
+        self.capacity = cap
+        ksz = torch.empty(0, dtype=key_dtype).element_size()
+        vsz = torch.empty(0, dtype=val_dtype).element_size()
+        out_vdt = nv.acc_dtype(val_dtype) if kind == "reduce" else val_dtype
         self.slots = []
         for _ in range(depth):
             s = self._Slot()
             s.stream = torch.cuda.Stream(device=self.device)
             s.d_keys = torch.empty(n_rows, dtype=key_dtype, device=self.device)
             s.d_vals = torch.empty(n_rows, dtype=val_dtype, device=self.device)
-            s.out_keys = torch.empty(n_rows, dtype=key_dtype).pin_memory()
-            s.out_vals = torch.empty(n_rows, dtype=nv.acc_dtype(val_dtype)).pin_memory()
+            s.out_keys = torch.empty(cap, dtype=key_dtype if kind == "reduce" else torch.int64).pin_memory()
+            s.out_vals = torch.empty(cap, dtype=out_vdt).pin_memory()
+            s.out_starts = torch.empty(cap + 1, dtype=torch.int64).pin_memory() if kind == "group" else None
+            s.px = None
+            if self.world > 1 and peer_mode is not None:
+                from . import peer
+                s.px = peer.PeerExchange(cap, key_dtype, val_dtype, self.device, group=group, mode="push")
             s.busy = False
             self.slots.append(s)
         self.next_submit = 0
         self.next_collect = 0
-        self.h2d_bytes = n_rows * (torch.empty(0, dtype=key_dtype).element_size() +
-                                   torch.empty(0, dtype=val_dtype).element_size())
+        self.h2d_bytes = n_rows * (ksz + vsz)
         self.d2h_bytes = 0
 
     def submit(self, h_keys, h_vals):
@@ -311,9 +393,16 @@ class HostShuffleStream(object):
                 s.d_vals[a:b].copy_(h_vals[a:b], non_blocking=True)
                 kc.append(s.d_keys[a:b])
                 vc.append(s.d_vals[a:b])
-            mo = map_side(kc, vc, self.P, self.thresholds, False, self.sub_bits, unordered=True)
-            rx = exchange(mo)
-            s.result = reduce_side(rx, self.op, self.P, self.thresholds)
+            mo = map_side(kc, vc, self.P, self.thresholds, False, self.sub_bits, unordered=self.kind == "reduce")
+            if s.px is not None:
+                from . import peer
+                rx = peer.exchange_push(s.px, mo, need_host_count=self.kind == "group")
+            else:
+                rx = exchange(mo, self.group)
+            if self.kind == "reduce":
+                s.result = reduce_side(rx, self.op, self.P, self.thresholds)
+            else:
+                s.result = group_side(rx, self.P, self.thresholds)
             s.nparts, s.part_first = rx.nparts, rx.part_first
         s.busy = True
 
@@ -322,21 +411,54 @@ class HostShuffleStream(object):
         if not s.busy:
             raise RuntimeError("nothing in flight")
         self.next_collect += 1
-        ok, ov, po, cnt = s.result
         with torch.cuda.stream(s.stream):
-            po_h, cnt_h = po.cpu().tolist(), cnt.cpu().tolist()      # waits for THIS batch only
-            res, d2h = [], 0
-            for j in range(s.nparts):
-                a, c = po_h[j], cnt_h[j]
-                s.out_keys[a:a + c].copy_(ok[a:a + c], non_blocking=True)
-                s.out_vals[a:a + c].copy_(ov[a:a + c], non_blocking=True)
-                d2h += c * (ok.element_size() + ov.element_size())
-                res.append((s.part_first + j, s.out_keys[a:a + c], s.out_vals[a:a + c]))
+            res = self._collect_reduce(s) if self.kind == "reduce" else self._collect_group(s)
             s.stream.synchronize()
+            if s.px is not None:
+                s.px.check()
         s.result = None
         s.busy = False
-        self.d2h_bytes = d2h
         return res
+
+    def _collect_reduce(self, s):
+        ok, ov, po, cnt = s.result
+        po_h, cnt_h = po.cpu().tolist(), cnt.cpu().tolist()      # waits for THIS batch only
+        check_counts(cnt_h)
+        res, at = [], 0
+        for j in range(s.nparts):
+            a, c = po_h[j], cnt_h[j]
+            s.out_keys[at:at + c].copy_(ok[a:a + c], non_blocking=True)
+            s.out_vals[at:at + c].copy_(ov[a:a + c], non_blocking=True)
+            res.append((s.part_first + j, s.out_keys[at:at + c], s.out_vals[at:at + c]))
+            at += c
+        self.d2h_bytes = at * (ok.element_size() + ov.element_size())
+        return res
+
+    def _collect_group(self, s):
+        gk, gs, ng, ov, off = s.result
+        G = int(ng.item())                                           # waits for THIS batch only
+        off_h = off.cpu().tolist()
+        nval = int(ov.numel())
+        s.out_keys[:G].copy_(gk[:G], non_blocking=True)
+        s.out_starts[:G + 1].copy_(gs[:G + 1], non_blocking=True)
+        s.out_vals[:nval].copy_(ov, non_blocking=True)
+        s.stream.synchronize()
+        starts = s.out_starts[:G + 1]
+        first = torch.searchsorted(starts[:-1].contiguous(), torch.tensor(off_h, dtype=torch.int64)).tolist() if G else \
+            [0] * len(off_h)
+        res = []
+        for j in range(s.nparts):
+            g0, g1 = first[j], first[j + 1]
+            res.append((s.part_first + j, s.out_keys[g0:g1], s.out_starts[g0:g1 + 1], s.out_vals))
+        self.d2h_bytes = G * 8 + (G + 1) * 8 + nval * ov.element_size()
+        return res
+
+    def close(self):
+        for s in self.slots:
+            if s.px is not None:
+                s.px.close()
+                s.px = None
+        self.slots = []
 
 
 def combine_map_output(mo, op, thresholds=None):
@@ -355,6 +477,7 @@ def combine_map_output(mo, op, thresholds=None):
     seg = (mo.offsets[1:] - mo.offsets[:-1]).unsqueeze(0)
     ok, ov, po, cnt = reduce_side(Received(mo.keys, mo.vals, seg, 0, P, sb), op, P, thresholds)
     po_h, cnt_h = po.cpu().tolist(), cnt.cpu().tolist()           # host read: sizes of the compacted columns
+    check_counts(cnt_h)
     keys = torch.cat([ok[a:a + c] for a, c in zip(po_h, cnt_h)])
     vals = torch.cat([ov[a:a + c] for a, c in zip(po_h, cnt_h)])
     return map_side([keys], [vals], P, thresholds, False, sb, unordered=True)
@@ -367,12 +490,13 @@ def reduce_by_key(key_chunks, val_chunks, P, op="sum", thresholds=None, group=No
     if sub_bits is None:
         import torch.distributed as dist
         G = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
-        sub_bits = choose_sub_bits(sum(int(k.numel()) for k in key_chunks) * G, P)
+        sub_bits = choose_sub_bits(sum(int(k.numel()) for k in key_chunks), P, G)
     mo = map_side(key_chunks, val_chunks, P, thresholds, False, sub_bits, unordered=True)
     if map_combine:
         mo = combine_map_output(mo, op, thresholds)
     rx = exchange(mo, group)
     ok, ov, po, cnt = reduce_side(rx, op, P, thresholds)
     po_h, cnt_h = po.cpu().tolist(), cnt.cpu().tolist()
+    check_counts(cnt_h)
     return [(rx.part_first + j, ok[po_h[j]:po_h[j] + cnt_h[j]], ov[po_h[j]:po_h[j] + cnt_h[j]])
             for j in range(rx.nparts)]

@@ -153,22 +153,56 @@ def _is_identity(f):
         return False
 
 
+_LIST_OPS_FORBIDDEN = ("POP_JUMP", "JUMP", "COMPARE_OP", "CONTAINS_OP", "IS_OP", "BINARY_SLICE", "BUILD_SLICE",
+                       "FOR_ITER", "GET_ITER", "BINARY_SUBSCR", "STORE_SUBSCR", "DELETE_SUBSCR", "MAKE_FUNCTION",
+                       "LOAD_GLOBAL", "LOAD_NAME", "LOAD_DEREF", "LOAD_CLOSURE", "IMPORT", "YIELD", "RAISE")
+
+
+def _straight_line_list_code(fn):
+    """The function's bytecode has no branch, comparison, slice, subscript, loop, nested function or reference to
+    anything outside its arguments, and touches no attribute but append/extend: whatever it does, it does the same
+    for lists of every length and content.  (A combiner like `c + [v] if len(c) < 5 else c` or a de-duplicating one
+    behaves like append on small probes; its bytecode gives it away.)"""
+    import dis
+    code = getattr(fn, "__code__", None) or getattr(getattr(fn, "__func__", None), "__code__", None)
+    if code is None:
+        return False
+    for ins in dis.get_instructions(code):
+        if any(ins.opname.startswith(bad) for bad in _LIST_OPS_FORBIDDEN):
+            return False
+        if ins.opname in ("LOAD_ATTR", "LOAD_METHOD") and ins.argval not in ("append", "extend"):
+            return False
+    return True
+
+
 def _builds_lists(create, merge_value, merge_combiners):
     """True for the list-collecting aggregator written by hand -- createCombiner(v) == [v], mergeValue appends,
-    mergeCombiners concatenates (e.g. dpark.bagel.DefaultListCombiner, or the usual
-    `combineByKey(lambda v: [v], lambda c, v: c + [v], lambda a, b: a + b)`): that is a groupByKey, whose GPU
-    path yields every key's values as a list in (map split, position) order -- the list these functions build
-    when they meet the rows in that order."""
-    a, b, c, d = object(), object(), object(), object()
+    mergeCombiners concatenates (e.g. the usual `combineByKey(lambda v: [v], lambda c, v: c + [v], lambda a, b: a + b)`):
+    that is a groupByKey, whose GPU path yields every key's values as a list in (map split, position) order -- the list
+    these functions build when they meet the rows in that order.
+
+    Sound by construction, not by sampling alone: all three functions must be straight-line code over their
+    arguments (_straight_line_list_code) AND behave as append/concatenate on probes of several sizes with repeated
+    elements.  Anything else (bounded lists, de-duplication, sorting ...) is NOT a group-by and falls through to the
+    NotImplementedError of the reduce-style recogniser."""
+    if not all(_straight_line_list_code(f) for f in (create, merge_value, merge_combiners)):
+        return False
+    a, b = object(), object()
     try:
         one = create(a)
         if type(one) is not list or len(one) != 1 or one[0] is not a:
             return False
-        two = merge_value([a], b)
-        if type(two) is not list or len(two) != 2 or two[0] is not a or two[1] is not b:
-            return False
-        four = merge_combiners([a, b], [c, d])
-        return type(four) is list and len(four) == 4 and all(x is y for x, y in zip(four, (a, b, c, d)))
+        for n in (1, 2, 7, 64, 200):
+            left = [a, b, a][:min(n, 3)] + [object() for _ in range(max(0, n - 3))]
+            v = left[0]                                   # a value already in the list (de-duplication would drop it)
+            got = merge_value(list(left), v)
+            if type(got) is not list or len(got) != n + 1 or any(x is not y for x, y in zip(got, left + [v])):
+                return False
+            right = list(reversed(left)) + [a]
+            both = merge_combiners(list(left), list(right))
+            if type(both) is not list or len(both) != 2 * n + 1 or any(x is not y for x, y in zip(both, left + right)):
+                return False
+        return True
     except Exception:
         return False
 
@@ -178,6 +212,9 @@ def recognize_aggregator(agg):
     (dpark/dependency.py:107-161), else NotImplementedError."""
     from .dependency import AddAggregator, GroupByAggregator, MergeAggregator
     if isinstance(agg, (GroupByAggregator, MergeAggregator)):
+        return "group", None
+    from . import bagel
+    if isinstance(agg, bagel.DefaultListCombiner):       # known list collector (dpark/bagel.py:40-49)
         return "group", None
     if isinstance(agg, AddAggregator):
         return "reduce", "sum"

@@ -50,7 +50,7 @@ def main():
         mine = [(p, k.cpu().numpy(), v.cpu().numpy()) for p, k, v in res]
         if px is not None:
             # fused scatter + exchange must deliver bit-identical receive buffers to the NCCL alltoallv
-            sb_eff = shuffle.choose_sub_bits(n * world, P) if sb is None else sb
+            sb_eff = shuffle.choose_sub_bits(n, P, world) if sb is None else sb
             kd = [torch.from_numpy(x).to(dev) for x in ks]
             vd = [torch.from_numpy(x).to(dev) for x in vs]
             rx_nccl = shuffle.exchange(shuffle.map_side(kd, vd, P, None, False, sb_eff))
@@ -58,7 +58,7 @@ def main():
             same = (torch.equal(rx_nccl.keys, rx_peer.keys) and torch.equal(rx_nccl.vals, rx_peer.vals)
                     and torch.equal(rx_nccl.seg, rx_peer.seg) and rx_nccl.part_first == rx_peer.part_first)
             # ... and so must the block push (local scatter + dpk_copy_segments)
-            rx_push = peer.exchange_push(px, shuffle.map_side(kd, vd, P, None, False, sb_eff))
+            rx_push = peer.exchange_push(px, shuffle.map_side(kd, vd, P, None, False, sb_eff), need_host_count=True)
             same = (same and torch.equal(rx_nccl.keys, rx_push.keys) and torch.equal(rx_nccl.vals, rx_push.vals)
                     and torch.equal(rx_nccl.seg, rx_push.seg) and rx_nccl.nparts == rx_push.nparts)
             flags = [None] * world
@@ -105,7 +105,7 @@ def main():
                 fg = np.searchsorted(gstarts[:-1], poff, side="left")
                 for p in range(first, first + nparts):
                     wk, wo, wv = wantg[p]
-                    g0, g1 = fg[p], fg[p + 1]
+                    g0, g1 = fg[p - first], fg[p - first + 1]    # poff: offsets of the rank's own partitions
                     got = {int(gkeys[g]): vals[gstarts[g]:gstarts[g + 1]] for g in range(g0, g1)}
                     good = len(got) == len(wk)
                     for i, key in enumerate(wk.tolist()):

@@ -312,7 +312,8 @@ def test_sample_rdd_draws_like_the_reference():
 
 def test_bench_reference_arm_prints_one_contract_line():
     """`bench.py --impl reference` (the CPU arm the driver runs next to ours): exactly one JSON line on stdout
-    with the contract's keys, measured on the oracle's CPython port (bounded sample so this stays quick)."""
+    with the contract's keys, measured on the UNMODIFIED reference when baseline/_ref was built (oracle/build_reference.py)
+    and on the oracle's CPython port otherwise (bounded sample so this stays quick)."""
     import json
     import subprocess
     import sys
@@ -327,7 +328,33 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert b["impl"] == "reference" and b["unit"] == "rows/s" and b["higher_is_better"] is True
     assert b["metric"] == "shuffled rows/sec (reduceByKey end-to-end)"
     assert b["value"] > 0 and b["n_gpus"] == 1 and b["scaling"] == "weak" and b["dtype"] == "int64"
-    assert b["cpu_baseline"]["kind"] == "port" and b["cpu_baseline"]["cores"] >= 1
+    assert b["cpu_baseline"]["kind"] in ("reference", "port") and b["cpu_baseline"]["cores"] >= 1
+    if b["cpu_baseline"]["kind"] == "reference":     # the reference's own compiled extension was loaded, nothing of ours
+        assert any("baseline/_ref/dpark/portable_hash" in x for x in b["cpu_baseline"]["native_so_loaded"])
     assert b["cpu_baseline"]["value"] == b["value"]
     assert b["e2e"] == {"value": b["value"], "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in b["config"]
+
+
+def test_only_straight_line_list_collectors_are_recognised_as_group_by():
+    """an aggregator that merely LOOKS like append/concat on small probes (bounded lists, de-duplication)
+    must not be run as an unbounded groupByKey; only straight-line collectors and the known classes are."""
+    from dpark_b200 import bagel, trace
+    from dpark_b200.dependency import Aggregator
+
+    def mv(c, v):
+        c.append(v)
+        return c
+
+    def mc(a, b):
+        a.extend(b)
+        return a
+    assert trace.recognize_aggregator(Aggregator(lambda v: [v], lambda c, v: c + [v], lambda a, b: a + b)) == ("group", None)
+    assert trace.recognize_aggregator(Aggregator(lambda v: [v], mv, mc)) == ("group", None)
+    assert trace.recognize_aggregator(bagel.DefaultListCombiner()) == ("group", None)
+    bounded = Aggregator(lambda v: [v], lambda c, v: c + [v] if len(c) < 5 else c, lambda a, b: (a + b)[:5])
+    dedup = Aggregator(lambda v: [v], lambda c, v: c if v in c else c + [v], lambda a, b: a + [x for x in b if x not in a])
+    srt = Aggregator(lambda v: [v], lambda c, v: sorted(c + [v]), lambda a, b: sorted(a + b))
+    for agg in (bounded, dedup, srt):
+        with pytest.raises(NotImplementedError):
+            trace.recognize_aggregator(agg)
