@@ -78,7 +78,10 @@ def parse():
     ap.add_argument("--scatter-threads", type=int, default=0, help="A/B: CTA size of the bulk multisplit (256|512)")
     ap.add_argument("--agg-ctas", type=int, default=0, help="A/B: resident CTAs per SM the merge kernel is compiled for (3|4)")
     ap.add_argument("--agg-cursor", type=int, default=-1, help="A/B: merge kernel output ranges by atomic cursor (1) or chained look-back (0)")
+    ap.add_argument("--agg-batched", type=int, default=-1, help="A/B: four rows in flight per thread in the merge kernel's insert phase")
     ap.add_argument("--agg-impl", type=int, default=-1, help="A/B: reduce-side merge kernel (0 = round 1, 1 = row-index tags)")
+    ap.add_argument("--overlap-push", type=int, default=1, help="N>1, push exchange: groups of map splits whose push "
+                    "overlaps the scatter of the next group (1 = no overlap)")
     ap.add_argument("--exchange", default="push", choices=["push", "fused", "peer", "nccl"],
                     help="N>1: push = local scatter, then one kernel pushing each peer's block over NVLink; "
                          "fused (alias peer) = the scatter kernel stores into peer memory; nccl = alltoallv")
@@ -102,6 +105,7 @@ def workload_config(args, world):
         "config": args.config, "rows_per_gpu": args.rows_per_gpu, "partitions": args.parts_per_gpu * world,
         "map_splits_per_gpu": args.map_splits, "parallelism": "dp%d" % world,
         "exchange": None if world == 1 else args.exchange, "map_combine": bool(args.map_combine),
+        "overlap_push_groups": args.overlap_push if world > 1 else None,
         "l2_policy": "inputs_larger_than_l2 (%.1f GB of rows per GPU per step vs 126 MB L2)"
                      % (args.rows_per_gpu * (_isz(cfg["kdt"]) + _isz(cfg["vdt"])) / 1e9),
         "sub_buckets_per_partition": 1 << shuffle.choose_sub_bits(args.rows_per_gpu, args.parts_per_gpu * world, world),
@@ -506,6 +510,8 @@ def run_ours(args):
         nv.set_option("agg_ctas", args.agg_ctas)
     if args.agg_cursor >= 0:
         nv.set_option("agg_cursor", args.agg_cursor)
+    if args.agg_batched >= 0:
+        nv.set_option("agg_batched", args.agg_batched)
 
     ex_events = []
     px = None
@@ -524,6 +530,9 @@ def run_ours(args):
     def step():
         if px is not None and px.mode == "fused" and not group and not args.map_combine:
             rx = peer.map_side_push(px, kc, vc, P, None, sub_bits)
+            return shuffle.reduce_side(rx, "sum", P)
+        if px is not None and px.mode == "push" and args.overlap_push > 1 and not group and not args.map_combine:
+            rx = peer.map_exchange_overlapped(px, kc, vc, P, None, sub_bits, True, args.overlap_push)
             return shuffle.reduce_side(rx, "sum", P)
         mo = shuffle.map_side(kc, vc, P, None, False, sub_bits, unordered=not group)
         if args.map_combine and not group:

@@ -101,6 +101,26 @@ class DparkContext(object):
             self.defaultParallelism = 2 if self.master == "local" else (os.cpu_count() or 2)
         self.defaultMinSplits = max(self.defaultParallelism, 2)
         self.initialized = True
+        self._join_process_group()
+
+    @staticmethod
+    def _join_process_group():
+        """Launched under torchrun (WORLD_SIZE > 1): one driver process per GPU, all running this script
+        (dpark_b200/spmd.py).  The process group is created here so that user scripts stay unchanged."""
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        if world <= 1:
+            return
+        import torch
+        import torch.distributed as dist
+        if dist.is_available() and not dist.is_initialized():
+            local = int(os.environ.get("LOCAL_RANK", "0"))
+            if torch.cuda.is_available():
+                from . import shuffle
+                shuffle.bind_to_gpu_numa_node(local)
+                torch.cuda.set_device(local)
+                dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            else:
+                dist.init_process_group("gloo")
 
     @staticmethod
     def setLogLevel(level):
@@ -173,8 +193,24 @@ class DparkContext(object):
         splits = rdd.splits
         if partitions is None:
             partitions = range(len(splits))
+        from . import spmd
+        rank, world = spmd.rank_world()
+        if world == 1:
+            for i in partitions:
+                yield func(rdd.iterator(splits[i]))
+            return
+        # one driver process per GPU, all running this script (dpark_b200/spmd.py): every rank joins the lineage's
+        # shuffles, computes the partitions it owns, and the per-partition results are shared with all ranks
+        partitions = list(partitions)
+        spmd.materialize_lineage(rdd)
+        n = len(splits)
+        mine = [(i, func(rdd.iterator(splits[i]))) for i in partitions if spmd.owner_of(i, n, world) == rank]
+        results = {}
+        for part in spmd.all_gather_objects(mine):
+            results.update(part)
+        spmd.sync_accumulators()
         for i in partitions:
-            yield func(rdd.iterator(splits[i]))
+            yield results[i]
 
     def start(self):
         self.init()

@@ -447,6 +447,7 @@ constexpr int AG_MAX_SB2 = 10;       // at most 1024 fine buckets per first-leve
 int g_agg_wide = 1;
 int g_agg_ctas = 3;
 int g_agg_cursor = 1;
+int g_agg_batched = 1;
 int g_agg_impl = 1;                  // dpk_set_option("agg_impl"): 1 = k_smem_aggregate2 (row-index tags), 0 = round-1 kernel
 int g_agg_target_rows = 2048;        // rows per fine bucket the split aims for (table load <= 0.5)
 
@@ -506,8 +507,11 @@ static int dispatch_op(const Ctx &c) {
         if (g_agg_impl == 1) {
             // dpk_set_option("agg_ctas"): resident CTAs per SM the kernel is compiled for (3: 80 registers, 4: 64)
             // dpk_set_option("agg_cursor"): 1 = output ranges reserved with one atomicAdd per fine bucket, 0 = chained look-back
-            auto agg2 = g_agg_cursor ? (g_agg_ctas == 4 ? k_smem_aggregate2<KeyT, ValT, AccT, 4, true> : k_smem_aggregate2<KeyT, ValT, AccT, 3, true>)
-                                     : (g_agg_ctas == 4 ? k_smem_aggregate2<KeyT, ValT, AccT, 4, false> : k_smem_aggregate2<KeyT, ValT, AccT, 3, false>);
+            // dpk_set_option("agg_batched"): 1 = four rows per thread in flight in the insert phase (default), 0 = probe loop per row
+            auto agg2 = k_smem_aggregate2<KeyT, ValT, AccT, 3, true, true>;
+            if (g_agg_cursor && g_agg_batched) agg2 = g_agg_ctas == 4 ? k_smem_aggregate2<KeyT, ValT, AccT, 4, true, true> : k_smem_aggregate2<KeyT, ValT, AccT, 3, true, true>;
+            else if (g_agg_cursor) agg2 = g_agg_ctas == 4 ? k_smem_aggregate2<KeyT, ValT, AccT, 4, true, false> : k_smem_aggregate2<KeyT, ValT, AccT, 3, true, false>;
+            else agg2 = k_smem_aggregate2<KeyT, ValT, AccT, 3, false, false>;
             const int smem2 = AG2_TAGS * 4 + AG2_CAP * 16;
             DPK_CUDA_TRY(cudaFuncSetAttribute(agg2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
             DPK_CUDA_TRY(cudaMemsetAsync(c.part_err, 0, (size_t)c.nparts * 4, c.st));
@@ -609,6 +613,11 @@ int dpk_set_option(const char *name, int64_t value) {
     if (strcmp(name, "agg_impl") == 0) {
         if (value != 0 && value != 1) return fail(DPK_ERR_INVALID, "agg_impl must be 0 or 1");
         g_agg_impl = (int)value;
+        return DPK_OK;
+    }
+    if (strcmp(name, "agg_batched") == 0) {
+        if (value != 0 && value != 1) return fail(DPK_ERR_INVALID, "agg_batched must be 0 or 1");
+        g_agg_batched = (int)value;
         return DPK_OK;
     }
     if (strcmp(name, "agg_cursor") == 0) {

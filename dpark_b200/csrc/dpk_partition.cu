@@ -482,7 +482,24 @@ __device__ __forceinline__ void flush_run(T *__restrict__ out, int64_t g, const 
     for (int i = head + mid; i < cnt; i++) dst[i] = s_col[s0 + i];
 }
 
-template <typename KeyT, typename ValT, int PRE, int NT>
+// bucket function specialised at compile time for the configurations the hot paths use (the generic PartFn::bucket
+// walks a chain of uniform branches per row; the kernel is issue-bound):
+//   FMODE 1: P a power of two (or 1), any sub_bits: (h & (P-1)) << sub_bits | top sub_bits bits of mixed(h)
+//   FMODE 2: second-level split (PartFn mode 5): bits of mixed(h) below the first-level ones
+//   FMODE 0: anything else (thresholds, magic divide, radix digits)
+template <int FMODE>
+__device__ __forceinline__ int bucket_of(const PartFn &f, int64_t h) {
+    if constexpr (FMODE == 1) {
+        const uint32_t sub = (uint32_t)(((uint64_t)PartFn::mixed(h) << f.sub_bits) >> 32);   // top sub_bits bits (0 when sub_bits == 0)
+        return (int)((((uint32_t)h & (uint32_t)(f.P - 1)) << f.sub_bits) | sub);
+    } else if constexpr (FMODE == 2) {
+        return (int)((PartFn::mixed(h) >> f.shift) & (uint32_t)(f.P - 1));
+    } else {
+        return f.bucket(h);
+    }
+}
+
+template <typename KeyT, typename ValT, int PRE, int NT, int FMODE>
 __global__ void __launch_bounds__(NT, 2)
 k_part_scatter_bulk(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, int64_t n, int64_t L,
                     PartFn f, const int32_t *__restrict__ tile_off, int32_t T,
@@ -522,22 +539,26 @@ k_part_scatter_bulk(const KeyT *__restrict__ keys, const ValT *__restrict__ vals
 
     KeyT k[ITEMS];
     ValT v[ITEMS];
+    // rows of the tile this thread holds: row j of warp w's lane l = tile + w * 32 * ITEMS + j * 32 + l
     auto load_tile = [&](int64_t tile) {
-        const int64_t wbase = tile + (int64_t)warp * (32 * ITEMS) + lane;
+        const KeyT *kp = keys + tile + warp * (32 * ITEMS) + lane;
         if (tile + TILE <= end) {
 #pragma unroll
-            for (int j = 0; j < ITEMS; j++) k[j] = keys[wbase + j * 32];
+            for (int j = 0; j < ITEMS; j++) k[j] = kp[j * 32];
             if constexpr (HAS_VAL) {
+                const ValT *vp = vals + tile + warp * (32 * ITEMS) + lane;
 #pragma unroll
-                for (int j = 0; j < ITEMS; j++) v[j] = vals[wbase + j * 32];
+                for (int j = 0; j < ITEMS; j++) v[j] = vp[j * 32];
             }
         } else {
+            const int left = (int)(end - tile) - warp * (32 * ITEMS) - lane;   // rows from this thread's first row to the end
 #pragma unroll
-            for (int j = 0; j < ITEMS; j++) k[j] = (wbase + j * 32) < end ? keys[wbase + j * 32] : KeyT(0);
+            for (int j = 0; j < ITEMS; j++) k[j] = j * 32 < left ? kp[j * 32] : KeyT(0);
             if constexpr (HAS_VAL) {
+                const ValT *vp = vals + tile + warp * (32 * ITEMS) + lane;
 #pragma unroll
                 for (int j = 0; j < ITEMS; j++)
-                    if ((wbase + j * 32) < end) v[j] = vals[wbase + j * 32];
+                    if (j * 32 < left) v[j] = vp[j * 32];
             }
         }
     };
@@ -547,17 +568,23 @@ k_part_scatter_bulk(const KeyT *__restrict__ keys, const ValT *__restrict__ vals
     int par = 0;
     for (int64_t tile = beg; tile < end; tile += TILE, par ^= 1) {
         uint32_t *cnt = s_cnt + par * P;
-        const int64_t wbase = tile + (int64_t)warp * (32 * ITEMS) + lane;
-        const bool full = tile + TILE <= end;
         // ---- rank: one shared-memory atomic per row on the tile's bucket counter
         uint32_t pr[ITEMS];  // bucket << 16 | rank inside the tile (both < 2^16: P <= 4096, TILE = 4096)
+        if (tile + TILE <= end) {   // full tile: no bounds predicates
 #pragma unroll
-        for (int j = 0; j < ITEMS; j++) {
-            const bool ok = full || (wbase + j * 32) < end;
-            pr[j] = 0xffffffffu;
-            if (ok) {
-                const int p = f.bucket(key_hash<KeyT, PRE>(k[j], f));
+            for (int j = 0; j < ITEMS; j++) {
+                const int p = bucket_of<FMODE>(f, key_hash<KeyT, PRE>(k[j], f));
                 pr[j] = ((uint32_t)p << 16) | atomicAdd(&cnt[p], 1u);
+            }
+        } else {
+            const int left = (int)(end - tile) - warp * (32 * ITEMS) - lane;
+#pragma unroll
+            for (int j = 0; j < ITEMS; j++) {
+                pr[j] = 0xffffffffu;
+                if (j * 32 < left) {
+                    const int p = bucket_of<FMODE>(f, key_hash<KeyT, PRE>(k[j], f));
+                    pr[j] = ((uint32_t)p << 16) | atomicAdd(&cnt[p], 1u);
+                }
             }
         }
         // the previous tile's bulk stores must have read the staging tile before it is overwritten
@@ -587,11 +614,11 @@ k_part_scatter_bulk(const KeyT *__restrict__ keys, const ValT *__restrict__ vals
         }
         __syncthreads();  // (B)
 
-        // ---- placement
+        // ---- placement (rows past the end carry bucket 0xffff)
 #pragma unroll
         for (int j = 0; j < ITEMS; j++) {
-            if (pr[j] != 0xffffffffu) {
-                const int p = (int)(pr[j] >> 16), r = (int)(pr[j] & 0xffffu);
+            const int p = (int)(pr[j] >> 16), r = (int)(pr[j] & 0xffffu);
+            if (p != 0xffff) {
                 s_key[s_sk[p] + r] = k[j];
                 if constexpr (HAS_VAL) s_val[s_sv[p] + r] = v[j];
             }
@@ -668,7 +695,10 @@ static int launch_scatter_bulk(const void *keys, const void *vals, int64_t n, co
     BulkSmem lay = bulk_smem((int)sizeof(KeyT), vb, f.nbuckets(), PT_TILE);
     // dpk_set_option("scatter_threads"): 512 (default; 8 rows per thread, 32 warps per SM) or 256 (16 rows per thread)
     const int nt = g_scatter_threads;
-    auto kern = nt == 512 ? k_part_scatter_bulk<KeyT, ValT, PRE, 512> : k_part_scatter_bulk<KeyT, ValT, PRE, 256>;
+    const int fmode = f.mode == 5 ? 2 : ((f.mode == 0 || f.mode == 1) ? 1 : 0);
+    auto kern = nt == 512 ? (fmode == 2 ? k_part_scatter_bulk<KeyT, ValT, PRE, 512, 2> :
+                             fmode == 1 ? k_part_scatter_bulk<KeyT, ValT, PRE, 512, 1> : k_part_scatter_bulk<KeyT, ValT, PRE, 512, 0>)
+                          : k_part_scatter_bulk<KeyT, ValT, PRE, 256, 0>;
     DPK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
     DPK_LAUNCH(pl.label_scatter ? pl.label_scatter : (pl.seg.cbeg ? "seg_scatter" : "part_scatter"), st,
                kern<<<pl.T, nt, (size_t)lay.total, st>>>((const KeyT *)keys, (const ValT *)vals, n, pl.L, f,

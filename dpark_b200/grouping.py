@@ -43,9 +43,9 @@ def _emit(res, P, part_off, gkeys, gstarts, ids, objs, key_decoder):
 
 
 def group_by_key(splits, P, thresholds, dev, res):
-    import torch.distributed as dist
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        raise NotImplementedError("the RDD surface drives one GPU; use dpark_b200.shuffle for multi-GPU runs")
+    if shuffle._world() > 1:
+        raise NotImplementedError("this is the one-GPU stage; under torch.distributed the rows are first routed to the "
+                                  "rank owning their partition (dpark_b200.engine._routed_shuffle)")
     objs, sizes = _concat_objs(splits)
     n = len(objs)
     kinds = set(c.key_kind for c in splits if c.n)

@@ -60,6 +60,7 @@ class PeerExchange(object):
             self._kb.append(torch.tensor([int(p) for p in hk.buffer_ptrs], dtype=torch.int64, device=self.device))
             self._vb.append(torch.tensor([int(p) for p in hv.buffer_ptrs], dtype=torch.int64, device=self.device))
         self.step = 0
+        self.side = torch.cuda.Stream(device=self.device, priority=-1)     # pushes that overlap the map side
         self.err = torch.zeros(1, dtype=torch.int64, device=self.device)   # max rows any rank needed beyond capacity
         self._closed = False
 
@@ -165,6 +166,75 @@ def exchange_push(px, mo, need_host_count=False):
         nrecv = min(int(recv_total[rank].item()), px.capacity)
         return Received(keys[:nrecv], None if vals is None else vals[:nrecv], seg, b0 >> sb, (b1 - b0) >> sb, sb)
     return Received(keys, vals, seg, b0 >> sb, (b1 - b0) >> sb, sb, bound=True)
+
+
+def map_exchange_overlapped(px, key_chunks, val_chunks, P, thresholds=None, sub_bits=0, unordered=True, halves=2):
+    """Map side + exchange with the push of the first half of the map splits running (on a side stream) while the
+    second half is still being scattered.  The rank's splits are divided into `halves` contiguous groups, every
+    group gets its own bucket-major buffer, and a group's blocks are pushed as soon as its scatter kernels are
+    done; all counts are known after the histogram pass, so ONE all-gather describes every group.  In a receive
+    buffer the groups of one source rank follow each other in split order, i.e. the layout is still
+    (map split order)-major then bucket-major: `Received.seg` simply has G * halves source rows.
+    Returns the Received view (bound = the whole receive buffer) like exchange_push."""
+    from . import shuffle as sh
+    G, rank, dev = px.world, px.rank, px.device
+    F = P << sub_bits
+    M = len(key_chunks)
+    H = max(1, min(halves, M))
+    counts, wss = [], []
+    for k in key_chunks:
+        c, ws = nv.partition_count(k, P, thresholds, False, sub_bits, None, None, unordered)
+        counts.append(c)
+        wss.append(ws)
+    cm = torch.stack(counts)                                            # [M, F]
+    bounds = [(M * h) // H for h in range(H + 1)]
+    gc = torch.stack([cm[bounds[h]:bounds[h + 1]].sum(0) for h in range(H)])    # [H, F] rows per group and bucket
+    all_counts = torch.empty(G * H * F, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(all_counts, gc.reshape(-1).contiguous(), group=px.group)   # the MapOutputTracker
+    all_counts = all_counts.view(G * H, F)                              # source (rank, group) major
+    blocks = [b << sub_bits for b in owner_blocks(P, G)]
+    has_v = val_chunks[0] is not None
+    main = torch.cuda.current_stream()
+    b0, b1 = blocks[rank], blocks[rank + 1]
+    need = None
+    for h in range(H):
+        src_row = rank * H + h
+        send_first, dst_first, rows, recv_total = push_plan(all_counts, blocks, src_row)
+        if need is None:
+            need = recv_total.max()
+            px.note_need(need)
+        rows = torch.minimum(rows, (px.capacity - dst_first).clamp_(min=0))
+        # this group's bucket-major buffer
+        sel = slice(bounds[h], bounds[h + 1])
+        n_h = sum(int(k.numel()) for k in key_chunks[sel])
+        offsets = torch.zeros(F + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(gc[h], 0, out=offsets[1:])
+        base = offsets[:-1].unsqueeze(0) + (torch.cumsum(cm[sel], 0) - cm[sel])
+        out_k = torch.empty(n_h, dtype=key_chunks[0].dtype, device=dev)
+        out_v = torch.empty(n_h, dtype=val_chunks[0].dtype, device=dev) if has_v else None
+        for i, m in enumerate(range(bounds[h], bounds[h + 1])):
+            nv.partition_scatter(key_chunks[m], val_chunks[m], P, base[i].contiguous(), out_k, out_v, wss[m], thresholds,
+                                 False, sub_bits, None, unordered)
+        cols = [(out_k.data_ptr(), px.key_base, out_k.element_size())]
+        if has_v:
+            cols.append((out_v.data_ptr(), px.val_base, out_v.element_size()))
+        src = torch.cat([a + send_first * sz for a, _, sz in cols]).contiguous()
+        dst = torch.cat([bb + dst_first * sz for _, bb, sz in cols]).contiguous()
+        nby = torch.cat([rows * sz for _, _, sz in cols]).contiguous()
+        ready = torch.cuda.Event()
+        ready.record(main)
+        with torch.cuda.stream(px.side):
+            px.side.wait_event(ready)
+            nv.copy_segments(src, dst, nby)
+            for t in (out_k, out_v, src, dst, nby):
+                if t is not None:
+                    t.record_stream(px.side)
+    main.wait_stream(px.side)
+    px.barrier()                                                        # every peer's stores have landed
+    seg = all_counts[:, b0:b1].contiguous()
+    keys, vals = px.keys, (px.vals if has_v else None)
+    px.advance()
+    return Received(keys, vals, seg, b0 >> sub_bits, (b1 - b0) >> sub_bits, sub_bits, bound=True)
 
 
 def map_side_push(px, key_chunks, val_chunks, P, thresholds=None, sub_bits=0, unordered=True):

@@ -56,6 +56,11 @@ class RDD(object):
     def compute(self, split):
         raise NotImplementedError
 
+    def parents(self):
+        """RDDs this one reads (the lineage walk of dpark_b200.spmd: under torch.distributed every rank must enter a
+        shuffle's collectives, also a rank that owns none of the partitions being computed)."""
+        return []
+
     def iterator(self, split):
         if self.should_cache:
             if self._cache is None:
@@ -439,6 +444,9 @@ class DerivedRDD(RDD):
         self.prev = prev
         self._splits = prev.splits
 
+    def parents(self):
+        return [self.prev]
+
     @property
     def splits(self):
         return self.prev.splits
@@ -738,6 +746,20 @@ class CoGroupedRDD(RDD):
         return iter(merged.items())
 
 
+def _parents_of_union(self):
+    return list(self.rdds)
+
+
+UnionRDD.parents = _parents_of_union
+
+
+def _parents_of_cogroup(self):
+    return ([self._grouped] if self._grouped is not None else []) + [self.rdds[i] for i in self.narrow]
+
+
+CoGroupedRDD.parents = _parents_of_cogroup
+
+
 class ShuffledRDD(RDD):
     """dpark/rdd.py:1101-1134.  The plan node is built eagerly (aggregator is
     recognised at construction, so unsupported combiners fail when the job is
@@ -764,6 +786,9 @@ class ShuffledRDD(RDD):
         if self.kind == "group":
             self.rddconf.op = conf.OP_GROUPBY
         self._result = None
+
+    def parents(self):
+        return [self.parent]
 
     def _materialize(self):
         if self._result is None:

@@ -145,12 +145,26 @@ class Received(object):
         self.bound = bound
 
 
+_LOCAL_ONLY = [0]
+
+
+class local_only(object):
+    """`with shuffle.local_only():` -- the shuffles inside run on THIS rank's rows alone even under torch.distributed
+    (the owner-side stage of dpark_b200.engine._routed_shuffle: the rows were already brought to their owner)."""
+
+    def __enter__(self):
+        _LOCAL_ONLY[0] += 1
+
+    def __exit__(self, *a):
+        _LOCAL_ONLY[0] -= 1
+
+
 def exchange(mo, group=None):
     """ShuffleFetcher replacement: one alltoallv of the bucket-major buffers
     (torch.distributed all_to_all_single with split sizes == grouped
     ncclSend/ncclRecv over NVLink).  With one rank it is the identity."""
     import torch.distributed as dist
-    G = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    G = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized() and not _LOCAL_ONLY[0]) else 1
     P, sb = mo.P, mo.sub_bits
     if G == 1:
         seg = (mo.offsets[1:] - mo.offsets[:-1]).unsqueeze(0)
@@ -246,7 +260,7 @@ def group_side(rx, P, thresholds=None, key_view=None, row_hash=None):
 
 def _world(group=None):
     import torch.distributed as dist
-    return dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    return dist.get_world_size(group) if (dist.is_available() and dist.is_initialized() and not _LOCAL_ONLY[0]) else 1
 
 
 def check_counts(cnt_h):
@@ -488,9 +502,9 @@ def reduce_by_key(key_chunks, val_chunks, P, op="sum", thresholds=None, group=No
     """Whole hot path for this rank's map splits.  Returns a list of
     (partition id, keys, vals) for the partitions this rank owns (device tensors)."""
     if sub_bits is None:
-        import torch.distributed as dist
-        G = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
-        sub_bits = choose_sub_bits(sum(int(k.numel()) for k in key_chunks), P, G)
+        # NOTE under torch.distributed every rank must pass the SAME sub_bits (the bucket layout is exchanged);
+        # callers with uneven inputs agree on it first (dpark_b200.engine._device_reduce)
+        sub_bits = choose_sub_bits(sum(int(k.numel()) for k in key_chunks), P, _world(group))
     mo = map_side(key_chunks, val_chunks, P, thresholds, False, sub_bits, unordered=True)
     if map_combine:
         mo = combine_map_output(mo, op, thresholds)

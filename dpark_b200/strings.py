@@ -15,8 +15,8 @@ Columnar form of the keys: one uint8 buffer + int64 offsets.  On the device:
 Only (representative id, combined value) pairs come back; the host decodes each
 distinct key once from the byte buffer it already holds.
 
-Multi-GPU exchange of variable-length keys is a later row:
-this module raises if torch.distributed is initialised with more than one rank.
+Under torch.distributed the rows are first routed to the rank owning their partition (dpark_b200.engine._routed_shuffle);
+this module is the one-GPU stage that then runs on the owner.
 """
 import numpy as np
 import torch
@@ -42,9 +42,9 @@ def _concat(splits):
 
 
 def reduce_by_key_bytes(splits, key_kind, P, thresholds, op, dev, res):
-    import torch.distributed as dist
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        raise NotImplementedError("str/bytes keys across several GPUs are not implemented yet")
+    if shuffle._world() > 1:
+        raise NotImplementedError("this is the one-GPU stage; under torch.distributed the rows are first routed to the "
+                                  "rank owning their partition (dpark_b200.engine._routed_shuffle)")
     data, offsets, vals, n = _concat(splits)
     if n == 0:
         for p in range(P):

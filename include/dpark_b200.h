@@ -157,6 +157,13 @@ int dpk_copy_segments(const uint64_t *src_ptrs, const uint64_t *dst_ptrs, const 
  * Accumulation: I64/I32 values -> int64 (exact while |sum| < 2^63, like the
  * reference's big ints); F64/F32 values -> float64 (the reference adds Python
  * floats); out_vals is 8 bytes per row.  out_keys/out_vals hold n entries.
+ * n may be an UPPER BOUND of the rows (e.g. the capacity of a receive buffer): with the
+ * default reduce_impl 2 only the rows seg_rows describes are read, so a multi-GPU caller
+ * needs no host read of the received row count.
+ * Errors that only the device can see: out_counts[j] == -1 marks a partition whose merge
+ * failed -- a fine bucket held more distinct keys than the shared-memory table takes even
+ * after splitting it by every spare hash bit (dpk_aggregate2.cuh); nothing is dropped
+ * silently, the caller that reads the counts raises (dpark_b200.shuffle.check_counts).
  */
 int64_t dpk_combine_workspace_bytes(int64_t n, int32_t nbuckets, int32_t nsrc);
 int dpk_combine(const void *keys, int key_kind, const int64_t *key_aux, const void *vals,
@@ -168,12 +175,23 @@ int dpk_combine(const void *keys, int key_kind, const int64_t *key_aux, const vo
  *   "reduce_impl"     2 (default) second-level split + one CTA per fine bucket merging in a
  *                     shared-memory table; 1 = per-bucket tables in HBM, one 8-CTA cluster per bucket;
  *                     0 = three grid-wide passes over global tables
- *   "agg_wide"        1 (default) claim a table slot and deposit the first value with one 128-bit
- *                     shared-memory CAS; 0 = 64-bit key CAS, then an atomic on the accumulator
+ *   "agg_impl"        1 (default) k_smem_aggregate2: staged rows + 32-bit row-index tags claimed with
+ *                     cas.b32; 0 = the round-1 kernel (128-bit {key, accumulator} slots)
+ *   "agg_cursor"      1 (default) a fine bucket reserves its output range with one atomicAdd on the
+ *                     partition's count (partitions are sets: any order); 0 = chained scan with
+ *                     decoupled look-back (deterministic order)
+ *   "agg_batched"     1 (default) four rows per thread in flight in the insert phase; 0 = probe loop per row
+ *   "agg_ctas"        3 (default) or 4 resident CTAs per SM the merge kernel is compiled for
+ *   "agg_wide"        round-1 kernel only: 1 (default) claim a table slot and deposit the first value with
+ *                     one 128-bit shared-memory CAS; 0 = 64-bit key CAS, then an atomic on the accumulator
  *   "agg_target_rows" rows per fine bucket the second-level split aims for (default 2048)
  *   "count_mode"      1 (default) one shared-memory atomic per row in the histogram pass; 0 = warp
  *                     peer masks + leader update
- *   "scatter_items"   16 (default) or 8 rows per thread and tile in the multisplit scatter */
+ *   "scatter_bulk"    1 (default) unordered multisplits (reduceByKey paths, second-level split) run
+ *                     k_part_scatter_bulk: one shared atomic per row for the rank, bucket runs leave the
+ *                     staged tile through cp.async.bulk (TMA, SASS UBLKCP); 0 = the round-1 kernel
+ *   "scatter_threads" 512 (default) or 256 threads per CTA of the bulk kernel (8 or 16 rows per thread)
+ *   "scatter_items"   round-1 kernel only: 16 (default) or 8 rows per thread and tile */
 int dpk_set_option(const char *name, int64_t value);
 
 /* ---- a10: reduce side of groupByKey (dpark/dependency.py:107-118 merged by
