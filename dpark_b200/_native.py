@@ -33,7 +33,7 @@ EXPORTS = [
     "dpk_launch_count", "dpk_prof_enable", "dpk_prof_count", "dpk_prof_get",
     "dpk_dict_encode_workspace_bytes", "dpk_dict_encode", "dpk_set_option",
     "dpk_key_or", "dpk_radix_pass", "dpk_group_heads_workspace_bytes", "dpk_group_heads", "dpk_gather_i64",
-    "dpk_partition_scatter_ptrs", "dpk_copy_segments",
+    "dpk_partition_scatter_ptrs", "dpk_copy_segments", "dpk_hash_tuple",
 ]
 
 _lib = None
@@ -62,6 +62,7 @@ def lib():
         L.dpk_hash_keys.argtypes = [vp, ci, i64, vp, vp]
         L.dpk_hash_bytes.argtypes = [vp, vp, i64, ci, vp, vp]
         L.dpk_partition_ids.argtypes = [vp, i64, i32, vp, i32, vp, vp]
+        L.dpk_hash_tuple.argtypes = [vp, i64, i32, vp, vp]
         L.dpk_partition_workspace_bytes.argtypes = [i64, i32]
         L.dpk_partition_count.argtypes = [vp, ci, vp, i64, i32, vp, i32, i32, vp, vp, i64, vp]
         L.dpk_partition_scatter.argtypes = [vp, ci, vp, vp, i32, i64, i32, vp, i32, i32, vp, vp, vp, vp, i64, vp]
@@ -164,6 +165,15 @@ def hash_bytes(data, offsets, mode):
     n = offsets.numel() - 1
     out = torch.empty(n, dtype=torch.int64, device=offsets.device)
     _check(lib().dpk_hash_bytes(_ptr(data), _ptr(offsets), n, mode, _ptr(out), _stream()))
+    return out
+
+
+def hash_tuple(item_hashes):
+    """tuple_hash (dpark/portable_hash.pyx:3-15) of n rows from their items' hashes: int64 tensor [arity, n]."""
+    _need_cuda(item_hashes)
+    arity, n = int(item_hashes.shape[0]), int(item_hashes.shape[1])
+    out = torch.empty(n, dtype=torch.int64, device=item_hashes.device)
+    _check(lib().dpk_hash_tuple(_ptr(item_hashes), n, arity, _ptr(out), _stream()))
     return out
 
 

@@ -131,6 +131,20 @@ DPK_HD int64_t hash_utf8_codepoints(const uint8_t *s, int64_t nbytes) {
     return (int64_t)value == -1 ? -2 : (int64_t)value;
 }
 
+// tuple_hash -- dpark/portable_hash.pyx:3-15 over the portable_hash values of the items (item_hash[a * stride + i] is
+// item a of row i); int64 wraparound like the Cython code.  An empty tuple hashes to 0x345678 + 97531.
+DPK_HD int64_t hash_tuple_items(const int64_t *item_hash, int64_t stride, int64_t i, int32_t arity) {
+    uint64_t mul = 1000003ull, value = 0x345678ull;
+    int64_t l = arity;
+    for (int32_t a = 0; a < arity; a++) {
+        l -= 1;
+        value = (value ^ (uint64_t)item_hash[(int64_t)a * stride + i]) * mul;
+        mul += (uint64_t)(82520 + l * 2);
+    }
+    value += 97531ull;
+    return (int64_t)value == -1 ? -2 : (int64_t)value;
+}
+
 // ------------------------------------------------- a2: HashPartitioner functor
 // getPartition = portable_hash(key) floor-mod P, or bisect_right(thresholds, h)
 // (dpark/dependency.py:229-233).  floor-mod by an arbitrary P without a 64-bit

@@ -102,6 +102,12 @@ __global__ void k_hash_bytes(const uint8_t *__restrict__ data, const int64_t *__
     }
 }
 
+__global__ void k_hash_tuple(const int64_t *__restrict__ item_hash, int64_t n, int32_t arity, int64_t *__restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) out[i] = hash_tuple_items(item_hash, n, i, arity);
+}
+
 __global__ void k_partition_ids(const int64_t *__restrict__ hash, int64_t n, PartFn f,
                                 int32_t *__restrict__ out) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -164,6 +170,15 @@ int dpk_hash_bytes(const uint8_t *data, const int64_t *offsets, int64_t n, int m
     if (mode != DPK_BYTES_SIGNED && mode != DPK_STR_UTF8) return fail(DPK_ERR_UNSUPPORTED, "bad bytes mode %d", mode);
     cudaStream_t st = (cudaStream_t)stream;
     DPK_LAUNCH("hash_bytes", st, k_hash_bytes<<<grid_for(n, 128), 128, 0, st>>>(data, offsets, n, mode, out_hash));
+    return DPK_OK;
+}
+
+int dpk_hash_tuple(const int64_t *item_hash, int64_t n, int32_t arity, int64_t *out_hash, dpk_stream_t stream) {
+    if (n < 0 || arity < 0 || arity > 64) return fail(DPK_ERR_INVALID, "bad n=%lld or arity=%d", (long long)n, arity);
+    if (n == 0) return DPK_OK;
+    if ((arity > 0 && !item_hash) || !out_hash) return fail(DPK_ERR_INVALID, "NULL pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    DPK_LAUNCH("hash_tuple", st, k_hash_tuple<<<grid_for(n, 256), 256, 0, st>>>(item_hash, n, arity, out_hash));
     return DPK_OK;
 }
 

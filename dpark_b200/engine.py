@@ -157,7 +157,7 @@ def _routed_shuffle(splits, kk, numeric, P, thr, op, dev, rank, world, blocks):
     for c in splits:
         if not c.n:
             continue
-        keys = columnar.decode_keys(c.key_kind, c.keys, c.key_offsets)
+        keys = columnar.decode_keys(c.key_kind, c.keys, c.key_offsets, c.key_objs)
         vals = c.objs if c.objs is not None else c.vals.tolist()
         h = columnar._hash_column(keys)
         t = None if thr is None else torch.tensor(thr, dtype=torch.int64, device=h.device)

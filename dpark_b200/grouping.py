@@ -82,10 +82,14 @@ def group_by_key(splits, P, thresholds, dev, res):
             offs.append(c.key_offsets[1:] + base)
             base += int(c.key_offsets[-1])
     offsets = np.concatenate(offs)
-    mode = nv.STR_UTF8 if kk == columnar.KEY_STR else nv.BYTES_SIGNED
     d_data = torch.from_numpy(data if data.size else np.zeros(1, np.uint8)).to(dev)
     d_off = torch.from_numpy(offsets).to(dev)
-    h = nv.hash_bytes(d_data, d_off, mode)
+    key_objs = None
+    if kk == columnar.KEY_TUPLE:             # identity = the canonical bytes; hash = tuple_hash of the leaves, on the device
+        key_objs = [k for c in splits if c.n for k in c.key_objs]
+        h = columnar.tuple_hashes_on_device(key_objs, dev)
+    else:
+        h = nv.hash_bytes(d_data, d_off, nv.STR_UTF8 if kk == columnar.KEY_STR else nv.BYTES_SIGNED)
     rep = nv.dict_encode(d_data, d_off, h)
     rowid = torch.arange(n, dtype=torch.int64, device=dev)
     # stable sort by representative id (rows of one string become adjacent, arrival order kept)
@@ -102,6 +106,9 @@ def group_by_key(splits, P, thresholds, dev, res):
     def decode(ids):
         out = []
         for r in ids.tolist():
+            if key_objs is not None:
+                out.append(key_objs[r])
+                continue
             b = raw[offsets[r]:offsets[r + 1]]
             out.append(b.decode("utf-8", "surrogatepass") if is_str else b)
         return out

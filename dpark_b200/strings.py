@@ -50,11 +50,15 @@ def reduce_by_key_bytes(splits, key_kind, P, thresholds, op, dev, res):
         for p in range(P):
             res.parts[p] = ([], [])
         return res
-    mode = nv.STR_UTF8 if key_kind == columnar.KEY_STR else nv.BYTES_SIGNED
     d_data = torch.from_numpy(data if data.size else np.zeros(1, np.uint8)).to(dev)
     d_off = torch.from_numpy(offsets).to(dev)
     d_vals = torch.from_numpy(vals).to(dev)
-    h = nv.hash_bytes(d_data, d_off, mode)
+    key_objs = None
+    if key_kind == columnar.KEY_TUPLE:       # identity = the canonical bytes; hash = tuple_hash of the leaves, on the device
+        key_objs = [k for c in splits if c.n for k in c.key_objs]
+        h = columnar.tuple_hashes_on_device(key_objs, dev)
+    else:
+        h = nv.hash_bytes(d_data, d_off, nv.STR_UTF8 if key_kind == columnar.KEY_STR else nv.BYTES_SIGNED)
     rep = nv.dict_encode(d_data, d_off, h)
     # map side: bucket-major by the hash of the string each id stands for; reduce side: merge per id
     sb = shuffle.choose_sub_bits(n, P)
@@ -71,6 +75,9 @@ def reduce_by_key_bytes(splits, key_kind, P, thresholds, op, dev, res):
         ids = ok_h[off_h[p]:off_h[p] + cnt_h[p]]
         keys = []
         for r in ids.tolist():
+            if key_objs is not None:
+                keys.append(key_objs[r])
+                continue
             b = raw[offs_l[r]:offs_l[r + 1]]
             keys.append(b.decode("utf-8", "surrogatepass") if is_str else b)
         res.parts[p] = (keys, ov_h[off_h[p]:off_h[p] + cnt_h[p]].tolist())

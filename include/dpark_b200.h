@@ -72,6 +72,10 @@ int dpk_hash_bytes(const uint8_t *data, const int64_t *offsets, int64_t n, int m
                    int64_t *out_hash, dpk_stream_t stream);
 
 /* ---- a2: HashPartitioner.getPartition (dpark/dependency.py:229-233) ------ */
+/* tuple keys (dpark/portable_hash.pyx:3-15, tuple_hash): the hash of row i's tuple from the portable_hash values of
+ * its `arity` items, item_hash[a * n + i] (item-major; computed with dpk_hash_keys / dpk_hash_bytes / this function
+ * for nested tuples, a constant column 1315925605 for None items, portable_hash.pyx:53-54). */
+int dpk_hash_tuple(const int64_t *item_hash, int64_t n, int32_t arity, int64_t *out_hash, dpk_stream_t stream);
 /* out_pid[i] = hash[i] floor-mod P, or bisect_right(thresholds, hash[i]) when
  * thresholds != NULL (nthr = P-1 ascending int64 on device). */
 int dpk_partition_ids(const int64_t *hash, int64_t n, int32_t P, const int64_t *thresholds,

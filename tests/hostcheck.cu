@@ -11,6 +11,9 @@ void hc_hash_bytes(const uint8_t *d, const int64_t *off, int64_t n, int mode, in
         o[i] = mode == 0 ? dpk::hash_bytes_signed(d + off[i], off[i + 1] - off[i])
                          : dpk::hash_utf8_codepoints(d + off[i], off[i + 1] - off[i]);
 }
+void hc_hash_tuple(const int64_t *item_hash, int64_t n, int32_t arity, int64_t *o) {
+    for (int64_t i = 0; i < n; i++) o[i] = dpk::hash_tuple_items(item_hash, n, i, arity);
+}
 int hc_partition(const int64_t *h, int64_t n, int32_t P, const int64_t *thr, int32_t nthr, int32_t *o) {
     dpk::PartFn f;
     int rc = dpk::make_partfn(P, thr, nthr, 0, &f);

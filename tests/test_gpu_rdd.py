@@ -221,3 +221,38 @@ def test_cogroup_matches_reference_on_the_gpu(case):
 @pytest.mark.parametrize("case", _cc.JOIN_CASES, ids=[c["name"] for c in _cc.JOIN_CASES])
 def test_joins_match_reference_on_the_gpu(case):
     _cc.check_join(case)
+
+
+def test_tuple_and_none_keys_reduce_and_group_like_python_and_partition_like_the_reference():
+    """a1 for tuple / None keys (dpark/portable_hash.pyx:3-15, 53-54): the device hashes decide the partition, the
+    canonical-bytes identity decides equality.  Layout is checked against the oracle's getPartition (pinned to the
+    reference's golden tuple vectors in test_oracle_golden.py), contents against plain Python dicts."""
+    import random
+    from oracle import oracle as orc
+    dc = ctx()
+    rnd = random.Random(11)
+    P = 5
+    for make in (lambda: (rnd.randint(-3, 3), "k%d" % rnd.randint(0, 4)),
+                 lambda: ("a", (rnd.randint(0, 2), float(rnd.randint(0, 2)))),
+                 lambda: (rnd.randint(0, 6), None, b"x" * rnd.randint(0, 2)),
+                 lambda: ()):
+        rows = [(make(), rnd.randint(-50, 50)) for _ in range(3000)]
+        want = {}
+        for k, v in rows:
+            want[k] = want.get(k, 0) + v
+        got = dc.parallelize(rows, 4).reduceByKey(lambda x, y: x + y, P).glom().collect()
+        assert len(got) == P
+        seen = {}
+        for p, part in enumerate(got):
+            for k, v in part:
+                assert orc.get_partition(k, P) == p, (k, p)
+                assert k not in seen
+                seen[k] = v
+        assert seen == want
+        groups = dict(dc.parallelize([(k, i) for i, (k, _) in enumerate(rows)], 4).groupByKey(P).collect())
+        wantg = {}
+        for i, (k, _) in enumerate(rows):
+            wantg.setdefault(k, []).append(i)
+        assert {k: list(v) for k, v in groups.items()} == wantg        # values in (map split, position) order
+    nones = dc.parallelize([(None, i) for i in range(100)], 3).reduceByKey(lambda x, y: x + y, 4).glom().collect()
+    assert [len(p) for p in nones] == [0, 1, 0, 0] and nones[1] == [(None, 4950)]     # portable_hash(None) % 4 == 1

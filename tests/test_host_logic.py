@@ -358,3 +358,37 @@ def test_only_straight_line_list_collectors_are_recognised_as_group_by():
     for agg in (bounded, dedup, srt):
         with pytest.raises(NotImplementedError):
             trace.recognize_aggregator(agg)
+
+
+def test_tuple_hash_device_function_matches_the_reference_vectors():
+    """a1 for tuple keys (dpark/portable_hash.pyx:3-15): the __host__ __device__ tuple_hash, fed with the item hashes
+    of the reference's own golden vectors, must reproduce the golden tuple hashes (incl. the empty tuple, nested
+    tuples and None items)."""
+    L = _hostcheck()
+    hv = load("hash_vectors.json")
+    rows = [(dec(r["key"]), r["hash"]) for r in hv["rows"] if isinstance(r["key"], dict) and "tu" in r["key"]]
+    assert len(rows) >= 5
+
+    def item_hash(x):
+        return orc.portable_hash(x)                 # leaves are pinned separately; here only the combination is tested
+    for key, want in rows:
+        items = np.array([item_hash(x) for x in key], dtype=np.int64).reshape(len(key), 1)
+        o = np.empty(1, dtype=np.int64)
+        L.hc_hash_tuple(_p(np.ascontiguousarray(items)), C.c_int64(1), C.c_int32(len(key)), _p(o))
+        assert int(o[0]) == want, key
+
+
+def test_tuple_and_none_keys_become_identity_bytes_with_one_shape():
+    from dpark_b200 import columnar
+    c = columnar.ingest_pairs([((1, "a"), 1), ((1, "b"), 2), ((1, "a"), 3)])
+    assert c.key_kind == "tuple" and c.key_objs == [(1, "a"), (1, "b"), (1, "a")]
+    blobs = [bytes(c.keys[c.key_offsets[i]:c.key_offsets[i + 1]]) for i in range(3)]
+    assert blobs[0] == blobs[2] != blobs[1]
+    c = columnar.ingest_pairs([(None, 1), (None, 2)])
+    assert c.key_kind == "tuple" and c.key_offsets.tolist() == [0, 0, 0]
+    with pytest.raises(TypeError):
+        columnar.ingest_pairs([((1, 2), 1), ((1, 2.0), 2)])          # same value in Python, different shape here
+    with pytest.raises(TypeError):
+        columnar.ingest_pairs([((1, 2), 1), ((1, 2, 3), 2)])
+    with pytest.raises(TypeError):
+        columnar.ingest_pairs([(None, 1), (3, 2)])

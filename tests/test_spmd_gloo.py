@@ -43,7 +43,7 @@ def _patch_gpu_stages():
             op = rest[0] if kind == "reduce" else None
             f = {"sum": lambda a, b: a + b, "min": min, "max": max}.get(op)
             for c in splits:
-                keys = columnar.decode_keys(c.key_kind, c.keys, c.key_offsets)
+                keys = columnar.decode_keys(c.key_kind, c.keys, c.key_offsets, c.key_objs)
                 vals = c.objs if c.objs is not None else c.vals.tolist()
                 for k, v in zip(keys, vals):
                     b = buckets[orc.get_partition(k, P, thr)]
