@@ -79,6 +79,7 @@ def parse():
     ap.add_argument("--agg-ctas", type=int, default=0, help="A/B: resident CTAs per SM the merge kernel is compiled for (3|4)")
     ap.add_argument("--agg-cursor", type=int, default=-1, help="A/B: merge kernel output ranges by atomic cursor (1) or chained look-back (0)")
     ap.add_argument("--agg-batched", type=int, default=-1, help="A/B: four rows in flight per thread in the merge kernel's insert phase")
+    ap.add_argument("--agg-pipe", type=int, default=-1, help="A/B: register-pipelined merge kernel (0 | 1 | 2 = two CTAs per SM)")
     ap.add_argument("--agg-impl", type=int, default=-1, help="A/B: reduce-side merge kernel (0 = round 1, 1 = row-index tags)")
     ap.add_argument("--overlap-push", type=int, default=1, help="N>1, push exchange: groups of map splits whose push "
                     "overlaps the scatter of the next group (1 = no overlap)")
@@ -512,6 +513,8 @@ def run_ours(args):
         nv.set_option("agg_cursor", args.agg_cursor)
     if args.agg_batched >= 0:
         nv.set_option("agg_batched", args.agg_batched)
+    if args.agg_pipe >= 0:
+        nv.set_option("agg_pipe", args.agg_pipe)
 
     ex_events = []
     px = None
@@ -573,7 +576,7 @@ def run_ours(args):
         if any(c < 0 for c in cnt_h):
             raise SystemExit("reduce side reported a failed partition (table overflow)")
         distinct_local = sum(cnt_h)
-        nrecv_local = int(ok_.numel())
+        nrecv_local = int(po_h[-1])        # part_offsets[nparts] = rows this rank's reduce side received
         checked = (ok_, ov_, po_h, cnt_h)
     parity = {"parity_checked": False}
     if not args.no_parity:

@@ -87,6 +87,10 @@ def lib():
         if L.dpk_abi_version() != 1:
             raise ImportError("dpark_b200: ABI version mismatch")
         _lib = L
+        # DPK_OPTIONS="name=value,..." applies dpk_set_option switches at load (A/B runs of whole test suites)
+        for item in filter(None, os.environ.get("DPK_OPTIONS", "").split(",")):
+            name, _, value = item.partition("=")
+            _check(L.dpk_set_option(name.strip().encode(), int(value)))
     return _lib
 
 

@@ -219,7 +219,11 @@ k_smem_aggregate2(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, 
                   const int64_t *__restrict__ part_offsets, KeyT *__restrict__ out_keys,
                   int64_t *__restrict__ out_vals, long long *__restrict__ out_counts,
                   unsigned long long *__restrict__ fb_state, int *__restrict__ work_counter,
-                  int *__restrict__ part_err) {
+                  int *__restrict__ part_err, const int *__restrict__ bucket_list, const int *__restrict__ bucket_count) {
+    // bucket_list != nullptr (CURSOR only): the tickets index a list of fine buckets (the oversized ones
+    // k_smem_aggregate3 left behind) instead of all nfine buckets
+    const int nwork = bucket_list ? *bucket_count : nfine;
+    auto bucket_of_ticket = [&](int t) { return bucket_list ? bucket_list[t] : t; };
     extern __shared__ __align__(16) long long s_dyn2[];  // [TAGS] u32 tags | [CAP] key bits | [CAP] accumulators
     uint32_t *s_tag = reinterpret_cast<uint32_t *>(s_dyn2);
     long long *s_key = s_dyn2 + AG2_TAGS / 2;
@@ -277,8 +281,8 @@ k_smem_aggregate2(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, 
     clear_tags();
     if (threadIdx.x == 0) {
         const int t = atomicAdd(work_counter, 1);
-        sh.next_fb[0] = t;
-        if (t < nfine) { sh.next_r0[0] = fine_off[t]; sh.next_r1[0] = fine_off[t + 1]; }
+        sh.next_fb[0] = t < nwork ? bucket_of_ticket(t) : nfine;
+        if (t < nwork) { const int b = bucket_of_ticket(t); sh.next_r0[0] = fine_off[b]; sh.next_r1[0] = fine_off[b + 1]; }
     }
     for (int it = 0;; it++) {
         __syncthreads();                                            // (A) also: previous write-out and tag clear finished
@@ -300,13 +304,14 @@ k_smem_aggregate2(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, 
         };
         auto prefetch_range = [&]() {
             if (CURSOR && threadIdx.x == 0) {
-                sh.next_fb[(it + 1) & 1] = nt;
-                if (nt < nfine) { nr0 = fine_off[nt]; nr1 = fine_off[nt + 1]; }
+                const int b = nt < nwork ? bucket_of_ticket(nt) : nfine;
+                sh.next_fb[(it + 1) & 1] = b;
+                if (b < nfine) { nr0 = fine_off[b]; nr1 = fine_off[b + 1]; }
             }
         };
         auto publish_range = [&]() {   // before a barrier that precedes (A) of the next iteration
             if (threadIdx.x == 0) {
-                if (!CURSOR) {
+                if (!CURSOR) {   // (look-back mode never runs in list mode)
                     nt = atomicAdd(work_counter, 1);
                     sh.next_fb[(it + 1) & 1] = nt;
                     if (nt < nfine) { nr0 = fine_off[nt]; nr1 = fine_off[nt + 1]; }

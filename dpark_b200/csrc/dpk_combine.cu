@@ -414,6 +414,7 @@ k_bucket_reduce(const KeyT *__restrict__ keys, const int64_t *__restrict__ aux, 
 // ===== implementation 2: second-level split + shared-memory tables (dpk_aggregate.cuh) =====
 #include "dpk_aggregate.cuh"
 #include "dpk_aggregate2.cuh"
+#include "dpk_aggregate3.cuh"
 
 // the key whose bits equal the free-slot marker lives in the side slot: append it
 template <typename KeyT>
@@ -447,6 +448,7 @@ constexpr int AG_MAX_SB2 = 10;       // at most 1024 fine buckets per first-leve
 int g_agg_wide = 1;
 int g_agg_ctas = 3;
 int g_agg_cursor = 1;
+int g_agg_pipe = 0;                  // dpk_set_option("agg_pipe"): 1 = k_smem_aggregate3 (rows prefetched into registers), 2 = same, 2 CTAs per SM
 int g_agg_batched = 1;
 int g_agg_impl = 1;                  // dpk_set_option("agg_impl"): 1 = k_smem_aggregate2 (row-index tags), 0 = round-1 kernel
 int g_agg_target_rows = 2048;        // rows per fine bucket the split aims for (table load <= 0.5)
@@ -514,10 +516,33 @@ static int dispatch_op(const Ctx &c) {
             else agg2 = k_smem_aggregate2<KeyT, ValT, AccT, 3, false, false>;
             const int smem2 = AG2_TAGS * 4 + AG2_CAP * 16;
             DPK_CUDA_TRY(cudaFuncSetAttribute(agg2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
-            DPK_CUDA_TRY(cudaMemsetAsync(c.part_err, 0, (size_t)c.nparts * 4, c.st));
+            DPK_CUDA_TRY(cudaMemsetAsync(c.part_err, 0, (size_t)(c.nparts + 2) * 4, c.st));
+            if (g_agg_pipe && g_agg_cursor) {
+                // register-pipelined fast path for the buckets that fit one window; the oversized ones go to a list
+                // (two ints behind the per-partition error flags: list length, list-mode work counter) and are merged by
+                // the staged kernel in a second launch
+                auto agg3 = g_agg_pipe == 2 ? k_smem_aggregate3<KeyT, ValT, AccT, 2> : k_smem_aggregate3<KeyT, ValT, AccT, 3>;
+                const int smem3 = AG2_TAGS * 4 + AG2_CAP * 8;
+                DPK_CUDA_TRY(cudaFuncSetAttribute(agg3, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
+                int *big_count = c.part_err + c.nparts, *list_counter = c.part_err + c.nparts + 1;
+                int *big_list = reinterpret_cast<int *>(c.fb_state);          // nfine * 8 bytes: idle in cursor mode
+                int g3 = sm_count() * (g_agg_pipe == 2 ? 2 : 3);
+                if (g3 > nfine) g3 = nfine;
+                DPK_LAUNCH("smem_aggregate", c.st, agg3<<<g3, AG2_THREADS, smem3, c.st>>>(
+                    rekeys, revals, c.op, ident, c.fine_off, nfine, (1 << c.f.sub_bits) * S2, c.part_off,
+                    (KeyT *)c.out_keys, c.out_vals, (long long *)c.out_counts, c.bucket_counter, big_list, big_count));
+                auto aggb = k_smem_aggregate2<KeyT, ValT, AccT, 3, true, false>;
+                DPK_CUDA_TRY(cudaFuncSetAttribute(aggb, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+                DPK_LAUNCH("smem_aggregate_big", c.st, aggb<<<sm_count(), AG2_THREADS, smem2, c.st>>>(
+                    rekeys, revals, c.op, c.fine_off, nfine, (1 << c.f.sub_bits) * S2, c.part_off,
+                    (KeyT *)c.out_keys, c.out_vals, (long long *)c.out_counts, c.fb_state, list_counter, c.part_err,
+                    big_list, big_count));
+            } else {
             DPK_LAUNCH("smem_aggregate", c.st, agg2<<<grid, AG2_THREADS, smem2, c.st>>>(
                 rekeys, revals, c.op, c.fine_off, nfine, (1 << c.f.sub_bits) * S2, c.part_off,
-                (KeyT *)c.out_keys, c.out_vals, (long long *)c.out_counts, c.fb_state, c.bucket_counter, c.part_err));
+                (KeyT *)c.out_keys, c.out_vals, (long long *)c.out_counts, c.fb_state, c.bucket_counter, c.part_err,
+                nullptr, nullptr));
+            }
             if (g_agg_cursor)
                 DPK_LAUNCH("agg_finalize", c.st, k_agg_finalize<<<1, 256, 0, c.st>>>(c.part_err, (long long *)c.out_counts, c.nparts));
             return DPK_OK;
@@ -618,6 +643,11 @@ int dpk_set_option(const char *name, int64_t value) {
     if (strcmp(name, "agg_batched") == 0) {
         if (value != 0 && value != 1) return fail(DPK_ERR_INVALID, "agg_batched must be 0 or 1");
         g_agg_batched = (int)value;
+        return DPK_OK;
+    }
+    if (strcmp(name, "agg_pipe") == 0) {
+        if (value < 0 || value > 2) return fail(DPK_ERR_INVALID, "agg_pipe must be 0, 1 or 2");
+        g_agg_pipe = (int)value;
         return DPK_OK;
     }
     if (strcmp(name, "agg_cursor") == 0) {

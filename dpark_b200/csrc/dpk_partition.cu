@@ -628,15 +628,35 @@ k_part_scatter_bulk(const KeyT *__restrict__ keys, const ValT *__restrict__ vals
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the TMA
         __syncthreads();  // (C)
 
-        // ---- copy-out: bucket runs leave through the TMA
-        for (int p = threadIdx.x; p < P; p += NT) {
-            const int c = (int)cnt[p];
-            if (c) {
-                const int64_t g = s_gpos[p];
-                flush_run<KeyT>(out_keys, g, s_key, key_addr, s_sk[p], c);
-                if constexpr (HAS_VAL) flush_run<ValT>(out_vals, g, s_val, val_addr, s_sv[p], c);
-                s_gpos[p] = g + c;
-                cnt[p] = 0;  // this array is used again two tiles from now (barriers A..C of the next tile in between)
+        // ---- copy-out: bucket runs leave through the TMA.  With values, lane pairs share a bucket (even lane: key
+        //      run, odd lane: value run) so that every thread issues at most one bulk store per round: the issue
+        //      rate of one thread bounds the bulk-store rate below 512-byte runs (profiles/r02_microbench.md)
+        if constexpr (HAS_VAL) {
+            for (int q0 = 0; q0 < 2 * P; q0 += NT) {
+                const int q = q0 + (int)threadIdx.x;
+                const int p = q >> 1;
+                const bool on = q < 2 * P;
+                const int c = on ? (int)cnt[p] : 0;
+                const int64_t g = on ? s_gpos[p] : 0;
+                if (c) {
+                    if (q & 1) flush_run<ValT>(out_vals, g, s_val, val_addr, s_sv[p], c);
+                    else flush_run<KeyT>(out_keys, g, s_key, key_addr, s_sk[p], c);
+                }
+                __syncwarp();   // both lanes of the pair have read the count and the position
+                if (c && !(q & 1)) {
+                    s_gpos[p] = g + c;
+                    cnt[p] = 0;  // this array is used again two tiles from now (barriers A..C of the next tile in between)
+                }
+            }
+        } else {
+            for (int p = threadIdx.x; p < P; p += NT) {
+                const int c = (int)cnt[p];
+                if (c) {
+                    const int64_t g = s_gpos[p];
+                    flush_run<KeyT>(out_keys, g, s_key, key_addr, s_sk[p], c);
+                    s_gpos[p] = g + c;
+                    cnt[p] = 0;
+                }
             }
         }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");

@@ -643,18 +643,23 @@ class OutputTextFileRDD(DerivedRDD):
     partitions write nothing; yields the paths written."""
 
     def __init__(self, rdd, path, ext="", overwrite=False, compress=False):
-        if os.path.exists(path):
-            if not os.path.isdir(path):
-                raise Exception("output must be dir")
-            if overwrite:
-                for n in os.listdir(path):
-                    p = os.path.join(path, n)
-                    if os.path.isdir(p):
-                        shutil.rmtree(p)
-                    else:
-                        os.remove(p)
-        else:
-            os.makedirs(path)
+        from . import spmd
+        rank, world = spmd.rank_world()
+        if rank == 0:                      # one driver process per GPU: rank 0 prepares the directory, everyone waits
+            if os.path.exists(path):
+                if not os.path.isdir(path):
+                    raise Exception("output must be dir")
+                if overwrite:
+                    for n in os.listdir(path):
+                        p = os.path.join(path, n)
+                        if os.path.isdir(p):
+                            shutil.rmtree(p)
+                        else:
+                            os.remove(p)
+            else:
+                os.makedirs(path, exist_ok=True)
+        if world > 1:
+            spmd.barrier()
         DerivedRDD.__init__(self, rdd)
         self.path = os.path.abspath(path)
         if ext and not ext.startswith("."):

@@ -81,6 +81,12 @@ def all_to_all_objects(per_dest):
     return out
 
 
+def barrier():
+    import torch.distributed as dist
+    if rank_world()[1] > 1:
+        dist.barrier()
+
+
 def agree_max(value):
     """max of an int over the ranks (sizes that every rank must choose identically)."""
     import torch.distributed as dist
