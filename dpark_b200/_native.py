@@ -33,7 +33,8 @@ EXPORTS = [
     "dpk_launch_count", "dpk_prof_enable", "dpk_prof_count", "dpk_prof_get",
     "dpk_dict_encode_workspace_bytes", "dpk_dict_encode", "dpk_set_option",
     "dpk_key_or", "dpk_radix_pass", "dpk_group_heads_workspace_bytes", "dpk_group_heads", "dpk_gather_i64",
-    "dpk_partition_scatter_ptrs", "dpk_copy_segments", "dpk_hash_tuple",
+    "dpk_partition_scatter_ptrs", "dpk_copy_segments", "dpk_hash_tuple", "dpk_push_plan",
+    "dpk_radix_pass_seg_workspace_bytes", "dpk_radix_pass_seg",
 ]
 
 _lib = None
@@ -69,6 +70,7 @@ def lib():
         L.dpk_partition.argtypes = [vp, ci, vp, vp, i32, i64, i32, vp, i32, i32, vp, vp, vp, vp, i64, vp]
         L.dpk_partition_scatter_ptrs.argtypes = [vp, ci, vp, vp, i32, i64, i32, vp, i32, i32, vp, vp, vp, i64, vp]
         L.dpk_copy_segments.argtypes = [vp, vp, vp, i32, vp]
+        L.dpk_push_plan.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, C.c_uint64, C.c_uint64, vp, i32, i32, i64, vp, vp, vp, vp, vp, vp]
         L.dpk_combine_workspace_bytes.argtypes = [i64, i32, i32]
         L.dpk_combine.argtypes = [vp, ci, vp, vp, ci, i64, ci, i32, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp,
                                   vp, vp, i64, vp]
@@ -76,6 +78,9 @@ def lib():
         L.dpk_key_or.argtypes = [vp, i64, vp, vp]
         L.dpk_gather_i64.argtypes = [vp, vp, i64, vp, vp]
         L.dpk_radix_pass.argtypes = [vp, vp, i32, i64, i32, i32, vp, vp, vp, i64, vp]
+        L.dpk_radix_pass_seg_workspace_bytes.restype = i64
+        L.dpk_radix_pass_seg_workspace_bytes.argtypes = [i64, i32, i32, i32]
+        L.dpk_radix_pass_seg.argtypes = [vp, vp, i32, i64, i32, i32, i32, i32, vp, vp, vp, vp, vp, i64, vp]
         L.dpk_group_heads_workspace_bytes.restype = i64
         L.dpk_group_heads_workspace_bytes.argtypes = [i64]
         L.dpk_group_heads.argtypes = [vp, i64, vp, vp, vp, vp, i64, vp]
@@ -250,6 +255,26 @@ def copy_segments(src_ptrs, dst_ptrs, nbytes):
     _check(lib().dpk_copy_segments(_ptr(src_ptrs), _ptr(dst_ptrs), _ptr(nbytes), nbytes.numel(), _stream()))
 
 
+def push_plan(all_counts, nranks, per_block, my_src, my_rank, keys, vals, dst_base, capacity, need_over, want_seg=True):
+    """dpk_push_plan: (src_ptrs, dst_ptrs, nbytes [ncols * nranks], seg [nsrc, own buckets] | None), one launch.
+    keys / vals: my bucket-major columns (vals may be None); dst_base: device int64 [ncols * nranks] receive-buffer
+    addresses (column-major)."""
+    _need_cuda(all_counts, dst_base, need_over)
+    nsrc, F = int(all_counts.shape[0]), int(all_counts.shape[1])
+    ncols = 1 if vals is None else 2
+    dev = all_counts.device
+    src = torch.empty(ncols * nranks, dtype=torch.int64, device=dev)
+    dst = torch.empty(ncols * nranks, dtype=torch.int64, device=dev)
+    nby = torch.empty(ncols * nranks, dtype=torch.int64, device=dev)
+    b0, b1 = min(F, my_rank * per_block), min(F, (my_rank + 1) * per_block)
+    seg = torch.empty((nsrc, b1 - b0), dtype=torch.int64, device=dev) if want_seg else None
+    _check(lib().dpk_push_plan(_ptr(all_counts), nsrc, nranks, F, per_block, my_src, my_rank, ncols,
+                               C.c_uint64(keys.data_ptr()), C.c_uint64(0 if vals is None else vals.data_ptr()),
+                               _ptr(dst_base), keys.element_size(), 0 if vals is None else vals.element_size(),
+                               capacity, _ptr(src), _ptr(dst), _ptr(nby), _ptr(need_over), _ptr(seg), _stream()))
+    return src, dst, nby, seg
+
+
 def partition(keys, vals, P, thresholds=None, prehashed=False, sub_bits=0, row_hash=None, unordered=False):
     """Stable hash-partition of one chunk (ShuffleMapTask._run, dpark/task.py:209-226).
     Returns (out_keys, out_vals, offsets[(P << sub_bits) + 1] int64 device)."""
@@ -357,6 +382,27 @@ def radix_pass(keys, vals, shift, bits, out_keys=None, out_vals=None, ws=None):
     vb = 0 if vals is None else vals.element_size()
     _check(lib().dpk_radix_pass(_ptr(keys), _ptr(vals), vb, keys.numel(), shift, bits, _ptr(out_keys),
                                 _ptr(out_vals), _ptr(ws), ws.numel(), _stream()))
+    return out_keys, out_vals
+
+
+def radix_pass_seg(keys, vals, shift, bits, seg_rows, out_keys=None, out_vals=None):
+    """One stable radix pass inside every first-level bucket (dpk_radix_pass_seg).  seg_rows: device int64
+    [nsrc, nbuckets].  Returns (out_keys, out_vals)."""
+    _need_cuda(keys, vals, seg_rows)
+    if keys.dtype != torch.int64:
+        raise TypeError("radix_pass_seg sorts int64 key bits")
+    nsrc, F = int(seg_rows.shape[0]), int(seg_rows.shape[1])
+    n = keys.numel()
+    if out_keys is None:
+        out_keys = torch.empty_like(keys)
+    if out_vals is None and vals is not None:
+        out_vals = torch.empty_like(vals)
+    ws_bytes = lib().dpk_radix_pass_seg_workspace_bytes(n, F, nsrc, bits)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=keys.device)
+    fine = torch.empty((F << bits) + 1, dtype=torch.int64, device=keys.device)
+    vb = 0 if vals is None else vals.element_size()
+    _check(lib().dpk_radix_pass_seg(_ptr(keys), _ptr(vals), vb, n, shift, bits, F, nsrc, _ptr(seg_rows.contiguous()),
+                                    _ptr(out_keys), _ptr(out_vals), _ptr(fine), _ptr(ws), ws_bytes, _stream()))
     return out_keys, out_vals
 
 

@@ -671,7 +671,7 @@ int dpk_set_option(const char *name, int64_t value) {
         return DPK_OK;
     }
     if (strcmp(name, "scatter_threads") == 0) {
-        if (value != 256 && value != 512) return fail(DPK_ERR_INVALID, "scatter_threads must be 256 or 512");
+        if (value != 256 && value != 512 && value != 1024) return fail(DPK_ERR_INVALID, "scatter_threads must be 256, 512 or 1024");
         g_scatter_threads = (int)value;
         return DPK_OK;
     }

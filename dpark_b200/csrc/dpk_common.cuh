@@ -227,7 +227,7 @@ int64_t seg_multisplit_ws_bytes(int64_t n, int32_t F1, int32_t S2, int32_t nsrc)
 int seg_multisplit(const void *keys, int key_kind, const void *vals, int32_t val_bytes, int64_t n,
                    const PartFn &fine, int32_t F1, int32_t nsrc, const int64_t *seg_start,
                    const int64_t *seg_rows, void *out_keys, void *out_vals, int64_t *fine_off, void *ws,
-                   int64_t ws_bytes, cudaStream_t st);
+                   int64_t ws_bytes, cudaStream_t st, bool stable = false);
 
 // murmur3 fmix64 -- slot hash for the reduce-side tables in HBM (implementations 0/1; not part of the
 // reference semantics; only spreads keys over table slots)

@@ -500,14 +500,16 @@ __device__ __forceinline__ int bucket_of(const PartFn &f, int64_t h) {
 }
 
 template <typename KeyT, typename ValT, int PRE, int NT, int FMODE>
-__global__ void __launch_bounds__(NT, 2)
+__global__ void __launch_bounds__(NT, NT == 1024 ? 1 : 2)
 k_part_scatter_bulk(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, int64_t n, int64_t L,
                     PartFn f, const int32_t *__restrict__ tile_off, int32_t T,
                     const int64_t *__restrict__ bucket_base, KeyT *__restrict__ out_keys,
                     ValT *__restrict__ out_vals, BulkSmem lay, SegTab seg) {
     constexpr bool HAS_VAL = !std::is_same<ValT, NoVal>::value;
-    constexpr int ITEMS = PT_TILE / NT;   // 16 rows per thread with 256 threads, 8 with 512 (twice the resident warps)
-    constexpr int TILE = PT_TILE;
+    // 256 threads x 16 rows or 512 x 8 (twice the resident warps) on 4096-row tiles, two CTAs per SM; 1024 x 8 on
+    // 8192-row tiles, one CTA per SM (bucket runs twice as long, half the barriers and scans per row)
+    constexpr int ITEMS = NT == 256 ? 16 : 8;
+    constexpr int TILE = NT * ITEMS;
     constexpr int NW = NT / 32;
     constexpr int AK = 16 / (int)sizeof(KeyT);
     constexpr int AV = HAS_VAL ? 16 / (int)sizeof(typename std::conditional<HAS_VAL, ValT, int64_t>::type) : 1;
@@ -712,11 +714,15 @@ static int launch_scatter_bulk(const void *keys, const void *vals, int64_t n, co
                                const int32_t *tile_off, const int64_t *bucket_base, void *out_keys,
                                void *out_vals, cudaStream_t st) {
     constexpr int vb = std::is_same<ValT, NoVal>::value ? 0 : (int)sizeof(ValT);
-    BulkSmem lay = bulk_smem((int)sizeof(KeyT), vb, f.nbuckets(), PT_TILE);
-    // dpk_set_option("scatter_threads"): 512 (default; 8 rows per thread, 32 warps per SM) or 256 (16 rows per thread)
-    const int nt = g_scatter_threads;
+    // dpk_set_option("scatter_threads"): 512 (default; 8 rows per thread, 4096-row tiles, 2 CTAs per SM), 256 (16 rows
+    // per thread) or 1024 (8192-row tiles, 1 CTA per SM)
+    int nt = g_scatter_threads;
+    if (nt == 1024 && bulk_smem((int)sizeof(KeyT), vb, f.nbuckets(), 8192).total > 220 * 1024) nt = 512;
+    BulkSmem lay = bulk_smem((int)sizeof(KeyT), vb, f.nbuckets(), nt == 1024 ? 8192 : PT_TILE);
     const int fmode = f.mode == 5 ? 2 : ((f.mode == 0 || f.mode == 1) ? 1 : 0);
-    auto kern = nt == 512 ? (fmode == 2 ? k_part_scatter_bulk<KeyT, ValT, PRE, 512, 2> :
+    auto kern = nt == 1024 ? (fmode == 2 ? k_part_scatter_bulk<KeyT, ValT, PRE, 1024, 2> :
+                              fmode == 1 ? k_part_scatter_bulk<KeyT, ValT, PRE, 1024, 1> : k_part_scatter_bulk<KeyT, ValT, PRE, 1024, 0>)
+              : nt == 512 ? (fmode == 2 ? k_part_scatter_bulk<KeyT, ValT, PRE, 512, 2> :
                              fmode == 1 ? k_part_scatter_bulk<KeyT, ValT, PRE, 512, 1> : k_part_scatter_bulk<KeyT, ValT, PRE, 512, 0>)
                           : k_part_scatter_bulk<KeyT, ValT, PRE, 256, 0>;
     DPK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
@@ -887,7 +893,7 @@ int64_t seg_multisplit_ws_bytes(int64_t n, int32_t F1, int32_t S2, int32_t nsrc)
 int seg_multisplit(const void *keys, int key_kind, const void *vals, int32_t val_bytes, int64_t n,
                    const PartFn &fine, int32_t F1, int32_t nsrc, const int64_t *seg_start,
                    const int64_t *seg_rows, void *out_keys, void *out_vals, int64_t *fine_off, void *ws,
-                   int64_t ws_bytes, cudaStream_t st) {
+                   int64_t ws_bytes, cudaStream_t st, bool stable) {
     const int32_t S2 = fine.nbuckets();
     if (ws_bytes < seg_multisplit_ws_bytes(n, F1, S2, nsrc)) return fail(DPK_ERR_WORKSPACE, "segmented multisplit workspace too small");
     const int64_t maxc = seg_max_chunks(n, F1, nsrc);
@@ -905,6 +911,11 @@ int seg_multisplit(const void *keys, int key_kind, const void *vals, int32_t val
     pl.L = 0;
     // the reduce side never needs the order of rows inside a fine bucket
     pl.seg = SegTab{cbeg, cend, ctotal, chunk_counts, chunk_off, nullptr, nullptr, (S2 % 2 == 0) ? 1 : (g_scatter_bulk ? 2 : 0)};
+    if (stable) {   // radix passes of the group-by: rows of a fine bucket keep their order (warp-match ranking)
+        pl.seg.unordered = 0;
+        pl.label_count = "radix_count";
+        pl.label_scatter = "radix_scatter";
+    }
     int rc = DPK_OK;
     if (n > 0) {
         rc = dispatch_count(keys, key_kind, n, pl, fine, nullptr, st);
@@ -1007,6 +1018,67 @@ int dpk_partition_scatter_ptrs(const void *keys, int key_kind, const int64_t *ke
     pl.seg.val_ptrs = val_dst_ptrs;
     return dispatch_scatter(keys, key_kind, vals, val_bytes, n, pl, f, (const int32_t *)ws, nullptr, nullptr, nullptr,
                             (cudaStream_t)stream);
+}
+
+// first row of segment (s, b) in a source-major, bucket-major buffer: single CTA
+__global__ void __launch_bounds__(PT_THREADS)
+k_seg_starts(const int64_t *__restrict__ seg_rows, int32_t nsrc, int32_t F, int64_t *__restrict__ seg_start) {
+    __shared__ long long s_part[PT_THREADS];
+    __shared__ long long s_carry;
+    const int E = (F + PT_THREADS - 1) / PT_THREADS;
+    const int b0 = threadIdx.x * E, b1 = min(b0 + E, F);
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int s = 0; s < nsrc; s++) {
+        long long mine = 0;
+        for (int b = b0; b < b1; b++) mine += seg_rows[(int64_t)s * F + b];
+        s_part[threadIdx.x] = mine;
+        __syncthreads();
+        long long base = s_carry, tot = 0;
+        for (int t = 0; t < PT_THREADS; t++) {
+            if (t < (int)threadIdx.x) base += s_part[t];
+            tot += s_part[t];
+        }
+        for (int b = b0; b < b1; b++) {
+            seg_start[(int64_t)s * F + b] = base;
+            base += seg_rows[(int64_t)s * F + b];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry += tot;
+        __syncthreads();
+    }
+}
+
+int64_t dpk_radix_pass_seg_workspace_bytes(int64_t n, int32_t nbuckets, int32_t nsrc, int32_t bits) {
+    if (n < 0) n = 0;
+    if (nbuckets < 1) nbuckets = 1;
+    if (nsrc < 1) nsrc = 1;
+    return align_up((int64_t)nbuckets * nsrc * 8, 256) + seg_multisplit_ws_bytes(n, nbuckets, 1 << bits, nsrc);
+}
+
+// One stable LSD radix pass INSIDE every first-level bucket (the group-by's reduce side sorts each hash bucket by
+// its key bits independently -- all rows of a key are in one bucket -- so no pass over the partition id is needed
+// afterwards): the input is source-major, bucket-major (seg_rows[nsrc][nbuckets], what the exchange delivers; nsrc = 1
+// for the later passes), the output is bucket-major with every bucket stably split by the digit `shift` (bits wide) of
+// the raw key bits.  out_fine_off[nbuckets << bits + 1] delimits the digit groups (optional, may be NULL... it is
+// always written into the workspace; pass a buffer to keep it).
+int dpk_radix_pass_seg(const int64_t *keys, const void *vals, int32_t val_bytes, int64_t n, int32_t shift, int32_t bits,
+                       int32_t nbuckets, int32_t nsrc, const int64_t *seg_rows, int64_t *out_keys, void *out_vals,
+                       int64_t *out_fine_off, void *ws, int64_t ws_bytes, dpk_stream_t stream) {
+    if (bits < 1 || bits > 10 || shift < 0 || shift > 63) return fail(DPK_ERR_INVALID, "bad radix digit shift=%d bits=%d", shift, bits);
+    if (n < 0 || n >= ((int64_t)1 << 31)) return fail(DPK_ERR_INVALID, "n=%lld out of range [0, 2^31)", (long long)n);
+    if (nbuckets < 1 || nsrc < 1 || !seg_rows || !out_fine_off || !ws) return fail(DPK_ERR_INVALID, "bad segment description");
+    if (n > 0 && (!keys || !out_keys)) return fail(DPK_ERR_INVALID, "NULL pointer");
+    if (ws_bytes < dpk_radix_pass_seg_workspace_bytes(n, nbuckets, nsrc, bits)) return fail(DPK_ERR_WORKSPACE, "workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t *seg_start = (int64_t *)ws;
+    void *ws2 = (char *)ws + align_up((int64_t)nbuckets * nsrc * 8, 256);
+    DPK_LAUNCH("seg_starts", st, k_seg_starts<<<1, PT_THREADS, 0, st>>>(seg_rows, nsrc, nbuckets, seg_start));
+    PartFn f;
+    f.P = 1 << bits; f.mode = 4; f.magic = 0; f.shift = shift; f.nthr = 0; f.thresholds = nullptr; f.sub_bits = 0;
+    f.row_hash = nullptr;
+    return seg_multisplit(keys, -1, vals, val_bytes, n, f, nbuckets, nsrc, seg_start, seg_rows, out_keys, out_vals,
+                          out_fine_off, ws2, ws_bytes - align_up((int64_t)nbuckets * nsrc * 8, 256), st, true);
 }
 
 // One stable LSD radix pass over int64 key bits: the same multisplit with the

@@ -67,9 +67,78 @@ k_copy_segments(const uint64_t *__restrict__ src_ptrs, const uint64_t *__restric
     }
 }
 
+// One launch instead of ~20 small tensor operations on the host side of every step: from the gathered counts matrix
+// (the MapOutputTracker) to the segment table of this rank's pushes, the rows every rank will receive and the segment
+// matrix of this rank's own partitions.  Single CTA; G <= 64 ranks, any F.
+//   all_counts[S][F]   rows source s holds for fine bucket b (S = G sources, or G * H when a rank sends H groups)
+//   my_src             this rank's source row (rank, or rank * H + group)
+//   per_blk            fine buckets per destination block (ceil(P / G) << sub_bits); destination d owns
+//                      [d * per_blk, min(F, (d + 1) * per_blk))
+//   src0/src1, dst_base[c][G], elem0/elem1   column c (keys, values): address of my bucket-major buffer, of every
+//                      rank's receive buffer, element size
+// Outputs: src_ptrs / dst_ptrs / nbytes [ncols][G] (clamped so that nothing is written past `capacity` rows of a
+// receive buffer), need_over = max(need_over, max_d rows d receives - capacity), seg_out[S][Fown] (Fown = my block).
+__global__ void __launch_bounds__(256)
+k_push_plan(const int64_t *__restrict__ all_counts, int32_t S, int32_t G, int32_t F, int32_t per_blk, int32_t my_src,
+            int32_t my_rank, int32_t ncols, uint64_t src0, uint64_t src1, const uint64_t *__restrict__ dst_base,
+            int32_t elem0, int32_t elem1, int64_t capacity, uint64_t *__restrict__ src_ptrs,
+            uint64_t *__restrict__ dst_ptrs, int64_t *__restrict__ nbytes, long long *__restrict__ need_over,
+            int64_t *__restrict__ seg_out) {
+    extern __shared__ long long s_R[];   // [S][G] rows source s sends to destination d
+    for (int i = threadIdx.x; i < S * G; i += blockDim.x) {
+        const int s = i / G, d = i % G;
+        const int b0 = min(F, d * per_blk), b1 = min(F, (d + 1) * per_blk);
+        long long r = 0;
+        for (int b = b0; b < b1; b++) r += all_counts[(int64_t)s * F + b];
+        s_R[i] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x < G) {
+        const int d = threadIdx.x;
+        long long send_first = 0, dst_first = 0, total = 0;
+        for (int dd = 0; dd < d; dd++) send_first += s_R[my_src * G + dd];
+        for (int s = 0; s < S; s++) {
+            if (s < my_src) dst_first += s_R[s * G + d];
+            total += s_R[s * G + d];
+        }
+        long long rows = s_R[my_src * G + d];
+        const long long room = capacity - dst_first;
+        if (rows > room) rows = room > 0 ? room : 0;
+        for (int c = 0; c < ncols; c++) {
+            const long long e = c ? elem1 : elem0;
+            src_ptrs[c * G + d] = (c ? src1 : src0) + (uint64_t)(send_first * e);
+            dst_ptrs[c * G + d] = dst_base[c * G + d] + (uint64_t)(dst_first * e);
+            nbytes[c * G + d] = rows * e;
+        }
+        if (total > capacity) atomicMax(need_over, total - capacity);
+    }
+    if (seg_out) {
+        const int b0 = min(F, my_rank * per_blk), b1 = min(F, (my_rank + 1) * per_blk), fo = b1 - b0;
+        for (int i = threadIdx.x; i < S * fo; i += blockDim.x) seg_out[i] = all_counts[(int64_t)(i / fo) * F + b0 + i % fo];
+    }
+}
+
 }  // namespace dpk
 
 using namespace dpk;
+
+extern "C" int dpk_push_plan(const int64_t *all_counts, int32_t nsrc, int32_t nranks, int32_t nbuckets, int32_t per_block,
+                             int32_t my_src, int32_t my_rank, int32_t ncols, uint64_t src_keys, uint64_t src_vals,
+                             const uint64_t *dst_base, int32_t key_bytes, int32_t val_bytes, int64_t capacity, uint64_t *src_ptrs,
+                             uint64_t *dst_ptrs, int64_t *nbytes, int64_t *need_over, int64_t *seg_out,
+                             dpk_stream_t stream) {
+    if (nranks < 1 || nranks > 64 || nsrc < nranks || nsrc > 4096 || ncols < 1 || ncols > 2 || per_block < 0)
+        return fail(DPK_ERR_INVALID, "bad push plan shape: %d sources, %d ranks, %d columns", nsrc, nranks, ncols);
+    if (!all_counts || !dst_base || !src_ptrs || !dst_ptrs || !nbytes || !need_over)
+        return fail(DPK_ERR_INVALID, "NULL pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t sh = (size_t)nsrc * nranks * sizeof(long long);
+    if (sh > 48 * 1024) return fail(DPK_ERR_UNSUPPORTED, "push plan: %d x %d sources x ranks exceed shared memory", nsrc, nranks);
+    DPK_LAUNCH("push_plan", st, k_push_plan<<<1, 256, sh, st>>>(all_counts, nsrc, nranks, nbuckets, per_block, my_src, my_rank,
+                                                             ncols, src_keys, src_vals, dst_base, key_bytes, val_bytes, capacity, src_ptrs,
+                                                             dst_ptrs, nbytes, (long long *)need_over, seg_out));
+    return DPK_OK;
+}
 
 extern "C" int dpk_copy_segments(const uint64_t *src_ptrs, const uint64_t *dst_ptrs, const int64_t *nbytes,
                                  int32_t nseg, dpk_stream_t stream) {

@@ -198,6 +198,7 @@ def _run_reduce(splits, P, thr, op, dev):
     vkinds = set(c.val_kind for c in splits if c.n)
     if len(vkinds) > 1:
         raise TypeError("reduceByKey values must be all int or all float on the B200 path")
+    _check_int_sum_range(splits, vkinds, op)
     if kk in (columnar.KEY_I64, columnar.KEY_F64):
         kdt = np.int64 if kk == columnar.KEY_I64 else np.float64
         kc = [torch.from_numpy(c.keys.astype(kdt, copy=False)).to(dev) for c in splits]
@@ -205,19 +206,22 @@ def _run_reduce(splits, P, thr, op, dev):
         if vkinds:
             vdt = torch.int64 if vkinds == {columnar.VAL_I64} else torch.float64
             vc = [v.to(vdt) for v in vc]
-        if vkinds == {columnar.VAL_I64} and op == "sum":
-            # the reference adds Python big ints; the device accumulates in int64.  A cheap sufficient check: if the
-            # sum of |v| over the whole shuffle stays below 2^63 no key's sum can wrap
-            bound = sum(float(np.abs(c.vals.astype(np.float64)).sum()) for c in splits if c.n)
-            if bound >= 2.0 ** 63:
-                raise OverflowError("reduceByKey(add): the values' magnitudes sum to %.3g >= 2^63; int64 accumulation on the "
-                                    "B200 path could wrap where the reference's big ints do not" % bound)
         parts = shuffle.reduce_by_key(kc, vc, P, op, thr)
         for p, k, v in parts:
             res.parts[p] = (k.cpu().numpy().tolist(), v.cpu().numpy().tolist())
         return res
     from . import strings
     return strings.reduce_by_key_bytes(splits, kk, P, thr, op, dev, res)
+
+
+def _check_int_sum_range(splits, vkinds, op):
+    """The reference adds Python big ints; the device accumulates in int64.  A cheap sufficient check on the ingested
+    columns: if the sum of |v| over the whole shuffle stays below 2^63 no key's sum can wrap."""
+    if vkinds == {columnar.VAL_I64} and op == "sum":
+        bound = sum(float(np.abs(c.vals.astype(np.float64)).sum()) for c in splits if c.n)
+        if bound >= 2.0 ** 63:
+            raise OverflowError("reduceByKey(add): the values' magnitudes sum to %.3g >= 2^63; int64 accumulation on the "
+                                "B200 path could wrap where the reference's big ints do not" % bound)
 
 
 def _run_group(splits, P, thr, dev):

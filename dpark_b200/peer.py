@@ -48,7 +48,7 @@ class PeerExchange(object):
         self.capacity = int(capacity)
         self.nbuf = max(1, int(buffers))
         name = self.group.group_name
-        self._keys, self._vals, self._hk, self._hv, self._kb, self._vb = [], [], [], [], [], []
+        self._keys, self._vals, self._hk, self._hv, self._kb, self._vb, self._db = [], [], [], [], [], [], []
         for _ in range(self.nbuf):
             k = symm.empty(self.capacity, dtype=key_dtype, device=self.device)
             v = symm.empty(self.capacity, dtype=val_dtype, device=self.device)
@@ -59,6 +59,7 @@ class PeerExchange(object):
             self._hv.append(hv)
             self._kb.append(torch.tensor([int(p) for p in hk.buffer_ptrs], dtype=torch.int64, device=self.device))
             self._vb.append(torch.tensor([int(p) for p in hv.buffer_ptrs], dtype=torch.int64, device=self.device))
+            self._db.append(torch.cat([self._kb[-1], self._vb[-1]]).contiguous())     # [2][G] for dpk_push_plan
         self.step = 0
         self.side = torch.cuda.Stream(device=self.device, priority=-1)     # pushes that overlap the map side
         self.err = torch.zeros(1, dtype=torch.int64, device=self.device)   # max rows any rank needed beyond capacity
@@ -80,6 +81,10 @@ class PeerExchange(object):
     @property
     def val_base(self):
         return self._vb[self.step % self.nbuf]
+
+    @property
+    def dst_base(self):
+        return self._db[self.step % self.nbuf]
 
     def barrier(self):
         self._hk[self.step % self.nbuf].barrier()
@@ -104,7 +109,7 @@ class PeerExchange(object):
         """Drop the symmetric allocations (all ranks must call it)."""
         if not self._closed:
             self._closed = True
-            self._keys, self._vals, self._hk, self._hv, self._kb, self._vb = [], [], [], [], [], []
+            self._keys, self._vals, self._hk, self._hv, self._kb, self._vb, self._db = [], [], [], [], [], [], []
 
 
 def push_plan(all_counts, blocks, rank):
@@ -144,26 +149,17 @@ def exchange_push(px, mo, need_host_count=False):
     dist.all_gather_into_tensor(all_counts, counts, group=px.group)   # the MapOutputTracker
     all_counts = all_counts.view(G, F)
     blocks = [b << sb for b in owner_blocks(P, G)]
-    send_first, dst_first, rows, recv_total = push_plan(all_counts, blocks, rank)
-    px.note_need(recv_total.max())
-    # clamp what is pushed to the capacity of the destination (an overflow is reported by check(); never write
-    # past a peer's buffer)
-    room = (px.capacity - dst_first).clamp_(min=0)
-    rows = torch.minimum(rows, room)
-    cols = [(mo.keys.data_ptr(), px.key_base, mo.keys.element_size())]
-    if mo.vals is not None:
-        cols.append((mo.vals.data_ptr(), px.val_base, mo.vals.element_size()))
-    src = torch.cat([a + send_first * sz for a, _, sz in cols])
-    dst = torch.cat([base + dst_first * sz for _, base, sz in cols])
-    nby = torch.cat([rows * sz for _, _, sz in cols])
-    nv.copy_segments(src.contiguous(), dst.contiguous(), nby.contiguous())
+    per_block = ((P + G - 1) // G) << sb
+    # one launch: segment table of my pushes (clamped to the receive buffers), capacity flag, my segment matrix
+    src, dst, nby, seg = nv.push_plan(all_counts, G, per_block, rank, rank, mo.keys, mo.vals,
+                                      px.dst_base if mo.vals is not None else px.key_base, px.capacity, px.err)
+    nv.copy_segments(src, dst, nby)
     px.barrier()                                                      # every peer's stores have landed
     b0, b1 = blocks[rank], blocks[rank + 1]
-    seg = all_counts[:, b0:b1].contiguous()
     keys, vals = px.keys, (px.vals if mo.vals is not None else None)
     px.advance()                                                      # the next step writes the other buffer set
     if need_host_count:
-        nrecv = min(int(recv_total[rank].item()), px.capacity)
+        nrecv = min(int(seg.sum().item()), px.capacity)
         return Received(keys[:nrecv], None if vals is None else vals[:nrecv], seg, b0 >> sb, (b1 - b0) >> sb, sb)
     return Received(keys, vals, seg, b0 >> sb, (b1 - b0) >> sb, sb, bound=True)
 

@@ -233,29 +233,43 @@ def sort_by_key_bits(keys, vals, bits=None):
 
 
 def group_side(rx, P, thresholds=None, key_view=None, row_hash=None):
-    """Reduce side of groupByKey (OrderedGroupByDiskHashMerger,
-    dpark/shuffle.py:626-646): stable sort of the received rows by key, then
-    partition-major, then CSR.  rx.keys: int64 key bits (for float keys pass
-    key_view=torch.float64 so that the partition step hashes them as floats; for
-    row-id keys pass row_hash so that the partition step uses the looked-up hash).
-    Returns (group_keys, group_starts, ngroups, values, part_offsets[nparts+1]); group g
-    holds values[group_starts[g] : group_starts[g+1]], groups are partition-major; part_offsets are the
-    value-row offsets of the partitions this rank owns."""
-    if rx.bound:   # the sort sizes its buffers on the host
-        nrecv = int(rx.seg.sum().item())
-        rx = Received(rx.keys[:nrecv], None if rx.vals is None else rx.vals[:nrecv], rx.seg, rx.part_first, rx.nparts,
-                      rx.sub_bits)
-    k, v = sort_by_key_bits(rx.keys, rx.vals)
+    """Reduce side of groupByKey (OrderedGroupByDiskHashMerger, dpark/shuffle.py:626-646): a stable sort of the
+    received rows by key INSIDE every first-level hash bucket (all rows of a key share a bucket, so no pass over the
+    partition id is needed: round 1 sorted the whole buffer by key bits and partitioned it again), then CSR heads.
+
+    The first pass takes the (source rank, bucket) segments as the exchange delivered them and writes bucket-major;
+    the later passes run bucket by bucket (`dpk_radix_pass_seg`), one per 8-bit digit in which any two keys differ.
+    rx.keys: int64 key bits (float keys: their canonical bits).  thresholds / key_view / row_hash are accepted for
+    compatibility and unused (the buckets already are what the partitioner decided on the map side).
+    Returns (group_keys, group_starts, ngroups, values, part_offsets[nparts+1]); group g holds
+    values[group_starts[g] : group_starts[g+1]], groups are partition-major; part_offsets are the value-row offsets of
+    the partitions this rank owns."""
     if row_hash is not None:
-        # keys are representative row ids: partition by the hash of the key they stand for,
-        # carrying the id as payload next to the value is not possible in a (k, v) pair, so
-        # partition (hash, value) and re-derive the ids afterwards from the values (row ids)
         raise NotImplementedError("row-id keys are handled by dpark_b200.grouping")
-    pk = k if key_view is None else k.view(key_view)
-    ok, ov, off = nv.partition(pk, v, P, thresholds)
-    gk, gs, ng = nv.group_heads(ok.view(torch.int64))
-    # offsets of the partitions this rank owns (the others are empty here)
-    return gk, gs, ng, ov, off[rx.part_first:rx.part_first + rx.nparts + 1]
+    dev = rx.keys.device
+    seg = rx.seg.contiguous()
+    if rx.bound:   # the sort sizes its buffers on the host
+        nrecv = int(seg.sum().item())
+        rx = Received(rx.keys[:nrecv], None if rx.vals is None else rx.vals[:nrecv], seg, rx.part_first, rx.nparts,
+                      rx.sub_bits)
+    k, v = rx.keys.view(torch.int64), rx.vals
+    n = int(k.numel())
+    nsrc, F = int(seg.shape[0]), int(seg.shape[1])
+    bucket_rows = seg.sum(0, keepdim=True).contiguous()                 # [1, F]
+    if n > 1:
+        ormask = int(nv.key_or(k).item()) & 0xFFFFFFFFFFFFFFFF          # tiny host read: which digits differ
+        cur = seg
+        for shift in range(0, 64, RADIX_BITS):
+            if (ormask >> shift) & ((1 << RADIX_BITS) - 1):
+                k, v = nv.radix_pass_seg(k, v, shift, RADIX_BITS, cur)
+                cur = bucket_rows
+        if cur is seg and nsrc > 1:                                     # one key only: still make the rows bucket-major
+            k, v = nv.radix_pass_seg(k, v, 0, 1, cur)
+    gk, gs, ng = nv.group_heads(k)
+    off = torch.zeros(rx.nparts + 1, dtype=torch.int64, device=dev)
+    if rx.nparts:
+        torch.cumsum(bucket_rows.view(rx.nparts, -1).sum(1), 0, out=off[1:])
+    return gk, gs, ng, v, off
 
 
 def _world(group=None):

@@ -145,6 +145,18 @@ int dpk_partition_scatter_ptrs(const void *keys, int key_kind, const int64_t *ke
  * and sizes of any alignment (16/8/4/1-byte accesses are chosen per item). */
 int dpk_copy_segments(const uint64_t *src_ptrs, const uint64_t *dst_ptrs, const int64_t *nbytes,
                       int32_t nseg, dpk_stream_t stream);
+/* The MapOutputTracker lookup (dpark/shuffle.py:809-826) for the push: from the gathered counts matrix
+ * all_counts[nsrc][nbuckets] (device) to the segment table dpk_copy_segments takes, in ONE launch.  Destination d owns
+ * the buckets [d * per_block, (d + 1) * per_block); this rank is source row my_src (= my_rank, or my_rank * H + group
+ * when every rank sends H groups of map splits).  My bucket-major key / value columns start at the device addresses
+ * src_keys / src_vals (ncols = 1: keys only), rank d's receive buffer for column c at dst_base[c * nranks + d] (device
+ * array), elements are key_bytes / val_bytes wide.  Writes src_ptrs / dst_ptrs /
+ * nbytes [ncols][nranks] (pushes are clamped to `capacity` rows per receive buffer), *need_over = max(*need_over,
+ * rows the fullest receive buffer lacks) and, if seg_out != NULL, seg_out[nsrc][own buckets] for dpk_combine. */
+int dpk_push_plan(const int64_t *all_counts, int32_t nsrc, int32_t nranks, int32_t nbuckets, int32_t per_block,
+                  int32_t my_src, int32_t my_rank, int32_t ncols, uint64_t src_keys, uint64_t src_vals,
+                  const uint64_t *dst_base, int32_t key_bytes, int32_t val_bytes, int64_t capacity, uint64_t *src_ptrs,
+                  uint64_t *dst_ptrs, int64_t *nbytes, int64_t *need_over, int64_t *seg_out, dpk_stream_t stream);
 
 /* ---- a9: reduce side, DiskHashMerger._merge (dpark/shuffle.py:600-608) ----
  * combined[k] = op(combined[k], v) over the n rows fetched for the nparts reduce
@@ -218,6 +230,15 @@ int dpk_gather_i64(const int64_t *src, const int64_t *idx, int64_t n, int64_t *o
 int dpk_radix_pass(const int64_t *keys, const void *vals, int32_t val_bytes, int64_t n, int32_t shift,
                    int32_t bits, int64_t *out_keys, void *out_vals, void *ws, int64_t ws_bytes,
                    dpk_stream_t stream);
+/* One stable radix pass INSIDE every first-level bucket: input source-major, bucket-major (seg_rows[nsrc][nbuckets]
+ * device int64: what the exchange delivers; nsrc = 1 once the rows are bucket-major), output bucket-major with every
+ * bucket stably split by the digit.  All rows of a key share a bucket, so after the passes over the differing digits
+ * every bucket is sorted by key and no pass over the partition id is needed (OrderedGroupByDiskHashMerger,
+ * dpark/shuffle.py:626-646).  out_fine_off[(nbuckets << bits) + 1] receives the digit-group boundaries. */
+int64_t dpk_radix_pass_seg_workspace_bytes(int64_t n, int32_t nbuckets, int32_t nsrc, int32_t bits);
+int dpk_radix_pass_seg(const int64_t *keys, const void *vals, int32_t val_bytes, int64_t n, int32_t shift,
+                       int32_t bits, int32_t nbuckets, int32_t nsrc, const int64_t *seg_rows, int64_t *out_keys,
+                       void *out_vals, int64_t *out_fine_off, void *ws, int64_t ws_bytes, dpk_stream_t stream);
 int64_t dpk_group_heads_workspace_bytes(int64_t n);
 int dpk_group_heads(const int64_t *sorted_keys, int64_t n, int64_t *out_keys, int64_t *out_starts,
                     int64_t *out_ngroups, void *ws, int64_t ws_bytes, dpk_stream_t stream);

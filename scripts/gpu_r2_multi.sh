@@ -31,6 +31,7 @@ for extra in "$@"; do
     c3) run c3 --config c3 --steps 3 --e2e-steps 1 ;;
     c3small) run c3small --config c3 --rows-per-gpu 20000000 --steps 3 --e2e-steps 1 ;;
     nccl) run c2nccl --exchange nccl --no-e2e ;;
+    pcie) echo "== pcie probe, all ranks at once"; timeout 300 $TR scripts/pcie_probe_multi.py 2>&1 | grep -E "alone|both" ;;
     overlap) run c2ov2 --overlap-push 2 --no-e2e ;;
     spmd) echo "== spmd_check"; timeout 900 $TR scripts/spmd_check.py > gpurun_out/spmd_check_n$N.log 2>&1; echo "rc=$?"; grep -E "^wc|^pagerank|Error|error" gpurun_out/spmd_check_n$N.log | head ;;
   esac

@@ -126,3 +126,34 @@ def test_map_side_combine_gives_the_same_partitions(op):
     mo = shuffle.map_side([torch.from_numpy(k).cuda()], [torch.from_numpy(v).cuda()], P, sub_bits=2, unordered=True)
     mc = shuffle.combine_map_output(mo, op)
     assert int(mc.keys.numel()) == len(np.unique(k)) and int(mc.offsets[-1]) == len(np.unique(k))
+
+
+@pytest.mark.parametrize("G,P,sb,H", [(2, 8, 0, 1), (3, 5, 1, 1), (8, 64, 3, 1), (4, 1, 3, 1), (8, 5, 2, 2)])
+def test_push_plan_kernel_equals_the_tensor_plan(G, P, sb, H):
+    """dpk_push_plan (one launch) against peer.push_plan (the tensor arithmetic the CPU tests pin to the alltoallv
+    layout): segment table of every source row, clamping at the receive-buffer capacity, the capacity flag and the
+    segment matrix of the rank's own buckets."""
+    from dpark_b200 import _native as nv
+    from dpark_b200 import peer, shuffle
+    rng = np.random.default_rng(G * 100 + P)
+    F = P << sb
+    S = G * H
+    counts = torch.from_numpy(rng.integers(0, 50, (S, F), dtype=np.int64)).cuda()
+    blocks = [b << sb for b in shuffle.owner_blocks(P, G)]
+    per_block = ((P + G - 1) // G) << sb
+    keys = torch.zeros(int(counts.sum()) + 8, dtype=torch.int64, device="cuda")
+    vals = torch.zeros(int(counts.sum()) + 8, dtype=torch.int32, device="cuda")
+    dst_base = torch.arange(1, 2 * G + 1, dtype=torch.int64, device="cuda") * (1 << 40)
+    for cap in (10 ** 9, int(counts.sum(0).max()) // 2 + 1):
+        for rank in range(G):
+            for h in range(H):
+                me = rank * H + h
+                need = torch.zeros(1, dtype=torch.int64, device="cuda")
+                src, dst, nby, seg = nv.push_plan(counts, G, per_block, me, rank, keys, vals, dst_base, cap, need)
+                sf, df, rows, tot = peer.push_plan(counts, blocks, me)
+                rows = torch.minimum(rows, (cap - df).clamp(min=0))
+                assert torch.equal(src[:G], keys.data_ptr() + sf * 8) and torch.equal(src[G:], vals.data_ptr() + sf * 4)
+                assert torch.equal(dst[:G], dst_base[:G] + df * 8) and torch.equal(dst[G:], dst_base[G:] + df * 4)
+                assert torch.equal(nby[:G], rows * 8) and torch.equal(nby[G:], rows * 4)
+                assert int(need) == max(0, int(tot.max()) - cap)
+                assert torch.equal(seg, counts[:, blocks[rank]:blocks[rank + 1]])

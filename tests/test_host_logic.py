@@ -392,3 +392,17 @@ def test_tuple_and_none_keys_become_identity_bytes_with_one_shape():
         columnar.ingest_pairs([((1, 2), 1), ((1, 2, 3), 2)])
     with pytest.raises(TypeError):
         columnar.ingest_pairs([(None, 1), (3, 2)])
+
+
+def test_int_sums_that_could_wrap_are_refused_and_float_zero_keys_are_canonical():
+    """int64 accumulation must not wrap silently where the reference's big ints would not; -0.0 and
+    0.0 are one key on every path (the group-by path used the raw bits)."""
+    from dpark_b200 import columnar, engine
+    big = columnar.ingest_pairs([(1, 2 ** 62), (2, 2 ** 62), (1, 5)])
+    with pytest.raises(OverflowError):
+        engine._check_int_sum_range([big], {columnar.VAL_I64}, "sum")
+    engine._check_int_sum_range([big], {columnar.VAL_I64}, "max")          # only sums can wrap
+    ok = columnar.ingest_pairs([(1, 2 ** 40), (2, -2 ** 40)])
+    engine._check_int_sum_range([ok], {columnar.VAL_I64}, "sum")
+    c = columnar.ingest_pairs([(-0.0, 1), (0.0, 2)])
+    assert np.signbit(c.keys).tolist() == [False, False]
