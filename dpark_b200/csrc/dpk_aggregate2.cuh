@@ -219,7 +219,19 @@ k_smem_aggregate2(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, 
                   const int64_t *__restrict__ part_offsets, KeyT *__restrict__ out_keys,
                   int64_t *__restrict__ out_vals, long long *__restrict__ out_counts,
                   unsigned long long *__restrict__ fb_state, int *__restrict__ work_counter,
-                  int *__restrict__ part_err, const int *__restrict__ bucket_list, const int *__restrict__ bucket_count) {
+                  int *__restrict__ part_err, const int *__restrict__ bucket_list, const int *__restrict__ bucket_count,
+                  long long *__restrict__ phase_cycles) {
+    // phase_cycles != nullptr (dpk_set_option("agg_timing", 1), debugging): thread 0 adds the cycles between the
+    // phase boundaries of every fast-path bucket: [0] top..rows loaded+staged (S), [1] S..inserts done (B),
+    // [2] B..output range known (D), [3] D..write-out issued, [4] write-out..next top (A), [5] buckets
+    long long tstamp = 0;
+    auto stamp = [&](int k) {
+        if (phase_cycles != nullptr && threadIdx.x == 0) {
+            const long long now = clock64();
+            if (k >= 0) atomicAdd(reinterpret_cast<unsigned long long *>(&phase_cycles[k]), (unsigned long long)(now - tstamp));
+            tstamp = now;
+        }
+    };
     // bucket_list != nullptr (CURSOR only): the tickets index a list of fine buckets (the oversized ones
     // k_smem_aggregate3 left behind) instead of all nfine buckets
     const int nwork = bucket_list ? *bucket_count : nfine;
@@ -286,6 +298,7 @@ k_smem_aggregate2(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, 
     }
     for (int it = 0;; it++) {
         __syncthreads();                                            // (A) also: previous write-out and tag clear finished
+        stamp(it ? 4 : -1);
         const int fb = sh.next_fb[it & 1];
         if (fb >= nfine) break;
         const int64_t r0 = sh.next_r0[it & 1], r1 = sh.next_r1[it & 1];
@@ -327,11 +340,13 @@ k_smem_aggregate2(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, 
             stage(r0, n, 0, std::integral_constant<int, AG2_ITEMS>(), prefetch_ticket);
             prefetch_range();
             __syncthreads();                                        // (S) rows staged
+            stamp(0);
             const unsigned mine = BATCHED ? ag2_insert_batched<AccT, AG2_ITEMS>(n, op, tag_base, key_base, acc_base, s_acc, offs, &lane_cnt)
                                           : ag2_insert<AccT, false, AG2_ITEMS>(0, n, 1, 0, op, tag_base, key_base, acc_base, s_acc, offs, &lane_cnt, slots);
             if (lane < AG2_ITEMS) sh.wcnt[lane * AG2_WARPS + warp] = lane_cnt;
             if (CURSOR) publish_range();
             __syncthreads();                                        // (B) inserts done, claim counts written
+            stamp(1);
             if (warp == 0) {
                 scan_claims();
                 __syncwarp();
@@ -352,6 +367,7 @@ k_smem_aggregate2(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, 
             }
             if (!CURSOR) publish_range();
             __syncthreads();                                        // (D) offsets known
+            stamp(2);
             const int64_t obase = pbase + (int64_t)sh.excl;
 #pragma unroll
             for (int j = 0; j < AG2_ITEMS; j++) {
@@ -363,6 +379,8 @@ k_smem_aggregate2(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, 
                 }
             }
             if (warp == 0) clear_tags();
+            stamp(3);
+            if (phase_cycles != nullptr && threadIdx.x == 0) atomicAdd(reinterpret_cast<unsigned long long *>(&phase_cycles[5]), 1ull);
             continue;  // barrier (A) of the next iteration orders the reads and the clear before the next staging
         }
 

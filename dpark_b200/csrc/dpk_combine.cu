@@ -446,10 +446,11 @@ int g_reduce_impl = 2;  // dpk_set_option("reduce_impl", 0|1|2)
 
 constexpr int AG_MAX_SB2 = 10;       // at most 1024 fine buckets per first-level bucket
 int g_agg_wide = 1;
-int g_agg_ctas = 3;
+int g_agg_ctas = 4;                  // measured: 4 resident CTAs (64 registers, some spills) 1.58 ms vs 1.72 ms at 3
+int g_agg_timing = 0;
 int g_agg_cursor = 1;
 int g_agg_pipe = 0;                  // dpk_set_option("agg_pipe"): 1 = k_smem_aggregate3 (rows prefetched into registers), 2 = same, 2 CTAs per SM
-int g_agg_batched = 1;
+int g_agg_batched = 0;               // measured: the four-rows-in-flight insert executes 40 % more instructions (spills) -> 2.22 ms vs 1.72 ms
 int g_agg_impl = 1;                  // dpk_set_option("agg_impl"): 1 = k_smem_aggregate2 (row-index tags), 0 = round-1 kernel
 int g_agg_target_rows = 2048;        // rows per fine bucket the split aims for (table load <= 0.5)
 
@@ -509,14 +510,22 @@ static int dispatch_op(const Ctx &c) {
         if (g_agg_impl == 1) {
             // dpk_set_option("agg_ctas"): resident CTAs per SM the kernel is compiled for (3: 80 registers, 4: 64)
             // dpk_set_option("agg_cursor"): 1 = output ranges reserved with one atomicAdd per fine bucket, 0 = chained look-back
-            // dpk_set_option("agg_batched"): 1 = four rows per thread in flight in the insert phase (default), 0 = probe loop per row
+            // dpk_set_option("agg_batched"): 1 = four rows per thread in flight in the insert phase, 0 (default) = probe loop per row
             auto agg2 = k_smem_aggregate2<KeyT, ValT, AccT, 3, true, true>;
             if (g_agg_cursor && g_agg_batched) agg2 = g_agg_ctas == 4 ? k_smem_aggregate2<KeyT, ValT, AccT, 4, true, true> : k_smem_aggregate2<KeyT, ValT, AccT, 3, true, true>;
             else if (g_agg_cursor) agg2 = g_agg_ctas == 4 ? k_smem_aggregate2<KeyT, ValT, AccT, 4, true, false> : k_smem_aggregate2<KeyT, ValT, AccT, 3, true, false>;
+            // (the batched variants are compiled for 3 CTAs per SM only when batched: see above)
             else agg2 = k_smem_aggregate2<KeyT, ValT, AccT, 3, false, false>;
             const int smem2 = AG2_TAGS * 4 + AG2_CAP * 16;
             DPK_CUDA_TRY(cudaFuncSetAttribute(agg2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
             DPK_CUDA_TRY(cudaMemsetAsync(c.part_err, 0, (size_t)(c.nparts + 2) * 4, c.st));
+            long long *timing = nullptr;
+            if (g_agg_timing) {
+                static long long *d_timing = nullptr;
+                if (!d_timing) DPK_CUDA_TRY(cudaMalloc(&d_timing, 64));
+                DPK_CUDA_TRY(cudaMemsetAsync(d_timing, 0, 64, c.st));
+                timing = d_timing;
+            }
             if (g_agg_pipe && g_agg_cursor) {
                 // register-pipelined fast path for the buckets that fit one window; the oversized ones go to a list
                 // (two ints behind the per-partition error flags: list length, list-mode work counter) and are merged by
@@ -536,12 +545,21 @@ static int dispatch_op(const Ctx &c) {
                 DPK_LAUNCH("smem_aggregate_big", c.st, aggb<<<sm_count(), AG2_THREADS, smem2, c.st>>>(
                     rekeys, revals, c.op, c.fine_off, nfine, (1 << c.f.sub_bits) * S2, c.part_off,
                     (KeyT *)c.out_keys, c.out_vals, (long long *)c.out_counts, c.fb_state, list_counter, c.part_err,
-                    big_list, big_count));
+                    big_list, big_count, nullptr));
             } else {
             DPK_LAUNCH("smem_aggregate", c.st, agg2<<<grid, AG2_THREADS, smem2, c.st>>>(
                 rekeys, revals, c.op, c.fine_off, nfine, (1 << c.f.sub_bits) * S2, c.part_off,
                 (KeyT *)c.out_keys, c.out_vals, (long long *)c.out_counts, c.fb_state, c.bucket_counter, c.part_err,
-                nullptr, nullptr));
+                nullptr, nullptr, timing));
+            if (timing) {   // debugging aid: synchronises and prints the per-phase averages of this launch
+                long long h[8];
+                DPK_CUDA_TRY(cudaMemcpyAsync(h, timing, sizeof(h), cudaMemcpyDeviceToHost, c.st));
+                DPK_CUDA_TRY(cudaStreamSynchronize(c.st));
+                const double nb = h[5] ? (double)h[5] : 1.0;
+                fprintf(stderr, "agg_timing: %lld buckets; cycles per bucket: load+stage %.0f | insert %.0f | reserve %.0f | write-out %.0f | "
+                        "to next top %.0f | total %.0f\n", h[5], h[0] / nb, h[1] / nb, h[2] / nb, h[3] / nb, h[4] / nb,
+                        (h[0] + h[1] + h[2] + h[3] + h[4]) / nb);
+            }
             }
             if (g_agg_cursor)
                 DPK_LAUNCH("agg_finalize", c.st, k_agg_finalize<<<1, 256, 0, c.st>>>(c.part_err, (long long *)c.out_counts, c.nparts));
@@ -645,6 +663,10 @@ int dpk_set_option(const char *name, int64_t value) {
         g_agg_batched = (int)value;
         return DPK_OK;
     }
+    if (strcmp(name, "agg_timing") == 0) {
+        g_agg_timing = value != 0;
+        return DPK_OK;
+    }
     if (strcmp(name, "agg_pipe") == 0) {
         if (value < 0 || value > 2) return fail(DPK_ERR_INVALID, "agg_pipe must be 0, 1 or 2");
         g_agg_pipe = (int)value;
@@ -673,6 +695,10 @@ int dpk_set_option(const char *name, int64_t value) {
     if (strcmp(name, "scatter_threads") == 0) {
         if (value != 256 && value != 512 && value != 1024) return fail(DPK_ERR_INVALID, "scatter_threads must be 256, 512 or 1024");
         g_scatter_threads = (int)value;
+        return DPK_OK;
+    }
+    if (strcmp(name, "scatter_seg_wide") == 0) {
+        g_scatter_seg_wide = value != 0;
         return DPK_OK;
     }
     if (strcmp(name, "scatter_bulk") == 0) {

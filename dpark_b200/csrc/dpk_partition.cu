@@ -42,6 +42,7 @@ int g_scatter_items = 16;
 // shared-memory ranking + TMA bulk stores of the staged bucket runs); 0 = the round-1 kernel (A/B switch)
 int g_scatter_bulk = 1;
 int g_scatter_threads = 512;
+int g_scatter_seg_wide = 1;   // dpk_set_option("scatter_seg_wide"): segmented launches use the 1024-thread / 8192-row form
 
 // Segmented mode (second-level split on the reduce side): the grid runs over a
 // device-resident chunk table instead of equal row ranges; every chunk lies inside
@@ -717,6 +718,7 @@ static int launch_scatter_bulk(const void *keys, const void *vals, int64_t n, co
     // dpk_set_option("scatter_threads"): 512 (default; 8 rows per thread, 4096-row tiles, 2 CTAs per SM), 256 (16 rows
     // per thread) or 1024 (8192-row tiles, 1 CTA per SM)
     int nt = g_scatter_threads;
+    if (nt == 512 && pl.seg.cbeg != nullptr && g_scatter_seg_wide) nt = 1024;   // second-level split: measured 0.79 vs 0.83 ms
     if (nt == 1024 && bulk_smem((int)sizeof(KeyT), vb, f.nbuckets(), 8192).total > 220 * 1024) nt = 512;
     BulkSmem lay = bulk_smem((int)sizeof(KeyT), vb, f.nbuckets(), nt == 1024 ? 8192 : PT_TILE);
     const int fmode = f.mode == 5 ? 2 : ((f.mode == 0 || f.mode == 1) ? 1 : 0);

@@ -196,8 +196,10 @@ int dpk_combine(const void *keys, int key_kind, const int64_t *key_aux, const vo
  *   "agg_cursor"      1 (default) a fine bucket reserves its output range with one atomicAdd on the
  *                     partition's count (partitions are sets: any order); 0 = chained scan with
  *                     decoupled look-back (deterministic order)
- *   "agg_batched"     1 (default) four rows per thread in flight in the insert phase; 0 = probe loop per row
- *   "agg_ctas"        3 (default) or 4 resident CTAs per SM the merge kernel is compiled for
+ *   "agg_batched"     1 = four rows per thread in flight in the insert phase; 0 (default) = probe loop per row
+ *   "agg_ctas"        4 (default) or 3 resident CTAs per SM the merge kernel is compiled for
+ *   "agg_pipe"        0 (default); 1 = k_smem_aggregate3 (rows stay in registers, next bucket prefetched: faster on
+ *                     duplicate-heavy data, slower on mostly-distinct keys)
  *   "agg_wide"        round-1 kernel only: 1 (default) claim a table slot and deposit the first value with
  *                     one 128-bit shared-memory CAS; 0 = 64-bit key CAS, then an atomic on the accumulator
  *   "agg_target_rows" rows per fine bucket the second-level split aims for (default 2048)
@@ -206,7 +208,8 @@ int dpk_combine(const void *keys, int key_kind, const int64_t *key_aux, const vo
  *   "scatter_bulk"    1 (default) unordered multisplits (reduceByKey paths, second-level split) run
  *                     k_part_scatter_bulk: one shared atomic per row for the rank, bucket runs leave the
  *                     staged tile through cp.async.bulk (TMA, SASS UBLKCP); 0 = the round-1 kernel
- *   "scatter_threads" 512 (default) or 256 threads per CTA of the bulk kernel (8 or 16 rows per thread)
+ *   "scatter_threads" 512 (default), 256 or 1024 threads per CTA of the bulk kernel (1024: 8192-row tiles)
+ *   "scatter_seg_wide" 1 (default): the segmented (second-level) launches use the 1024-thread form
  *   "scatter_items"   round-1 kernel only: 16 (default) or 8 rows per thread and tile */
 int dpk_set_option(const char *name, int64_t value);
 
