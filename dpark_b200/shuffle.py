@@ -98,6 +98,22 @@ class MapOutput(object):
         self.keys, self.vals, self.offsets, self.P, self.sub_bits = keys, vals, offsets, P, sub_bits
 
 
+def _as_one(chunks):
+    """One tensor spanning `chunks` if they are consecutive contiguous slices of the same storage, else None."""
+    first = chunks[0]
+    if first is None or not first.is_contiguous():
+        return None
+    base = first.untyped_storage().data_ptr()
+    ptr, total = first.data_ptr(), 0
+    for c in chunks:
+        if (c is None or c.dtype != first.dtype or c.dim() != 1 or not c.is_contiguous() or c.data_ptr() != ptr
+                or c.untyped_storage().data_ptr() != base):
+            return None
+        ptr += c.numel() * c.element_size()
+        total += c.numel()
+    return torch.empty(0, dtype=first.dtype, device=first.device).set_(first.untyped_storage(), first.storage_offset(), (total,))
+
+
 def map_side(key_chunks, val_chunks, P, thresholds=None, prehashed=False, sub_bits=0, row_hash=None,
              unordered=False):
     """Hash-partition all local map splits into ONE bucket-major buffer.
@@ -106,6 +122,13 @@ def map_side(key_chunks, val_chunks, P, thresholds=None, prehashed=False, sub_bi
     order).  Rows of a bucket are ordered by (map split, position) -- the order
     OrderedGroupByDiskHashMerger produces (dpark/shuffle.py:626-646)."""
     F = P << sub_bits
+    if len(key_chunks) > 1:
+        # map splits that are consecutive slices of one buffer (the usual case: a batch copied to the device and
+        # cut into map tasks) are partitioned in ONE launch pair: rows of a bucket stay in (split, position) order
+        # because that IS the buffer's row order; 2 launches instead of 2 per split, no per-split tails
+        whole_k, whole_v = _as_one(key_chunks), (_as_one(val_chunks) if val_chunks[0] is not None else None)
+        if whole_k is not None and (val_chunks[0] is None or whole_v is not None) and whole_k.numel() < (1 << 31):
+            key_chunks, val_chunks = [whole_k], [whole_v]
     if len(key_chunks) == 1:
         k, v, off = nv.partition(key_chunks[0], val_chunks[0], P, thresholds, prehashed, sub_bits, row_hash, unordered)
         return MapOutput(k, v, off, P, sub_bits)

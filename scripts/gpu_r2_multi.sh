@@ -26,9 +26,10 @@ run c2
 shift
 for extra in "$@"; do
   case $extra in
-    c4) run c4 --config c4 --e2e-steps 1 ;;
+    c4) run c4 --config c4 --steps 5 --e2e-steps 1 --e2e-depth 2 ;;
+    c4mc) run c4mc --config c4 --steps 5 --map-combine --no-e2e ;;
     c4small) run c4small --config c4 --rows-per-gpu 100000000 --e2e-steps 1 ;;
-    c3) run c3 --config c3 --steps 3 --e2e-steps 1 ;;
+    c3) run c3 --config c3 --steps 3 --e2e-steps 1 --e2e-depth 2 ;;
     c3small) run c3small --config c3 --rows-per-gpu 20000000 --steps 3 --e2e-steps 1 ;;
     nccl) run c2nccl --exchange nccl --no-e2e ;;
     pcie) echo "== pcie probe, all ranks at once"; timeout 300 $TR scripts/pcie_probe_multi.py 2>&1 | grep -E "alone|both" ;;

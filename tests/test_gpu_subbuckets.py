@@ -195,3 +195,32 @@ def test_slot_claim_variants_agree_with_the_oracle(wide, op, vkind):
             assert np.array_equal(gv[o1], want[p][1][o2])
         else:   # float sums: accumulation order differs; tolerance 1e-9 * sum|v|
             assert np.allclose(gv[o1], want[p][1][o2], rtol=0, atol=1e-9 * np.abs(v).sum())
+
+
+@pytest.mark.parametrize("unordered", [False, True])
+def test_consecutive_slices_are_partitioned_in_one_launch_with_the_same_result(unordered):
+    """Map splits that are consecutive slices of one buffer take ONE count + scatter launch pair (shuffle._as_one);
+    the bucket-major output must equal the per-split path's: bit-identical when stable, the same rows per bucket when
+    the order inside a bucket is free."""
+    from dpark_b200 import shuffle
+    rng = np.random.default_rng(3)
+    n, P, sb, M = 300_001, 6, 3, 5
+    k = torch.from_numpy(rng.integers(-10 ** 6, 10 ** 6, n, dtype=np.int64)).cuda()
+    v = torch.arange(n, dtype=torch.int64, device="cuda")
+    per = -(-n // M)
+    kc = [k[i * per:min(n, (i + 1) * per)] for i in range(M)]
+    vc = [v[i * per:min(n, (i + 1) * per)] for i in range(M)]
+    assert shuffle._as_one(kc) is not None
+    before = nv().launch_count()
+    one = shuffle.map_side(kc, vc, P, None, False, sb, unordered=unordered)
+    launches_one = nv().launch_count() - before
+    sep = shuffle.map_side([c.clone() for c in kc], [c.clone() for c in vc], P, None, False, sb, unordered=unordered)
+    assert launches_one <= 4 and torch.equal(one.offsets, sep.offsets)
+    if not unordered:
+        assert torch.equal(one.keys, sep.keys) and torch.equal(one.vals, sep.vals)
+    else:
+        off = one.offsets.cpu().tolist()
+        for b in range(P << sb):
+            a, e = off[b], off[b + 1]
+            assert torch.equal(one.vals[a:e].sort().values, sep.vals[a:e].sort().values)
+            assert torch.equal(one.keys[a:e], k[one.vals[a:e]])
