@@ -452,7 +452,9 @@ int g_agg_cursor = 1;
 int g_agg_pipe = 0;                  // dpk_set_option("agg_pipe"): 1 = k_smem_aggregate3 (rows prefetched into registers), 2 = same, 2 CTAs per SM
 int g_agg_batched = 0;               // measured: the four-rows-in-flight insert executes 40 % more instructions (spills) -> 2.22 ms vs 1.72 ms
 int g_agg_impl = 1;                  // dpk_set_option("agg_impl"): 1 = k_smem_aggregate2 (row-index tags), 0 = round-1 kernel
-int g_agg_target_rows = 2048;        // rows per fine bucket the split aims for (table load <= 0.5)
+int g_agg_target_rows = 1536;        // rows per fine bucket the split aims for: the average must stay well below the
+                                     // 2048-row window (duplicate-heavy keys widen the spread: C4 at 1907 rows on
+                                     // average sent 29 % of its buckets through the multi-window path)
 
 static inline int choose_sb2(int64_t n, int32_t F) {
     int sb2 = 0;
@@ -530,7 +532,8 @@ static int dispatch_op(const Ctx &c) {
                 // register-pipelined fast path for the buckets that fit one window; the oversized ones go to a list
                 // (two ints behind the per-partition error flags: list length, list-mode work counter) and are merged by
                 // the staged kernel in a second launch
-                auto agg3 = g_agg_pipe == 2 ? k_smem_aggregate3<KeyT, ValT, AccT, 2> : k_smem_aggregate3<KeyT, ValT, AccT, 3>;
+                auto agg3 = g_agg_pipe == 2 ? k_smem_aggregate3<KeyT, ValT, AccT, 2, false>
+                          : (g_agg_batched ? k_smem_aggregate3<KeyT, ValT, AccT, 3, true> : k_smem_aggregate3<KeyT, ValT, AccT, 3, false>);
                 const int smem3 = AG2_TAGS * 4 + AG2_CAP * 8;
                 DPK_CUDA_TRY(cudaFuncSetAttribute(agg3, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
                 int *big_count = c.part_err + c.nparts, *list_counter = c.part_err + c.nparts + 1;
