@@ -33,6 +33,7 @@ constexpr int AG2_TAGS = 4096;
 constexpr int AG2_CAP = 2048;                       // staged rows per window
 constexpr int AG2_ITEMS = AG2_CAP / AG2_THREADS;    // 8 rows per thread and window
 constexpr int AG2_GEN_ITEMS = 4;                    // general path: rows per thread and window (register pressure)
+constexpr uint32_t AG2_IDX_MASK = 0xfffu;            // low tag bits: staged row index + 1 (<= AG2_CAP = 2^11)
 constexpr int AG2_MINW = 256;                       // a window smaller than this is not worth a round: split the pass
 constexpr int AG2_MAX_M = 1 << 16;                  // hash-disjoint passes use hash bits 12..27
 constexpr int AG2_STACK = 40;
@@ -87,19 +88,25 @@ __device__ __forceinline__ unsigned ag2_insert(int lo, int hi, int m, int r, int
             const uint32_t hs = slot_hash32((uint64_t)k);
             if (m == 1 || (int)((hs >> 12) & (uint32_t)(m - 1)) == r) {
                 uint32_t h = hs & (AG2_TAGS - 1);
+                // tag = 20 fingerprint bits of the slot hash | staged row index + 1: a slot owned by another key is
+                // recognised from the tag alone (no key load, no 64-bit compare) except for one in 2^20 collisions
+                const uint32_t fp = hs & ~(uint32_t)AG2_IDX_MASK;
                 for (;;) {
                     uint32_t t = sm_ld_u32(tag_base + h * 4u);
                     if (t == 0u) {
-                        t = sm_cas_u32(tag_base + h * 4u, 0u, (uint32_t)idx + 1u);
+                        t = sm_cas_u32(tag_base + h * 4u, 0u, fp | ((uint32_t)idx + 1u));
                         if (t == 0u) { claimed = true; break; }
                     }
-                    if (sm_ld_s64(key_base + (t - 1u) * 8u) == k) {   // a row of the same key owns the slot: add into its accumulator
-                        const long long mv = sm_ld_s64(acc_base + (uint32_t)idx * 8u);
-                        if constexpr (std::is_same<AccT, double>::value)
-                            sm_apply<double>(op, acc_base + (t - 1u) * 8u, s_acc + (t - 1u), __longlong_as_double(mv));
-                        else
-                            sm_apply<int64_t>(op, acc_base + (t - 1u) * 8u, s_acc + (t - 1u), (int64_t)mv);
-                        break;
+                    if ((t & ~(uint32_t)AG2_IDX_MASK) == fp) {
+                        const uint32_t o = (t & AG2_IDX_MASK) - 1u;
+                        if (sm_ld_s64(key_base + o * 8u) == k) {   // a row of the same key owns the slot: add into its accumulator
+                            const long long mv = sm_ld_s64(acc_base + (uint32_t)idx * 8u);
+                            if constexpr (std::is_same<AccT, double>::value)
+                                sm_apply<double>(op, acc_base + o * 8u, s_acc + o, __longlong_as_double(mv));
+                            else
+                                sm_apply<int64_t>(op, acc_base + o * 8u, s_acc + o, (int64_t)mv);
+                            break;
+                        }
                     }
                     h = (h + 1u) & (AG2_TAGS - 1);
                 }
@@ -144,8 +151,13 @@ __device__ __forceinline__ unsigned ag2_insert_batched(int n, int op, uint32_t t
             const int idx = (g + u) * AG2_THREADS + (int)threadIdx.x;
             k[u] = idx < n ? sm_ld_s64(key_base + (uint32_t)idx * 8u) : 0ll;
         }
+        uint32_t fpb[4];
 #pragma unroll
-        for (int u = 0; u < 4; u++) h[u] = slot_hash32((uint64_t)k[u]) & (AG2_TAGS - 1);
+        for (int u = 0; u < 4; u++) {   // (slot hash, fingerprint)
+            const uint32_t hs = slot_hash32((uint64_t)k[u]);
+            h[u] = hs & (AG2_TAGS - 1);
+            fpb[u] = hs & ~(uint32_t)AG2_IDX_MASK;
+        }
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             const int idx = (g + u) * AG2_THREADS + (int)threadIdx.x;
@@ -156,7 +168,7 @@ __device__ __forceinline__ unsigned ag2_insert_batched(int n, int op, uint32_t t
             const int idx = (g + u) * AG2_THREADS + (int)threadIdx.x;
             claimed[u] = false;
             if (t[u] == 0u) {
-                t[u] = sm_cas_u32(tag_base + h[u] * 4u, 0u, (uint32_t)idx + 1u);
+                t[u] = sm_cas_u32(tag_base + h[u] * 4u, 0u, fpb[u] | ((uint32_t)idx + 1u));
                 claimed[u] = t[u] == 0u;
             }
         }
@@ -167,16 +179,19 @@ __device__ __forceinline__ unsigned ag2_insert_batched(int n, int op, uint32_t t
                 uint32_t hh = h[u], tt = t[u];
                 for (;;) {
                     if (tt == 0u) {
-                        tt = sm_cas_u32(tag_base + hh * 4u, 0u, (uint32_t)idx + 1u);
+                        tt = sm_cas_u32(tag_base + hh * 4u, 0u, fpb[u] | ((uint32_t)idx + 1u));
                         if (tt == 0u) { claimed[u] = true; break; }
                     }
-                    if (sm_ld_s64(key_base + (tt - 1u) * 8u) == k[u]) {
-                        const long long mv = sm_ld_s64(acc_base + (uint32_t)idx * 8u);
-                        if constexpr (std::is_same<AccT, double>::value)
-                            sm_apply<double>(op, acc_base + (tt - 1u) * 8u, s_acc + (tt - 1u), __longlong_as_double(mv));
-                        else
-                            sm_apply<int64_t>(op, acc_base + (tt - 1u) * 8u, s_acc + (tt - 1u), (int64_t)mv);
-                        break;
+                    if ((tt & ~(uint32_t)AG2_IDX_MASK) == fpb[u]) {
+                        const uint32_t o = (tt & AG2_IDX_MASK) - 1u;
+                        if (sm_ld_s64(key_base + o * 8u) == k[u]) {
+                            const long long mv = sm_ld_s64(acc_base + (uint32_t)idx * 8u);
+                            if constexpr (std::is_same<AccT, double>::value)
+                                sm_apply<double>(op, acc_base + o * 8u, s_acc + o, __longlong_as_double(mv));
+                            else
+                                sm_apply<int64_t>(op, acc_base + o * 8u, s_acc + o, (int64_t)mv);
+                            break;
+                        }
                     }
                     hh = (hh + 1u) & (AG2_TAGS - 1);
                     tt = sm_ld_u32(tag_base + hh * 4u);
@@ -212,7 +227,7 @@ __device__ __forceinline__ uint32_t ag2_slot(const uint32_t (&slots)[3], int j) 
 // kernel's stall samples sat at the barrier behind it, ~78 polls per bucket -- and widening the window to 256
 // predecessors made it worse; the atomic costs a fixed L2 round trip, no waiting on other CTAs, and lifts the
 // in-order requirement, so the next ticket and its row range are prefetched a bucket ahead.
-template <typename KeyT, typename ValT, typename AccT, int MINB, bool CURSOR, bool BATCHED>
+template <typename KeyT, typename ValT, typename AccT, int MINB, bool CURSOR, bool BATCHED, bool FAST_ONLY = false>
 __global__ void __launch_bounds__(AG2_THREADS, MINB)
 k_smem_aggregate2(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, int op,
                   const int64_t *__restrict__ fine_off, int32_t nfine, int32_t fine_per_part,
@@ -220,7 +235,10 @@ k_smem_aggregate2(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, 
                   int64_t *__restrict__ out_vals, long long *__restrict__ out_counts,
                   unsigned long long *__restrict__ fb_state, int *__restrict__ work_counter,
                   int *__restrict__ part_err, const int *__restrict__ bucket_list, const int *__restrict__ bucket_count,
-                  long long *__restrict__ phase_cycles) {
+                  long long *__restrict__ phase_cycles, int *__restrict__ big_list = nullptr, int *__restrict__ big_count = nullptr) {
+    // FAST_ONLY (CURSOR only): this instance contains the one-window path alone -- the general path's live state cost
+    // the hot loop registers (r02f: 244 B of spills per thread at 64 registers, 0.3 GB of local-memory traffic per
+    // launch) -- and appends oversized buckets to big_list for a second launch of the full kernel in list mode
     // phase_cycles != nullptr (dpk_set_option("agg_timing", 1), debugging): thread 0 adds the cycles between the
     // phase boundaries of every fast-path bucket: [0] top..rows loaded+staged (S), [1] S..inserts done (B),
     // [2] B..output range known (D), [3] D..write-out issued, [4] write-out..next top (A), [5] buckets
@@ -384,6 +402,13 @@ k_smem_aggregate2(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, 
             continue;  // barrier (A) of the next iteration orders the reads and the clear before the next staging
         }
 
+        if constexpr (FAST_ONLY) {
+            if (threadIdx.x == 0) big_list[atomicAdd(big_count, 1)] = fb;
+            prefetch_ticket();
+            prefetch_range();
+            publish_range();
+            continue;
+        }
         // ================= general path: windows behind resident distinct rows, hash-disjoint passes on overflow
         prefetch_ticket();
         prefetch_range();
@@ -424,7 +449,8 @@ k_smem_aggregate2(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, 
                         const int ni = nres + sh.wcnt[j * AG2_WARPS + warp] + ag2_off(offs, j);
                         s_key[ni] = kv[j];
                         s_acc[ni] = av[j];
-                        s_tag[ag2_slot(slots, j)] = (uint32_t)ni + 1u;
+                        const uint32_t sl = ag2_slot(slots, j);
+                        s_tag[sl] = (s_tag[sl] & ~(uint32_t)AG2_IDX_MASK) | ((uint32_t)ni + 1u);
                     }
                 }
                 nres += sh.total;

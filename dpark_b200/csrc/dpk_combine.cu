@@ -448,13 +448,14 @@ constexpr int AG_MAX_SB2 = 10;       // at most 1024 fine buckets per first-leve
 int g_agg_wide = 1;
 int g_agg_ctas = 4;                  // measured: 4 resident CTAs (64 registers, some spills) 1.58 ms vs 1.72 ms at 3
 int g_agg_timing = 0;
+int g_agg_split = 1;
 int g_agg_cursor = 1;
 int g_agg_pipe = 0;                  // dpk_set_option("agg_pipe"): 1 = k_smem_aggregate3 (rows prefetched into registers), 2 = same, 2 CTAs per SM
 int g_agg_batched = 0;               // measured: the four-rows-in-flight insert executes 40 % more instructions (spills) -> 2.22 ms vs 1.72 ms
 int g_agg_impl = 1;                  // dpk_set_option("agg_impl"): 1 = k_smem_aggregate2 (row-index tags), 0 = round-1 kernel
-int g_agg_target_rows = 1536;        // rows per fine bucket the split aims for: the average must stay well below the
-                                     // 2048-row window (duplicate-heavy keys widen the spread: C4 at 1907 rows on
-                                     // average sent 29 % of its buckets through the multi-window path)
+int g_agg_target_rows = 2048;        // rows per fine bucket the split aims for (measured on the C4 shape: an average of
+                                     // 954 rows at a 1536 target costs more -- 7.4 ms merge + 5.3 ms 1024-way split -- than
+                                     // 1907 rows with 29 % of the buckets in the multi-window path: 5.0 + 4.0 ms)
 
 static inline int choose_sb2(int64_t n, int32_t F) {
     int sb2 = 0;
@@ -548,12 +549,30 @@ static int dispatch_op(const Ctx &c) {
                 DPK_LAUNCH("smem_aggregate_big", c.st, aggb<<<sm_count(), AG2_THREADS, smem2, c.st>>>(
                     rekeys, revals, c.op, c.fine_off, nfine, (1 << c.f.sub_bits) * S2, c.part_off,
                     (KeyT *)c.out_keys, c.out_vals, (long long *)c.out_counts, c.fb_state, list_counter, c.part_err,
-                    big_list, big_count, nullptr));
+                    big_list, big_count, nullptr, nullptr, nullptr));
+            } else if (g_agg_cursor && !g_agg_batched && g_agg_split) {
+                // dpk_set_option("agg_split") 1 (default): the hot launch holds the one-window path only (fewer live
+                // registers); oversized buckets are listed and merged by the full kernel in a second, usually empty launch
+                auto fast = g_agg_ctas == 4 ? k_smem_aggregate2<KeyT, ValT, AccT, 4, true, false, true>
+                                            : k_smem_aggregate2<KeyT, ValT, AccT, 3, true, false, true>;
+                DPK_CUDA_TRY(cudaFuncSetAttribute(fast, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+                int *big_count = c.part_err + c.nparts, *list_counter = c.part_err + c.nparts + 1;
+                int *big_list = reinterpret_cast<int *>(c.fb_state);          // nfine * 8 bytes: idle in cursor mode
+                DPK_LAUNCH("smem_aggregate", c.st, fast<<<grid, AG2_THREADS, smem2, c.st>>>(
+                    rekeys, revals, c.op, c.fine_off, nfine, (1 << c.f.sub_bits) * S2, c.part_off,
+                    (KeyT *)c.out_keys, c.out_vals, (long long *)c.out_counts, c.fb_state, c.bucket_counter, c.part_err,
+                    nullptr, nullptr, timing, big_list, big_count));
+                auto aggb = k_smem_aggregate2<KeyT, ValT, AccT, 3, true, false>;
+                DPK_CUDA_TRY(cudaFuncSetAttribute(aggb, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+                DPK_LAUNCH("smem_aggregate_big", c.st, aggb<<<sm_count() * 2, AG2_THREADS, smem2, c.st>>>(
+                    rekeys, revals, c.op, c.fine_off, nfine, (1 << c.f.sub_bits) * S2, c.part_off,
+                    (KeyT *)c.out_keys, c.out_vals, (long long *)c.out_counts, c.fb_state, list_counter, c.part_err,
+                    big_list, big_count, nullptr, nullptr, nullptr));
             } else {
             DPK_LAUNCH("smem_aggregate", c.st, agg2<<<grid, AG2_THREADS, smem2, c.st>>>(
                 rekeys, revals, c.op, c.fine_off, nfine, (1 << c.f.sub_bits) * S2, c.part_off,
                 (KeyT *)c.out_keys, c.out_vals, (long long *)c.out_counts, c.fb_state, c.bucket_counter, c.part_err,
-                nullptr, nullptr, timing));
+                nullptr, nullptr, timing, nullptr, nullptr));
             if (timing) {   // debugging aid: synchronises and prints the per-phase averages of this launch
                 long long h[8];
                 DPK_CUDA_TRY(cudaMemcpyAsync(h, timing, sizeof(h), cudaMemcpyDeviceToHost, c.st));
@@ -664,6 +683,10 @@ int dpk_set_option(const char *name, int64_t value) {
     if (strcmp(name, "agg_batched") == 0) {
         if (value != 0 && value != 1) return fail(DPK_ERR_INVALID, "agg_batched must be 0 or 1");
         g_agg_batched = (int)value;
+        return DPK_OK;
+    }
+    if (strcmp(name, "agg_split") == 0) {
+        g_agg_split = value != 0;
         return DPK_OK;
     }
     if (strcmp(name, "agg_timing") == 0) {

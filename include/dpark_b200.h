@@ -202,7 +202,7 @@ int dpk_combine(const void *keys, int key_kind, const int64_t *key_aux, const vo
  *                     duplicate-heavy data, slower on mostly-distinct keys)
  *   "agg_wide"        round-1 kernel only: 1 (default) claim a table slot and deposit the first value with
  *                     one 128-bit shared-memory CAS; 0 = 64-bit key CAS, then an atomic on the accumulator
- *   "agg_target_rows" rows per fine bucket the second-level split aims for (default 1536; the window holds 2048)
+ *   "agg_target_rows" rows per fine bucket the second-level split aims for (default 2048 = the window)
  *   "count_mode"      1 (default) one shared-memory atomic per row in the histogram pass; 0 = warp
  *                     peer masks + leader update
  *   "scatter_bulk"    1 (default) unordered multisplits (reduceByKey paths, second-level split) run

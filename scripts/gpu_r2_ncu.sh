@@ -15,7 +15,7 @@ cap() {  # regex tag skip count
   ls -la gpurun_out/${TAG}_$2.ncu-rep
   rm -f gpurun_out/${TAG}_$2.ncu-rep
 }
-cap k_smem_aggregate agg 3 1
-cap k_part_scatter scatter 34 2
-cap k_part_count count 34 2
+cap k_smem_aggregate agg 6 2
+cap k_part_scatter scatter 6 2
+cap k_part_count count 6 2
 du -sh gpurun_out
