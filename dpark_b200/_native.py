@@ -33,7 +33,8 @@ EXPORTS = [
     "dpk_launch_count", "dpk_prof_enable", "dpk_prof_count", "dpk_prof_get",
     "dpk_dict_encode_workspace_bytes", "dpk_dict_encode", "dpk_set_option",
     "dpk_key_or", "dpk_radix_pass", "dpk_group_heads_workspace_bytes", "dpk_group_heads", "dpk_gather_i64",
-    "dpk_partition_scatter_ptrs", "dpk_copy_segments", "dpk_hash_tuple", "dpk_push_plan",
+    "dpk_partition_scatter_ptrs", "dpk_copy_segments", "dpk_hash_tuple", "dpk_push_plan", "dpk_fused_plan",
+    "dpk_tokenize_blocks", "dpk_tokenize_count", "dpk_tokenize_emit", "dpk_gather_bytes",
     "dpk_radix_pass_seg_workspace_bytes", "dpk_radix_pass_seg",
 ]
 
@@ -71,6 +72,12 @@ def lib():
         L.dpk_partition_scatter_ptrs.argtypes = [vp, ci, vp, vp, i32, i64, i32, vp, i32, i32, vp, vp, vp, i64, vp]
         L.dpk_copy_segments.argtypes = [vp, vp, vp, i32, vp]
         L.dpk_push_plan.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, C.c_uint64, C.c_uint64, vp, i32, i32, i64, vp, vp, vp, vp, vp, vp]
+        L.dpk_fused_plan.argtypes = [vp, i32, i32, i32, i32, i32, vp, i32, i32, i64, C.c_uint64, C.c_uint64, vp, vp, vp, vp, vp]
+        L.dpk_tokenize_blocks.restype = i64
+        L.dpk_tokenize_blocks.argtypes = [i64]
+        L.dpk_tokenize_count.argtypes = [vp, i64, vp, vp, vp]
+        L.dpk_tokenize_emit.argtypes = [vp, i64, vp, vp, vp, vp]
+        L.dpk_gather_bytes.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp]
         L.dpk_combine_workspace_bytes.argtypes = [i64, i32, i32]
         L.dpk_combine.argtypes = [vp, ci, vp, vp, ci, i64, ci, i32, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp,
                                   vp, vp, i64, vp]
@@ -275,6 +282,27 @@ def push_plan(all_counts, nranks, per_block, my_src, my_rank, keys, vals, dst_ba
     return src, dst, nby, seg
 
 
+def fused_plan(all_counts, nranks, per_block, my_rank, dst_base, key_bytes, val_bytes, capacity, dump_keys, dump_vals,
+               need_over, want_seg=True):
+    """dpk_fused_plan: (key_ptrs[F], val_ptrs[F] | None, seg [nranks, own buckets] | None), one launch: where every
+    bucket of this rank's map output goes in its owner's receive buffer (see include/dpark_b200.h)."""
+    _need_cuda(all_counts, dst_base, need_over, dump_keys, dump_vals)
+    G, F = int(all_counts.shape[0]), int(all_counts.shape[1])
+    if G != nranks:
+        raise ValueError("all_counts has %d source rows for %d ranks" % (G, nranks))
+    ncols = 1 if dump_vals is None else 2
+    dev = all_counts.device
+    kp = torch.empty(F, dtype=torch.int64, device=dev)
+    vp_ = torch.empty(F, dtype=torch.int64, device=dev) if ncols == 2 else None
+    b0, b1 = min(F, my_rank * per_block), min(F, (my_rank + 1) * per_block)
+    seg = torch.empty((G, b1 - b0), dtype=torch.int64, device=dev) if want_seg else None
+    _check(lib().dpk_fused_plan(_ptr(all_counts), nranks, F, per_block, my_rank, ncols, _ptr(dst_base), key_bytes,
+                                val_bytes if ncols == 2 else 0, capacity, C.c_uint64(dump_keys.data_ptr()),
+                                C.c_uint64(0 if dump_vals is None else dump_vals.data_ptr()), _ptr(kp), _ptr(vp_),
+                                _ptr(need_over), _ptr(seg), _stream()))
+    return kp, vp_, seg
+
+
 def partition(keys, vals, P, thresholds=None, prehashed=False, sub_bits=0, row_hash=None, unordered=False):
     """Stable hash-partition of one chunk (ShuffleMapTask._run, dpark/task.py:209-226).
     Returns (out_keys, out_vals, offsets[(P << sub_bits) + 1] int64 device)."""
@@ -350,6 +378,48 @@ def dict_encode(data, offsets, hashes):
     _check(lib().dpk_dict_encode(_ptr(data), _ptr(offsets), _ptr(hashes), n, _ptr(rep), _ptr(ws), ws_bytes,
                                  _stream()))
     return rep
+
+
+# ---- f4: device text ingest --------------------------------------------------------
+def tokenize(data):
+    """Tokens (str.split() without arguments) of an ASCII byte range on the device: (starts, lens, ascii) -- int64
+    device tensors in text order; ascii False = the range holds a byte >= 0x80 and must be tokenised by Python
+    (starts / lens are None then).  One host read (the token count sizes the outputs)."""
+    _need_cuda(data)
+    n = int(data.numel())
+    dev = data.device
+    if n == 0:
+        z = torch.zeros(0, dtype=torch.int64, device=dev)
+        return z, z.clone(), True
+    nb = int(lib().dpk_tokenize_blocks(n))
+    counts = torch.empty(nb + 1, dtype=torch.int64, device=dev)   # [nb] = the high-byte flag
+    counts[nb] = 0
+    _check(lib().dpk_tokenize_count(_ptr(data), n, _ptr(counts), C.c_void_p(counts.data_ptr() + 8 * nb), _stream()))
+    incl = torch.cumsum(counts[:nb], 0)
+    total, flag = int(incl[-1].item()), int(counts[nb].item())
+    if flag & 1:
+        return None, None, False
+    base = (incl - counts[:nb]).contiguous()
+    starts = torch.empty(total, dtype=torch.int64, device=dev)
+    lens = torch.empty(total, dtype=torch.int64, device=dev)
+    if total:
+        _check(lib().dpk_tokenize_emit(_ptr(data), n, _ptr(base), _ptr(starts), _ptr(lens), _stream()))
+    return starts, lens, True
+
+
+def gather_bytes(data, starts, lens, idx=None):
+    """Selected rows made contiguous: (bytes uint8, offsets int64 [m + 1]) with row i = data[starts[r] : starts[r] +
+    lens[r]], r = idx[i] (idx None: every row)."""
+    _need_cuda(data, starts, lens, idx)
+    sel = lens if idx is None else lens[idx]
+    m = int(sel.numel())
+    off = torch.zeros(m + 1, dtype=torch.int64, device=data.device)
+    if m:
+        torch.cumsum(sel, 0, out=off[1:])
+    out = torch.empty(int(off[-1].item()) if m else 0, dtype=torch.uint8, device=data.device)
+    if m and out.numel():
+        _check(lib().dpk_gather_bytes(_ptr(data), _ptr(starts), _ptr(lens), _ptr(idx), m, _ptr(off), _ptr(out), _stream()))
+    return out, off
 
 
 # ---- a10: groupByKey reduce side ---------------------------------------------------

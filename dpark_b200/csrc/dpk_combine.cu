@@ -727,6 +727,16 @@ int dpk_set_option(const char *name, int64_t value) {
         g_scatter_seg_wide = value != 0;
         return DPK_OK;
     }
+    if (strcmp(name, "scatter_ptr_bulk") == 0) {
+        if (value != 0 && value != 1) return fail(DPK_ERR_INVALID, "scatter_ptr_bulk must be 0 or 1");
+        g_scatter_ptr_bulk = (int)value;
+        return DPK_OK;
+    }
+    if (strcmp(name, "scatter_ptr_threads") == 0) {
+        if (value != 512 && value != 1024) return fail(DPK_ERR_INVALID, "scatter_ptr_threads must be 512 or 1024");
+        g_scatter_ptr_threads = (int)value;
+        return DPK_OK;
+    }
     if (strcmp(name, "scatter_bulk") == 0) {
         if (value != 0 && value != 1) return fail(DPK_ERR_INVALID, "scatter_bulk must be 0 or 1");
         g_scatter_bulk = (int)value;

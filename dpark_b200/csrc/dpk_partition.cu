@@ -42,7 +42,13 @@ int g_scatter_items = 16;
 // shared-memory ranking + TMA bulk stores of the staged bucket runs); 0 = the round-1 kernel (A/B switch)
 int g_scatter_bulk = 1;
 int g_scatter_threads = 512;
-int g_scatter_seg_wide = 1;   // dpk_set_option("scatter_seg_wide"): segmented launches use the 1024-thread / 8192-row form
+int g_scatter_seg_wide = 1;
+// dpk_set_option("scatter_ptr_bulk"): 1 (default) = the fused scatter + exchange (pointer mode) runs the TMA bulk-store
+// kernel for unordered multisplits; 0 = the round-1 kernel (per-thread 8-byte stores over NVLink).
+// dpk_set_option("scatter_ptr_threads"): CTA size of the bulk kernel in pointer mode: 1024 (default; 8192-row tiles: the
+// bucket runs that cross NVLink are twice as long) or 512
+int g_scatter_ptr_bulk = 1;
+int g_scatter_ptr_threads = 1024;   // dpk_set_option("scatter_seg_wide"): segmented launches use the 1024-thread / 8192-row form
 
 // Segmented mode (second-level split on the reduce side): the grid runs over a
 // device-resident chunk table instead of equal row ranges; every chunk lies inside
@@ -447,10 +453,10 @@ k_part_scatter(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, int
 // fence.proxy.async -> barrier -> bulk stores (asynchronous; their shared-memory reads are awaited with
 // cp.async.bulk.wait_group.read right before the next placement).
 struct BulkSmem {
-    int64_t key_off, val_off, gpos_off, cnt_off, sk_off, sv_off, total;
+    int64_t key_off, val_off, gpos_off, cnt_off, sk_off, sv_off, vd_off, total;
     int32_t key_slots, val_slots;
 };
-static BulkSmem bulk_smem(int kb, int vb, int32_t P, int tile) {
+static BulkSmem bulk_smem(int kb, int vb, int32_t P, int tile, bool ptr_mode = false) {
     BulkSmem s;
     int64_t o = 0;
     const int padk = 16 / kb - 1, padv = vb ? 16 / vb - 1 : 0;
@@ -462,6 +468,7 @@ static BulkSmem bulk_smem(int kb, int vb, int32_t P, int tile) {
     s.cnt_off = o; o += align_up((int64_t)P * 4 * 2, 16);    // two alternating count arrays
     s.sk_off = o; o += align_up((int64_t)P * 4, 16);
     s.sv_off = o; o += align_up((int64_t)P * 4, 16);
+    s.vd_off = o; if (ptr_mode && vb) o += align_up((int64_t)P * 8, 16);   // pointer mode: value slot - key slot, in elements
     s.total = o;
     return s;
 }
@@ -500,7 +507,7 @@ __device__ __forceinline__ int bucket_of(const PartFn &f, int64_t h) {
     }
 }
 
-template <typename KeyT, typename ValT, int PRE, int NT, int FMODE>
+template <typename KeyT, typename ValT, int PRE, int NT, int FMODE, bool PTRS = false>
 __global__ void __launch_bounds__(NT, NT == 1024 ? 1 : 2)
 k_part_scatter_bulk(const KeyT *__restrict__ keys, const ValT *__restrict__ vals, int64_t n, int64_t L,
                     PartFn f, const int32_t *__restrict__ tile_off, int32_t T,
@@ -523,6 +530,13 @@ k_part_scatter_bulk(const KeyT *__restrict__ keys, const ValT *__restrict__ vals
     uint32_t *s_cnt = reinterpret_cast<uint32_t *>(smem + lay.cnt_off);      // [2][P]
     int32_t *s_sk = reinterpret_cast<int32_t *>(smem + lay.sk_off);          // start of bucket p's key run in the staging tile
     int32_t *s_sv = reinterpret_cast<int32_t *>(smem + lay.sv_off);
+    // Pointer mode (PTRS: fused scatter + exchange, seg.key_ptrs != nullptr; out_keys == out_vals == nullptr): s_gpos[p] is
+    // the ABSOLUTE element index (address / sizeof(KeyT)) of the next key slot of bucket p -- in this GPU's memory or in
+    // a peer's receive buffer mapped over NVLink -- and s_vd[p] the distance, in elements, from there to the value slot
+    // (address / sizeof(ValT) - address / sizeof(KeyT)): the bucket runs of a tile leave through the TMA straight into
+    // the buffer their reducer reads.
+    constexpr bool ptrs = PTRS;
+    int64_t *s_vd = reinterpret_cast<int64_t *>(smem + lay.vd_off);
     const uint32_t key_addr = (uint32_t)__cvta_generic_to_shared(s_key);
     const uint32_t val_addr = (uint32_t)__cvta_generic_to_shared(s_val);
 
@@ -533,6 +547,12 @@ k_part_scatter_bulk(const KeyT *__restrict__ keys, const ValT *__restrict__ vals
     const int64_t end = seg.cbeg ? seg.cend[blockIdx.x] : min(n, ((int64_t)(blockIdx.x + 1) * L / T) * PT_TILE);
     if (seg.cbeg) {
         for (int p = threadIdx.x; p < P; p += NT) s_gpos[p] = seg.chunk_off[(int64_t)blockIdx.x * P + p];
+    } else if constexpr (PTRS) {
+        for (int p = threadIdx.x; p < P; p += NT) {
+            const int64_t ke = (int64_t)(seg.key_ptrs[p] / sizeof(KeyT));
+            s_gpos[p] = ke + (int64_t)tile_off[(int64_t)p * T + blockIdx.x];
+            if constexpr (HAS_VAL) s_vd[p] = (int64_t)(seg.val_ptrs[p] / sizeof(ValT)) - ke;
+        }
     } else {
         for (int p = threadIdx.x; p < P; p += NT)
             s_gpos[p] = bucket_base[p] + (int64_t)tile_off[(int64_t)p * T + blockIdx.x];
@@ -608,7 +628,7 @@ k_part_scatter_bulk(const KeyT *__restrict__ keys, const ValT *__restrict__ vals
                 const int basek = run + i * (AK - 1);
                 s_sk[i] = basek + (int)((gk - (uint32_t)basek) & (uint32_t)(AK - 1));
                 if constexpr (HAS_VAL) {
-                    const uint32_t gv = (uint32_t)(((uintptr_t)(out_vals + g)) / sizeof(ValT));
+                    const uint32_t gv = (uint32_t)(((uintptr_t)(out_vals + (ptrs ? g + s_vd[i] : g))) / sizeof(ValT));
                     const int basev = run + i * (AV - 1);
                     s_sv[i] = basev + (int)((gv - (uint32_t)basev) & (uint32_t)(AV - 1));
                 }
@@ -642,7 +662,7 @@ k_part_scatter_bulk(const KeyT *__restrict__ keys, const ValT *__restrict__ vals
                 const int c = on ? (int)cnt[p] : 0;
                 const int64_t g = on ? s_gpos[p] : 0;
                 if (c) {
-                    if (q & 1) flush_run<ValT>(out_vals, g, s_val, val_addr, s_sv[p], c);
+                    if (q & 1) flush_run<ValT>(out_vals, ptrs ? g + s_vd[p] : g, s_val, val_addr, s_sv[p], c);
                     else flush_run<KeyT>(out_keys, g, s_key, key_addr, s_sk[p], c);
                 }
                 __syncwarp();   // both lanes of the pair have read the count and the position
@@ -722,9 +742,21 @@ static int launch_scatter_bulk(const void *keys, const void *vals, int64_t n, co
     // rows of 4-byte columns: a 4096-row tile's bucket runs are 64 bytes, where the bulk stores are issue-bound
     // (measured on C4: 1057 GB/s with 4096-row tiles against 2003 GB/s with 8192-row tiles)
     if (nt == 512 && g_scatter_seg_wide && sizeof(KeyT) <= 4 && (vb == 0 || vb <= 4)) nt = 1024;
-    if (nt == 1024 && bulk_smem((int)sizeof(KeyT), vb, f.nbuckets(), 8192).total > 220 * 1024) nt = 512;
-    BulkSmem lay = bulk_smem((int)sizeof(KeyT), vb, f.nbuckets(), nt == 1024 ? 8192 : PT_TILE);
+    const bool ptr_mode = pl.seg.key_ptrs != nullptr;
+    if (ptr_mode && nt == 512 && g_scatter_ptr_threads == 1024) nt = 1024;
+    if (nt == 1024 && bulk_smem((int)sizeof(KeyT), vb, f.nbuckets(), 8192, ptr_mode).total > 220 * 1024) nt = 512;
+    BulkSmem lay = bulk_smem((int)sizeof(KeyT), vb, f.nbuckets(), nt == 1024 ? 8192 : PT_TILE, ptr_mode);
     const int fmode = f.mode == 5 ? 2 : ((f.mode == 0 || f.mode == 1) ? 1 : 0);
+    if (ptr_mode) {   // fused scatter + exchange: only the map-side bucket functions occur
+        auto kp = nt == 1024 ? (fmode == 1 ? k_part_scatter_bulk<KeyT, ValT, PRE, 1024, 1, true> : k_part_scatter_bulk<KeyT, ValT, PRE, 1024, 0, true>)
+                             : (fmode == 1 ? k_part_scatter_bulk<KeyT, ValT, PRE, 512, 1, true> : k_part_scatter_bulk<KeyT, ValT, PRE, 512, 0, true>);
+        if (nt != 512 && nt != 1024) return fail(DPK_ERR_UNSUPPORTED, "pointer mode needs 512- or 1024-thread CTAs");
+        DPK_CUDA_TRY(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
+        DPK_LAUNCH(pl.label_scatter ? pl.label_scatter : "part_scatter", st,
+                   kp<<<pl.T, nt, (size_t)lay.total, st>>>((const KeyT *)keys, (const ValT *)vals, n, pl.L, f, tile_off, pl.T,
+                                                          bucket_base, (KeyT *)out_keys, (ValT *)out_vals, lay, pl.seg));
+        return DPK_OK;
+    }
     auto kern = nt == 1024 ? (fmode == 2 ? k_part_scatter_bulk<KeyT, ValT, PRE, 1024, 2> :
                               fmode == 1 ? k_part_scatter_bulk<KeyT, ValT, PRE, 1024, 1> : k_part_scatter_bulk<KeyT, ValT, PRE, 1024, 0>)
               : nt == 512 ? (fmode == 2 ? k_part_scatter_bulk<KeyT, ValT, PRE, 512, 2> :
@@ -745,7 +777,7 @@ static int launch_scatter(const void *keys, const void *vals, int64_t n, const P
     Plan pl = pl_in;
     if (pl.seg.unordered == 2) {  // unordered + plain/segmented destination: the TMA bulk-store kernel
         constexpr int vb = std::is_same<ValT, NoVal>::value ? 0 : (int)sizeof(ValT);
-        if (bulk_smem((int)sizeof(KeyT), vb, f.nbuckets(), PT_TILE).total <= 110 * 1024)
+        if (bulk_smem((int)sizeof(KeyT), vb, f.nbuckets(), PT_TILE, pl.seg.key_ptrs != nullptr).total <= 110 * 1024)
             return launch_scatter_bulk<KeyT, ValT, PRE>(keys, vals, n, pl, f, tile_off, bucket_base, out_keys, out_vals, st);
         pl.seg.unordered = (f.nbuckets() % 2 == 0) ? 1 : 0;  // too many buckets for two resident CTAs: the round-1 kernel
     }
@@ -775,7 +807,7 @@ static int dispatch_scatter(const void *keys, int key_kind, const void *vals, in
     if (key_kind >= DPK_K_UNORDERED) {  // caller does not need input order inside a bucket
         key_kind -= DPK_K_UNORDERED;
         if (f.nbuckets() % 2 == 0) pl.seg.unordered = 1;  // packed 16-bit counter pairs need an even bucket count
-        if (g_scatter_bulk && pl.seg.key_ptrs == nullptr) pl.seg.unordered = 2;
+        if (g_scatter_bulk && (pl.seg.key_ptrs == nullptr || g_scatter_ptr_bulk)) pl.seg.unordered = 2;
     } else if (pl.seg.unordered && g_scatter_bulk && pl.seg.key_ptrs == nullptr) {
         pl.seg.unordered = 2;  // segmented mode (reduce side): never ordered
     }

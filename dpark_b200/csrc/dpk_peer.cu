@@ -118,9 +118,77 @@ k_push_plan(const int64_t *__restrict__ all_counts, int32_t S, int32_t G, int32_
     }
 }
 
+// The plan of the FUSED scatter + exchange (dpk_partition_scatter_ptrs): for every fine bucket b of this rank's map
+// output the address its rows go to -- the slot of (source = this rank, bucket b) in the OWNER's receive buffer, layout
+// source-rank-major then bucket-major exactly as the push form delivers it -- plus this rank's segment matrix and the
+// capacity flag.  A bucket that would end past `capacity` rows of its receive buffer is pointed at a local dump buffer
+// instead (dump0/dump1: >= this rank's row count; position = the bucket's local bucket-major offset), so a too-small
+// buffer can never be overrun; need_over reports it.  Single CTA; G <= 64 ranks, F <= 4096 buckets.
+__global__ void __launch_bounds__(256)
+k_fused_plan(const int64_t *__restrict__ all_counts, int32_t G, int32_t F, int32_t per_blk, int32_t my_rank, int32_t ncols,
+             const uint64_t *__restrict__ dst_base, int32_t elem0, int32_t elem1, int64_t capacity, uint64_t dump0,
+             uint64_t dump1, uint64_t *__restrict__ key_ptrs, uint64_t *__restrict__ val_ptrs,
+             long long *__restrict__ need_over, int64_t *__restrict__ seg_out) {
+    extern __shared__ long long s_fp[];
+    long long *s_R = s_fp;             // [G][G] rows source s sends to destination d
+    long long *s_mine = s_fp + G * G;  // [F] my rows per bucket
+    for (int i = threadIdx.x; i < G * G; i += blockDim.x) {
+        const int s = i / G, d = i % G;
+        const int b0 = min(F, d * per_blk), b1 = min(F, (d + 1) * per_blk);
+        long long r = 0;
+        for (int b = b0; b < b1; b++) r += all_counts[(int64_t)s * F + b];
+        s_R[i] = r;
+    }
+    for (int b = threadIdx.x; b < F; b += blockDim.x) s_mine[b] = all_counts[(int64_t)my_rank * F + b];
+    __syncthreads();
+    if (threadIdx.x < G) {
+        const int d = threadIdx.x;
+        long long dst_first = 0, total = 0, local_first = 0;
+        for (int dd = 0; dd < d; dd++) local_first += s_R[my_rank * G + dd];
+        for (int s = 0; s < G; s++) {
+            if (s < my_rank) dst_first += s_R[s * G + d];
+            total += s_R[s * G + d];
+        }
+        const int b0 = min(F, d * per_blk), b1 = min(F, (d + 1) * per_blk);
+        long long run = 0;
+        for (int b = b0; b < b1; b++) {
+            const long long c = s_mine[b];
+            const bool fits = dst_first + run + c <= capacity;
+            key_ptrs[b] = fits ? dst_base[d] + (uint64_t)((dst_first + run) * elem0) : dump0 + (uint64_t)((local_first + run) * elem0);
+            if (ncols > 1)
+                val_ptrs[b] = fits ? dst_base[G + d] + (uint64_t)((dst_first + run) * elem1)
+                                   : dump1 + (uint64_t)((local_first + run) * elem1);
+            run += c;
+        }
+        if (total > capacity) atomicMax(need_over, total - capacity);
+    }
+    if (seg_out) {
+        const int b0 = min(F, my_rank * per_blk), b1 = min(F, (my_rank + 1) * per_blk), fo = b1 - b0;
+        for (int i = threadIdx.x; i < G * fo; i += blockDim.x) seg_out[i] = all_counts[(int64_t)(i / fo) * F + b0 + i % fo];
+    }
+}
+
 }  // namespace dpk
 
 using namespace dpk;
+
+extern "C" int dpk_fused_plan(const int64_t *all_counts, int32_t nranks, int32_t nbuckets, int32_t per_block, int32_t my_rank,
+                              int32_t ncols, const uint64_t *dst_base, int32_t key_bytes, int32_t val_bytes, int64_t capacity,
+                              uint64_t dump_keys, uint64_t dump_vals, uint64_t *key_ptrs, uint64_t *val_ptrs,
+                              int64_t *need_over, int64_t *seg_out, dpk_stream_t stream) {
+    if (nranks < 1 || nranks > 64 || nbuckets < 1 || nbuckets > 4096 || ncols < 1 || ncols > 2 || per_block < 0 ||
+        my_rank < 0 || my_rank >= nranks)
+        return fail(DPK_ERR_INVALID, "bad fused plan shape: %d ranks, %d buckets, %d columns", nranks, nbuckets, ncols);
+    if (!all_counts || !dst_base || !key_ptrs || (ncols > 1 && !val_ptrs) || !need_over || !dump_keys || (ncols > 1 && !dump_vals))
+        return fail(DPK_ERR_INVALID, "NULL pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t sh = ((size_t)nranks * nranks + nbuckets) * sizeof(long long);
+    DPK_CUDA_TRY(cudaFuncSetAttribute(k_fused_plan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+    DPK_LAUNCH("fused_plan", st, k_fused_plan<<<1, 256, sh, st>>>(all_counts, nranks, nbuckets, per_block, my_rank, ncols, dst_base,
+                                                               key_bytes, val_bytes, capacity, dump_keys, dump_vals, key_ptrs,
+                                                               val_ptrs, (long long *)need_over, seg_out));
+    return DPK_OK;
+}
 
 extern "C" int dpk_push_plan(const int64_t *all_counts, int32_t nsrc, int32_t nranks, int32_t nbuckets, int32_t per_block,
                              int32_t my_src, int32_t my_rank, int32_t ncols, uint64_t src_keys, uint64_t src_vals,

@@ -51,6 +51,9 @@ def _gather_parent(srdd, numeric_values, only=None):
     return out
 
 
+TEXT_INGEST = True            # dpark_b200.textingest: tokenise textFile -> split -> (w, 1) pipelines on the device
+
+
 def run_shuffle(srdd):
     from . import spmd
     rank, world = spmd.rank_world()
@@ -60,6 +63,12 @@ def run_shuffle(srdd):
     P = srdd.partitioner.numPartitions
     thr = srdd.partitioner.thresholds
     if srdd.kind == "reduce":
+        from . import textingest
+        text = textingest.recognize(srdd.parent) if TEXT_INGEST else None
+        if text is not None:     # the word-count shape: tokenise on the device (None back: a non-ASCII split, row-wise path)
+            res = textingest.reduce_tokens(text, range(len(text.splits)), P, thr, srdd.op, dev, ShuffleResult(P))
+            if res is not None:
+                return res
         splits = _gather_parent(srdd, True)
         return _run_reduce(splits, P, thr, srdd.op, dev)
     splits = _gather_parent(srdd, False)
@@ -90,7 +99,20 @@ def _run_shuffle_spmd(srdd, rank, world):
     nsplits = len(srdd.parent.splits)
     mine = set(spmd.my_indices(nsplits, rank, world))
     numeric = srdd.kind == "reduce"
-    splits = _gather_parent(srdd, numeric, only=mine)
+    splits = None
+    if numeric and TEXT_INGEST:
+        # the word-count shape: this rank's splits are tokenised AND combined on its GPU (the reference's map-side
+        # combine, dpark/task.py:221-226); what is routed to the owners are the distinct (word, partial count) pairs
+        from . import textingest
+        text = textingest.recognize(srdd.parent)
+        if text is not None:
+            part = textingest.reduce_tokens(text, sorted(mine), P, thr, srdd.op, dev, ShuffleResult(P))
+            if part is not None:
+                ks = [k for p in range(P) for k in part.parts[p][0]]
+                vs = [v for p in range(P) for v in part.parts[p][1]]
+                splits = [columnar.ingest_pairs(zip(ks, vs), "textFile", True)]
+    if splits is None:
+        splits = _gather_parent(srdd, numeric, only=mine)
     blocks = shuffle.owner_blocks(P, world)
     tensor_in = bool(splits) and not isinstance(splits[0], columnar.Columns)
     # what every rank must agree on before any collective: key kind, value kinds

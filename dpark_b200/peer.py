@@ -64,6 +64,7 @@ class PeerExchange(object):
         self.side = torch.cuda.Stream(device=self.device, priority=-1)     # pushes that overlap the map side
         self.err = torch.zeros(1, dtype=torch.int64, device=self.device)   # max rows any rank needed beyond capacity
         self._closed = False
+        self._dump = None
 
     # the buffer set of the current step
     @property
@@ -104,6 +105,13 @@ class PeerExchange(object):
             self.err.zero_()
             raise RuntimeError("peer receive buffer too small: a step needed %d rows, capacity %d (results of that "
                                "step are invalid)" % (self.capacity + over, self.capacity))
+
+    def dump(self, rows, with_vals=True):
+        """Local columns a fused scatter diverts overflowing buckets into (never read; sized to this rank's rows)."""
+        if self._dump is None or self._dump[0].numel() < rows:
+            self._dump = (torch.empty(max(rows, 1), dtype=self._keys[0].dtype, device=self.device),
+                          torch.empty(max(rows, 1), dtype=self._vals[0].dtype, device=self.device))
+        return self._dump[0], (self._dump[1] if with_vals else None)
 
     def close(self):
         """Drop the symmetric allocations (all ranks must call it)."""
@@ -165,7 +173,72 @@ def exchange_push(px, mo, need_host_count=False):
 
 
 def map_exchange_overlapped(px, key_chunks, val_chunks, P, thresholds=None, sub_bits=0, unordered=True, halves=2):
-    """Map side + exchange with the push of the first half of the map splits running (on a side stream) while the
+    """Map side + exchange with the push of one group of map splits running (on a side stream) while the next group is
+    still being scattered.  The rank's splits are divided into `halves` contiguous groups, every group gets its own
+    bucket-major buffer, and a group's blocks are pushed as soon as its scatter kernel is done; all counts are known
+    after the histogram pass, so ONE all-gather describes every group.  In a receive buffer the groups of one source
+    rank follow each other in split order, i.e. the layout is still (map split order)-major then bucket-major:
+    `Received.seg` simply has G * halves source rows.  Groups whose splits are consecutive slices of one buffer (the
+    usual case) take one launch pair each and one dpk_push_plan launch for their segment table.
+    Returns the Received view (bound = the whole receive buffer) like exchange_push."""
+    from . import shuffle as sh
+    G, rank, dev = px.world, px.rank, px.device
+    F = P << sub_bits
+    M = len(key_chunks)
+    H = max(1, min(halves, M))
+    has_v = val_chunks[0] is not None
+    bounds = [(M * h) // H for h in range(H + 1)]
+    gk, gv = [], []
+    for h in range(H):
+        sel = slice(bounds[h], bounds[h + 1])
+        k1 = sh._as_one(key_chunks[sel])
+        v1 = sh._as_one(val_chunks[sel]) if has_v else None
+        if k1 is None or (has_v and v1 is None) or k1.numel() >= (1 << 31):
+            return _map_exchange_overlapped_splits(px, key_chunks, val_chunks, P, thresholds, sub_bits, unordered, H)
+        gk.append(k1)
+        gv.append(v1)
+    counts, wss = [], []
+    for k in gk:
+        c, ws = nv.partition_count(k, P, thresholds, False, sub_bits, None, None, unordered)
+        counts.append(c)
+        wss.append(ws)
+    gc = torch.stack(counts)                                            # [H, F] rows per group and bucket
+    all_counts = torch.empty(G * H * F, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(all_counts, gc.reshape(-1), group=px.group)   # the MapOutputTracker
+    all_counts = all_counts.view(G * H, F)                              # source (rank, group) major
+    per_block = ((P + G - 1) // G) << sub_bits
+    main = torch.cuda.current_stream()
+    seg = None
+    for h in range(H):
+        offsets = torch.zeros(F + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(gc[h], 0, out=offsets[1:])
+        out_k = torch.empty_like(gk[h])
+        out_v = torch.empty_like(gv[h]) if has_v else None
+        nv.partition_scatter(gk[h], gv[h], P, offsets, out_k, out_v, wss[h], thresholds, False, sub_bits, None, unordered)
+        src, dst, nby, sg = nv.push_plan(all_counts, G, per_block, rank * H + h, rank, out_k, out_v,
+                                         px.dst_base if has_v else px.key_base, px.capacity, px.err, want_seg=(h == 0))
+        if h == 0:
+            seg = sg
+        ready = torch.cuda.Event()
+        ready.record(main)
+        with torch.cuda.stream(px.side):
+            px.side.wait_event(ready)
+            nv.copy_segments(src, dst, nby)
+            for t in (out_k, out_v, src, dst, nby):
+                if t is not None:
+                    t.record_stream(px.side)
+    main.wait_stream(px.side)
+    px.barrier()                                                        # every peer's stores have landed
+    blocks = [b << sub_bits for b in owner_blocks(P, G)]
+    b0, b1 = blocks[rank], blocks[rank + 1]
+    keys, vals = px.keys, (px.vals if has_v else None)
+    px.advance()
+    return Received(keys, vals, seg, b0 >> sub_bits, (b1 - b0) >> sub_bits, sub_bits, bound=True)
+
+
+def _map_exchange_overlapped_splits(px, key_chunks, val_chunks, P, thresholds=None, sub_bits=0, unordered=True, halves=2):
+    """map_exchange_overlapped for splits that are NOT consecutive slices of one buffer (a launch pair per split).
+    Map side + exchange with the push of the first half of the map splits running (on a side stream) while the
     second half is still being scattered.  The rank's splits are divided into `halves` contiguous groups, every
     group gets its own bucket-major buffer, and a group's blocks are pushed as soon as its scatter kernels are
     done; all counts are known after the histogram pass, so ONE all-gather describes every group.  In a receive
@@ -234,46 +307,51 @@ def map_exchange_overlapped(px, key_chunks, val_chunks, P, thresholds=None, sub_
 
 
 def map_side_push(px, key_chunks, val_chunks, P, thresholds=None, sub_bits=0, unordered=True):
-    """Map side + exchange in one pass: returns the Received view of THIS rank's buffer."""
+    """Map side + exchange in ONE pass over the rows (mode "fused"): the multisplit kernel stores every bucket run of
+    a tile straight into the slot of (this rank, bucket) in the owner's receive buffer -- local memory or a peer's
+    over NVLink; unordered multisplits (the reduceByKey map side) leave through the TMA (`cp.async.bulk` shared ->
+    global, k_part_scatter_bulk in pointer mode), ordered ones (groupByKey) through the round-1 kernel's stores.  No
+    bucket-major send buffer, no copy pass.  Nothing is read by the host: the pointer table, the segment matrix and
+    the capacity flag come from one small kernel (dpk_fused_plan); a bucket that would overrun its receive buffer
+    is diverted to a local dump buffer and PeerExchange.check() reports it.
+    Returns the Received view (bound = the whole receive buffer) like exchange_push."""
+    from . import shuffle as sh
     G, rank, dev = px.world, px.rank, px.device
     F = P << sub_bits
+    has_v = val_chunks[0] is not None
+    if len(key_chunks) > 1:   # consecutive slices of one buffer: one launch pair (shuffle.map_side does the same)
+        whole_k, whole_v = sh._as_one(key_chunks), (sh._as_one(val_chunks) if has_v else None)
+        if whole_k is not None and (not has_v or whole_v is not None) and whole_k.numel() < (1 << 31):
+            key_chunks, val_chunks = [whole_k], [whole_v]
     counts, wss = [], []
     for k in key_chunks:
         c, ws = nv.partition_count(k, P, thresholds, False, sub_bits, None, None, unordered)
         counts.append(c)
         wss.append(ws)
-    cm = torch.stack(counts)                                        # [M, F] rows per chunk and bucket
-    mine = cm.sum(0).contiguous()                                   # [F]
+    cm = counts[0].unsqueeze(0) if len(counts) == 1 else torch.stack(counts)     # [M, F] rows per chunk and bucket
+    mine = counts[0] if len(counts) == 1 else cm.sum(0).contiguous()             # [F]
     all_counts = torch.empty(G * F, dtype=torch.int64, device=dev)
     dist.all_gather_into_tensor(all_counts, mine, group=px.group)   # the MapOutputTracker
     all_counts = all_counts.view(G, F)
-    blocks = [b << sub_bits for b in owner_blocks(P, G)]
-    # rows every source sends to every destination: R[s][d]
-    R = torch.stack([all_counts[:, blocks[d]:blocks[d + 1]].sum(1) for d in range(G)], dim=1)   # [G, G]
-    src_base = torch.cumsum(R, 0) - R                               # [s][d]: rows of earlier sources at d
-    need = int(R.sum(0).max().item())                               # host read: capacity check (stores cannot be clamped here)
-    if need > px.capacity:
-        raise RuntimeError("peer receive buffer too small: need %d rows, capacity %d" % (need, px.capacity))
-    # offset of my bucket b inside its owner's buffer
-    dst_off = torch.empty(F, dtype=torch.int64, device=dev)
-    owner = torch.empty(F, dtype=torch.int64, device=dev)
-    for d in range(G):
-        b0, b1 = blocks[d], blocks[d + 1]
-        if b1 > b0:
-            seg = all_counts[rank, b0:b1]
-            dst_off[b0:b1] = src_base[rank, d] + (torch.cumsum(seg, 0) - seg)
-            owner[b0:b1] = d
-    chunk_off = torch.cumsum(cm, 0) - cm                            # rows of earlier local chunks per bucket
-    ksz, vsz = key_chunks[0].element_size(), val_chunks[0].element_size()
-    kbase, vbase = px.key_base[owner], px.val_base[owner]
-    for m, (k, v) in enumerate(zip(key_chunks, val_chunks)):
-        off = dst_off + chunk_off[m]
-        nv.partition_scatter_ptrs(k, v, P, (kbase + off * ksz).contiguous(), (vbase + off * vsz).contiguous(),
-                                  wss[m], thresholds, False, sub_bits, None, unordered)
+    per_block = ((P + G - 1) // G) << sub_bits
+    n_local = sum(int(k.numel()) for k in key_chunks)
+    dump_k, dump_v = px.dump(n_local, has_v)
+    ksz = key_chunks[0].element_size()
+    vsz = val_chunks[0].element_size() if has_v else 0
+    kp, vp, seg = nv.fused_plan(all_counts, G, per_block, rank, px.dst_base if has_v else px.key_base, ksz, vsz,
+                                px.capacity, dump_k, dump_v, px.err)
+    if len(key_chunks) == 1:
+        nv.partition_scatter_ptrs(key_chunks[0], val_chunks[0], P, kp, vp, wss[0], thresholds, False, sub_bits, None,
+                                  unordered)
+    else:
+        chunk_off = torch.cumsum(cm, 0) - cm                        # rows of earlier local chunks per bucket
+        for m, (k, v) in enumerate(zip(key_chunks, val_chunks)):
+            nv.partition_scatter_ptrs(k, v, P, (kp + chunk_off[m] * ksz).contiguous(),
+                                      (vp + chunk_off[m] * vsz).contiguous() if has_v else None,
+                                      wss[m], thresholds, False, sub_bits, None, unordered)
     px.barrier()                                                    # every peer's stores have landed
+    blocks = [b << sub_bits for b in owner_blocks(P, G)]
     b0, b1 = blocks[rank], blocks[rank + 1]
-    nrecv = int(R[:, rank].sum().item())
-    seg = all_counts[:, b0:b1].contiguous()
-    keys, vals = px.keys, px.vals
+    keys, vals = px.keys, (px.vals if has_v else None)
     px.advance()
-    return Received(keys[:nrecv], vals[:nrecv], seg, b0 >> sub_bits, (b1 - b0) >> sub_bits, sub_bits)
+    return Received(keys, vals, seg, b0 >> sub_bits, (b1 - b0) >> sub_bits, sub_bits, bound=True)

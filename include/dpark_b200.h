@@ -157,6 +157,17 @@ int dpk_push_plan(const int64_t *all_counts, int32_t nsrc, int32_t nranks, int32
                   int32_t my_src, int32_t my_rank, int32_t ncols, uint64_t src_keys, uint64_t src_vals,
                   const uint64_t *dst_base, int32_t key_bytes, int32_t val_bytes, int64_t capacity, uint64_t *src_ptrs,
                   uint64_t *dst_ptrs, int64_t *nbytes, int64_t *need_over, int64_t *seg_out, dpk_stream_t stream);
+/* The same lookup for the FUSED scatter + exchange (dpk_partition_scatter_ptrs): key_ptrs[b] / val_ptrs[b] (device
+ * arrays of nbuckets entries) = the address of the slot of (source my_rank, bucket b) in its owner's receive buffer,
+ * laid out source-rank-major then bucket-major exactly as the push delivers it.  A bucket that would end past
+ * `capacity` rows of the owner's buffer is pointed into the local dump columns dump_keys / dump_vals (>= this rank's
+ * row count) at its local bucket-major offset, and *need_over reports the overflow, so a too-small receive buffer is
+ * never overrun.  nbuckets <= 4096.  Replaces, with dpk_partition_scatter_ptrs, the reducers' pull of every map
+ * output over files + HTTP (dpark/shuffle.py:309-420) by stores over NVLink issued by the map-side scatter itself. */
+int dpk_fused_plan(const int64_t *all_counts, int32_t nranks, int32_t nbuckets, int32_t per_block, int32_t my_rank,
+                   int32_t ncols, const uint64_t *dst_base, int32_t key_bytes, int32_t val_bytes, int64_t capacity,
+                   uint64_t dump_keys, uint64_t dump_vals, uint64_t *key_ptrs, uint64_t *val_ptrs, int64_t *need_over,
+                   int64_t *seg_out, dpk_stream_t stream);
 
 /* ---- a9: reduce side, DiskHashMerger._merge (dpark/shuffle.py:600-608) ----
  * combined[k] = op(combined[k], v) over the n rows fetched for the nparts reduce
@@ -245,6 +256,21 @@ int dpk_radix_pass_seg(const int64_t *keys, const void *vals, int32_t val_bytes,
 int64_t dpk_group_heads_workspace_bytes(int64_t n);
 int dpk_group_heads(const int64_t *sorted_keys, int64_t n, int64_t *out_keys, int64_t *out_starts,
                     int64_t *out_ngroups, void *ws, int64_t ws_bytes, dpk_stream_t stream);
+
+/* ---- f4: device text ingest (dpark/rdd.py:1633-1711 TextFileRDD + the tokenising flatMap of examples/wc.py:10-12) ----
+ * Tokens of an ASCII byte range that begins and ends on line boundaries = its maximal runs of non-whitespace bytes
+ * (str.split() without arguments: ' ', \t \n \v \f \r, \x1c..\x1f).  dpk_tokenize_count writes the number of token
+ * starts of every 4096-byte block (dpk_tokenize_blocks(n) entries) and ORs bit 0 into *flags (device) if any byte is
+ * >= 0x80 (the caller must then tokenise that range row-wise in Python: Unicode whitespace, decoding errors);
+ * dpk_tokenize_emit takes the EXCLUSIVE scan of those counts and writes (start, length) of every token in text order.
+ * dpk_gather_bytes makes selected rows contiguous: out[out_off[i] ..) = data[starts[r] .. starts[r] + lens[r]),
+ * r = idx ? idx[i] : i -- the (data, offsets) form dpk_hash_bytes / dpk_dict_encode take. */
+int64_t dpk_tokenize_blocks(int64_t n);
+int dpk_tokenize_count(const uint8_t *data, int64_t n, int64_t *block_counts, int64_t *flags, dpk_stream_t stream);
+int dpk_tokenize_emit(const uint8_t *data, int64_t n, const int64_t *block_base, int64_t *starts, int64_t *lens,
+                      dpk_stream_t stream);
+int dpk_gather_bytes(const uint8_t *data, const int64_t *starts, const int64_t *lens, const int64_t *idx, int64_t m,
+                     const int64_t *out_off, uint8_t *out, dpk_stream_t stream);
 
 /* ---- variable-length keys (str / bytes): key identity on the device ---------
  * The reference's dicts compare keys by value; two different strings may share

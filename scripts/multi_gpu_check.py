@@ -55,8 +55,21 @@ def main():
             vd = [torch.from_numpy(x).to(dev) for x in vs]
             rx_nccl = shuffle.exchange(shuffle.map_side(kd, vd, P, None, False, sb_eff))
             rx_peer = peer.map_side_push(px, kd, vd, P, None, sb_eff, unordered=False)   # stable mode: bit-comparable
-            same = (torch.equal(rx_nccl.keys, rx_peer.keys) and torch.equal(rx_nccl.vals, rx_peer.vals)
+            nrx = int(rx_peer.seg.sum().item())          # bound view: the whole receive buffer
+            same = (nrx == rx_nccl.keys.numel() and torch.equal(rx_nccl.keys, rx_peer.keys[:nrx])
+                    and torch.equal(rx_nccl.vals, rx_peer.vals[:nrx])
                     and torch.equal(rx_nccl.seg, rx_peer.seg) and rx_nccl.part_first == rx_peer.part_first)
+            px.check()
+            # the unordered fused form (TMA bulk stores into the peers' buffers) feeds the same merge: same partitions
+            rx_f = peer.map_side_push(px, kd, vd, P, None, sb_eff, unordered=True)
+            fk, fv, fpo, fcnt = shuffle.reduce_side(rx_f, "sum", P)
+            px.check()
+            fpo, fcnt = fpo.cpu().tolist(), fcnt.cpu().tolist()
+            for j, (p, wk_, wv_) in enumerate(mine):
+                gk_ = fk[fpo[j]:fpo[j] + fcnt[j]].cpu().numpy()
+                gv_ = fv[fpo[j]:fpo[j] + fcnt[j]].cpu().numpy()
+                o1, o2 = np.argsort(gk_), np.argsort(wk_)
+                same = same and np.array_equal(gk_[o1], wk_[o2]) and np.array_equal(gv_[o1], wv_[o2])
             # ... and so must the block push (local scatter + dpk_copy_segments)
             rx_push = peer.exchange_push(px, shuffle.map_side(kd, vd, P, None, False, sb_eff), need_host_count=True)
             same = (same and torch.equal(rx_nccl.keys, rx_push.keys) and torch.equal(rx_nccl.vals, rx_push.vals)

@@ -1,9 +1,10 @@
 #!/usr/bin/env python
 """BASELINE config 1 (examples/wc.py shape) through the operator surface on the GPU:
 1 M lines x 10 tokens from a 50 k-word vocabulary `w<i>` with Zipf(1.0) frequencies,
-4 input partitions, reduceByKey(+, numSplits=6), saveAsTextFile.  Reports where the time goes
-(the upstream tokeniser is Python, as in the reference: the end-to-end number is host-bound)
-and checks the word counts against a plain Python Counter."""
+4 input partitions, reduceByKey(+, numSplits=6), saveAsTextFile.  Reports where the time goes and checks the word
+counts against a plain Python Counter.  The tokenising flatMap is recognised and run on the device
+(dpark_b200/textingest.py); `wc_e2e.py <lines> rowwise` runs the user's Python generator per line instead, as the
+reference does (host-bound)."""
 import collections
 import os
 import sys
@@ -18,6 +19,7 @@ sys.path.insert(0, ROOT)
 
 def main():
     lines_n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
+    rowwise = len(sys.argv) > 2 and sys.argv[2] == "rowwise"     # A/B: tokenise with the user's Python generator
     sys.argv = sys.argv[:1]
     rng = np.random.default_rng(1)
     vocab = 50_000
@@ -32,6 +34,9 @@ def main():
     from dpark_b200 import DparkContext
     from dpark_b200 import _native as nv
     dc = DparkContext("local")
+    if rowwise:
+        from dpark_b200 import engine
+        engine.TEXT_INGEST = False
 
     def fm(x):
         for wd in x.strip().split():
@@ -43,7 +48,7 @@ def main():
     sh = rdd.reduceByKey(lambda x, y: x + y, numSplits=6)
     l0 = nv.launch_count()
     t1 = time.perf_counter()
-    sh._materialize()                      # ingest (Python tokeniser + columnarise) + GPU shuffle
+    sh._materialize()                      # ingest (device tokeniser, or Python tokeniser + columnarise) + GPU shuffle
     t2 = time.perf_counter()
     sh.map(lambda x: " ".join(list(map(str, x)))).saveAsTextFile(out, overwrite=False)
     t3 = time.perf_counter()
@@ -55,8 +60,8 @@ def main():
     want = collections.Counter("w%d" % i for i in ids.ravel())
     assert got == dict(want), "word counts differ"
     rows = lines_n * 10
-    print("wc: %d lines, %d tokens, %d distinct words, 6 partitions -> counts identical to a Python Counter" %
-          (lines_n, rows, len(got)))
+    print("wc (%s): %d lines, %d tokens, %d distinct words, 6 partitions -> counts identical to a Python Counter" %
+          ("row-wise Python tokeniser" if rowwise else "device tokeniser", lines_n, rows, len(got)))
     print("  ingest + GPU shuffle %.2f s, egress + save %.2f s, total %.2f s (%.2e tokens/s end to end); "
           "%d kernel launches" % (t2 - t1, t3 - t2, t3 - t0, rows / (t3 - t0), nv.launch_count() - l0))
 

@@ -154,6 +154,90 @@ def test_pointer_mode_scatter_equals_plain_scatter():
     assert torch.equal(ok, mo.keys) and torch.equal(ov, mo.vals) and torch.equal(off, mo.offsets)
 
 
+@pytest.mark.parametrize("threads", [512, 1024])
+@pytest.mark.parametrize("kinds", [("int64", "int64"), ("int32", "float32"), ("int64", None)])
+def test_pointer_mode_bulk_scatter_unordered(kinds, threads):
+    """The fused scatter + exchange for unordered multisplits (reduceByKey map side): k_part_scatter_bulk in pointer
+    mode -- bucket runs leave through the TMA to per-bucket absolute addresses.  With local addresses of buckets laid
+    out in a PERMUTED order (as in a peer's receive buffer, where a bucket's slot has nothing to do with its number)
+    every bucket must hold exactly the rows the plain multisplit puts there, as a multiset of (key, value) pairs."""
+    rng = np.random.default_rng(7)
+    n, P, sb = 700001, 8, 5
+    F = P << sb
+    kdt, vdt = kinds
+    k = rng.integers(-2 ** 30, 2 ** 30, n).astype(kdt)
+    v = None if vdt is None else (np.arange(n).astype(vdt))
+    dk, dv = dev(k), (None if v is None else dev(v))
+    nv().set_option("scatter_ptr_threads", threads)
+    try:
+        pk, pv, off = nv().partition(dk, dv, P, sub_bits=sb, unordered=True)
+        counts, ws = nv().partition_count(dk, P, sub_bits=sb, unordered=True)
+        assert torch.equal(counts, off[1:] - off[:-1])
+        perm = torch.from_numpy(rng.permutation(F)).cuda()
+        # bucket b's slot: buckets laid out in perm order, 3 pad rows between slots (odd alignment phases)
+        c_perm = counts[perm]
+        start_perm = torch.cumsum(c_perm + 3, 0) - (c_perm + 3)
+        start = torch.empty(F, dtype=torch.int64, device="cuda")
+        start[perm] = start_perm
+        total = int((c_perm + 3).sum().item())
+        ok = torch.zeros(total, dtype=dk.dtype, device="cuda")
+        ov = None if dv is None else torch.zeros(total, dtype=dv.dtype, device="cuda")
+        kp = (ok.data_ptr() + start * ok.element_size()).contiguous()
+        vp = None if dv is None else (ov.data_ptr() + start * ov.element_size()).contiguous()
+        nv().partition_scatter_ptrs(dk, dv, P, kp, vp, ws, sub_bits=sb, unordered=True)
+        torch.cuda.synchronize()
+    finally:
+        nv().set_option("scatter_ptr_threads", 1024)
+    okh, pkh = ok.cpu().numpy(), pk.cpu().numpy()
+    ovh, pvh = (None, None) if dv is None else (ov.cpu().numpy(), pv.cpu().numpy())
+    offh, sth, ch = off.cpu().numpy(), start.cpu().numpy(), counts.cpu().numpy()
+    for b in range(F):
+        got_k = okh[sth[b]:sth[b] + ch[b]]
+        want_k = pkh[offh[b]:offh[b + 1]]
+        if dv is None:
+            assert np.array_equal(np.sort(got_k), np.sort(want_k)), b
+        else:
+            got = np.stack([got_k.astype(np.int64), ovh[sth[b]:sth[b] + ch[b]].astype(np.int64)])
+            want = np.stack([want_k.astype(np.int64), pvh[offh[b]:offh[b + 1]].astype(np.int64)])
+            assert np.array_equal(got[:, np.lexsort(got)], want[:, np.lexsort(want)]), b
+        assert not okh[sth[b] + ch[b]:sth[b] + ch[b] + 3].any(), "pad rows behind bucket %d were written" % b
+
+
+def test_fused_plan_matches_the_push_layout_and_diverts_overflow():
+    """dpk_fused_plan: slot of (source rank, bucket) in the owner's receive buffer = source-rank-major, bucket-major
+    (what exchange_push delivers); a bucket that would end past the capacity goes to the dump columns."""
+    rng = np.random.default_rng(3)
+    G, P, sb = 4, 6, 2           # 6 partitions on 4 ranks: blocks of 2, the last rank owns none
+    F = P << sb
+    per_block = ((P + G - 1) // G) << sb
+    counts = rng.integers(0, 50, (G, F)).astype(np.int64)
+    allc = dev(counts)
+    base = np.arange(1, 2 * G + 1, dtype=np.int64) * (1 << 30)       # fake receive-buffer addresses [2][G]
+    dump_k = torch.empty(int(counts.sum()), dtype=torch.int64, device="cuda")
+    dump_v = torch.empty(int(counts.sum()), dtype=torch.float32, device="cuda")
+    for cap in (1 << 20, 300):
+        for rank in range(G):
+            err = torch.zeros(1, dtype=torch.int64, device="cuda")
+            kp, vp, seg = nv().fused_plan(allc, G, per_block, rank, dev(base), 8, 4, cap, dump_k, dump_v, err)
+            kp, vp, seg = kp.cpu().numpy(), vp.cpu().numpy(), seg.cpu().numpy()
+            b0, b1 = min(F, rank * per_block), min(F, (rank + 1) * per_block)
+            assert np.array_equal(seg, counts[:, b0:b1])
+            over = 0
+            for d in range(G):
+                lo, hi = min(F, d * per_block), min(F, (d + 1) * per_block)
+                first = counts[:rank, lo:hi].sum()
+                over = max(over, counts[:, lo:hi].sum() - cap)
+                run = 0
+                for b in range(lo, hi):
+                    local = counts[rank, :b].sum()
+                    if first + run + counts[rank, b] <= cap:
+                        assert kp[b] == base[d] + (first + run) * 8 and vp[b] == base[G + d] + (first + run) * 4
+                    else:
+                        assert kp[b] == dump_k.data_ptr() + local * 8 and vp[b] == dump_v.data_ptr() + local * 4
+                    run += counts[rank, b]
+            assert int(err.item()) == max(0, over)
+
+
 def test_choose_sub_bits_bounds():
     from dpark_b200 import shuffle
     assert shuffle.choose_sub_bits(1000, 8) == 0

@@ -58,6 +58,7 @@ def _patch_gpu_stages():
     columnar._hash_column = hash_column
     nv.partition_ids = partition_ids
     engine._device = lambda: torch.device("cpu")
+    engine.TEXT_INGEST = False     # the device tokeniser needs a GPU (tests/test_gpu_textingest.py); rows go through Python here
     engine.ROUTE_EVERYTHING = True
     engine._run_reduce = local("reduce")
     engine._run_group = local("group")

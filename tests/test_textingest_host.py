@@ -1,0 +1,111 @@
+"""Host logic of the device text ingest (dpark_b200/textingest.py): which user functions are recognised as the
+word-count tokeniser (structurally, never by probing), and which bytes a split owns.  No GPU needed."""
+import os
+import sys
+
+import pytest
+
+from dpark_b200 import textingest as ti
+
+
+def fm(x):
+    for w in x.strip().split():
+        yield (w, 1)
+
+
+def fm_other_names(line):
+    for word in line.split():
+        yield (word, 1)
+
+
+def fm_sep(x):
+    for w in x.strip().split(","):
+        yield (w, 1)
+
+
+def fm_two(x):
+    for w in x.strip().split():
+        yield (w, 2)
+
+
+def fm_lower(x):
+    for w in x.strip().split():
+        yield (w.lower(), 1)
+
+
+def fm_default(x, n=1):
+    for w in x.strip().split():
+        yield (w, 1)
+
+
+ONE = 1
+
+
+def fm_global(x):
+    for w in x.strip().split():
+        yield (w, ONE)
+
+
+def ctx():
+    sys.argv = [sys.argv[0]]
+    from dpark_b200 import DparkContext
+    return DparkContext("local")
+
+
+def test_only_exact_tokenisers_are_recognised(tmp_path):
+    p = tmp_path / "t.txt"
+    p.write_text("a b\n")
+    dc = ctx()
+    tf = dc.textFile(str(p))
+    yes = [tf.flatMap(fm), tf.flatMap(fm_other_names), tf.flatMap(lambda x: [(w, 1) for w in x.split()]),
+           tf.flatMap(lambda l: l.split()).map(lambda w: (w, 1)),
+           tf.flatMap(lambda l: l.strip().split()).map(lambda w: (w, 1))]
+    for r in yes:
+        assert ti.recognize(r) is tf
+    k = 1
+    no = [tf.flatMap(fm_sep), tf.flatMap(fm_two), tf.flatMap(fm_lower), tf.flatMap(fm_default), tf.flatMap(fm_global),
+          tf.flatMap(lambda l: l.split()).map(lambda w: (w, 1.0)),
+          tf.flatMap(lambda l: l.split()).map(lambda w: (w, k)),                 # closure
+          tf.flatMap(lambda l: l.split(None, 1)).map(lambda w: (w, 1)),
+          tf.flatMap(lambda l: l.split()).filter(lambda w: w).map(lambda w: (w, 1)),
+          tf.map(lambda l: l.upper()).flatMap(fm),                                # something between file and tokeniser
+          dc.makeRDD(["a b"], 1).flatMap(fm)]
+    for r in no:
+        assert ti.recognize(r) is None
+
+
+def test_a_subclassed_text_rdd_is_left_alone(tmp_path):
+    from dpark_b200.rdd import TextFileRDD
+
+    class Mine(TextFileRDD):
+        pass
+
+    p = tmp_path / "t.txt"
+    p.write_text("a b\n")
+    dc = ctx()
+    assert ti.recognize(Mine(dc, str(p)).flatMap(fm)) is None
+
+
+@pytest.mark.parametrize("split_size", [1, 3, 7, 16, 1000])
+def test_owned_ranges_are_the_lines_a_split_yields(tmp_path, split_size):
+    """owned_range == the bytes of the lines TextFileRDD.compute yields for the split (a line belongs to the split it
+    starts in), for splits smaller than a line, empty lines, a missing final newline."""
+    from dpark_b200.rdd import TextFileRDD
+    body = b"alpha beta\n\n\ngamma\nd\n" + b"x" * 40 + b"\nlast line without newline"
+    p = tmp_path / "t.txt"
+    p.write_bytes(body)
+    dc = ctx()
+    tf = TextFileRDD(dc, str(p), splitSize=split_size)
+    size = os.path.getsize(str(p))
+    prev_end = 0
+    for sp in tf.splits:
+        a, b = ti.owned_range(str(p), sp.begin, sp.end, size)
+        assert a == prev_end or a >= prev_end
+        lines = list(tf.compute(sp))
+        chunk = body[a:b]
+        want = chunk.decode().split("\n")
+        if chunk.endswith(b"\n"):
+            want = want[:-1]
+        assert (lines == want) if chunk else (lines == [])
+        prev_end = b
+    assert prev_end == size
