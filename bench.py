@@ -83,6 +83,10 @@ def parse():
     ap.add_argument("--agg-impl", type=int, default=-1, help="A/B: reduce-side merge kernel (0 = round 1, 1 = row-index tags)")
     ap.add_argument("--overlap-push", type=int, default=1, help="N>1, push exchange: groups of map splits whose push "
                     "overlaps the scatter of the next group (1 = no overlap)")
+    ap.add_argument("--pipeline", default="", help="N>1, push exchange, reduceByKey configs: GxQ = map splits in G groups "
+                    "(push of one overlaps the multisplit of the next) and every block in Q parts (reduce side of a part "
+                    "overlaps the push of the next): dpark_b200.peer.shuffle_pipelined; '' or 'off' = one push, then reduce")
+    ap.add_argument("--copy-sms", type=int, default=-1, help="N>1, overlapped push: whole SMs the overlapped copy kernel takes")
     ap.add_argument("--exchange", default="push", choices=["push", "fused", "peer", "nccl"],
                     help="N>1: push = local scatter, then one kernel pushing each peer's block over NVLink; "
                          "fused (alias peer) = the scatter kernel stores into peer memory; nccl = alltoallv")
@@ -107,6 +111,7 @@ def workload_config(args, world):
         "map_splits_per_gpu": args.map_splits, "parallelism": "dp%d" % world,
         "exchange": None if world == 1 else args.exchange, "map_combine": bool(args.map_combine),
         "overlap_push_groups": args.overlap_push if world > 1 else None,
+        "pipeline": (args.pipeline or None) if world > 1 else None,
         "l2_policy": "inputs_larger_than_l2 (%.1f GB of rows per GPU per step vs 126 MB L2)"
                      % (args.rows_per_gpu * (_isz(cfg["kdt"]) + _isz(cfg["vdt"])) / 1e9),
         "sub_buckets_per_partition": 1 << shuffle.choose_sub_bits(args.rows_per_gpu, args.parts_per_gpu * world, world),
@@ -526,11 +531,20 @@ def run_ours(args):
             from dpark_b200 import peer
             px = peer.PeerExchange(int(n * recv_factor) + (1 << 20), kdt, xv_dt, dev,
                                    mode="push" if args.exchange == "push" else "fused")
+            if args.copy_sms >= 0:
+                px.copy_sms = args.copy_sms
         except Exception as e:  # symmetric memory unavailable on this box/build: say so, use NCCL
             sys.stderr.write("peer exchange unavailable (%s: %s); using NCCL alltoallv\n" % (type(e).__name__, e))
             px = None
 
+    pipe = None
+    if args.pipeline and args.pipeline != "off" and px is not None and px.mode == "push" and not group and not args.map_combine:
+        g_, q_ = args.pipeline.lower().split("x")
+        pipe = (int(g_), int(q_))
+
     def step():
+        if pipe is not None:
+            return peer.shuffle_pipelined(px, kc, vc, P, "sum", None, sub_bits, pipe[0], pipe[1])
         if px is not None and px.mode == "fused" and not group and not args.map_combine:
             rx = peer.map_side_push(px, kc, vc, P, None, sub_bits)
             return shuffle.reduce_side(rx, "sum", P)
@@ -571,6 +585,8 @@ def run_ours(args):
         nrecv_local = int(ov_.numel())
         checked = (gk_, gs_, ng_, ov_, poff_)
     else:
+        if pipe is not None:
+            out = peer.merge_part_results(out)
         ok_, ov_, po_, cnt_ = out
         po_h, cnt_h = po_.cpu().tolist(), cnt_.cpu().tolist()
         if any(c < 0 for c in cnt_h):

@@ -33,7 +33,7 @@ EXPORTS = [
     "dpk_launch_count", "dpk_prof_enable", "dpk_prof_count", "dpk_prof_get",
     "dpk_dict_encode_workspace_bytes", "dpk_dict_encode", "dpk_set_option",
     "dpk_key_or", "dpk_radix_pass", "dpk_group_heads_workspace_bytes", "dpk_group_heads", "dpk_gather_i64",
-    "dpk_partition_scatter_ptrs", "dpk_copy_segments", "dpk_hash_tuple", "dpk_push_plan", "dpk_fused_plan",
+    "dpk_partition_scatter_ptrs", "dpk_copy_segments", "dpk_hash_tuple", "dpk_push_plan", "dpk_push_plan_part", "dpk_pipe_plan", "dpk_fused_plan",
     "dpk_tokenize_blocks", "dpk_tokenize_count", "dpk_tokenize_emit", "dpk_gather_bytes",
     "dpk_radix_pass_seg_workspace_bytes", "dpk_radix_pass_seg",
 ]
@@ -72,6 +72,8 @@ def lib():
         L.dpk_partition_scatter_ptrs.argtypes = [vp, ci, vp, vp, i32, i64, i32, vp, i32, i32, vp, vp, vp, i64, vp]
         L.dpk_copy_segments.argtypes = [vp, vp, vp, i32, vp]
         L.dpk_push_plan.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, C.c_uint64, C.c_uint64, vp, i32, i32, i64, vp, vp, vp, vp, vp, vp]
+        L.dpk_push_plan_part.argtypes = [vp, i32, i32, i32, i32, i32, i32, i64, i32, i32, i32, C.c_uint64, C.c_uint64, vp, i32, i32, i64, vp, vp, vp, vp, vp, vp]
+        L.dpk_pipe_plan.argtypes = [vp, i32, i32, i32, i32, i32, i64, i32, i32, i32, C.c_uint64, C.c_uint64, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp]
         L.dpk_fused_plan.argtypes = [vp, i32, i32, i32, i32, i32, vp, i32, i32, i64, C.c_uint64, C.c_uint64, vp, vp, vp, vp, vp]
         L.dpk_tokenize_blocks.restype = i64
         L.dpk_tokenize_blocks.argtypes = [i64]
@@ -253,33 +255,70 @@ def partition_scatter_ptrs(keys, vals, P, key_ptrs, val_ptrs, ws, thresholds=Non
                                             _ptr(val_ptrs), _ptr(ws), ws.numel(), _stream()))
 
 
-def copy_segments(src_ptrs, dst_ptrs, nbytes):
+def copy_segments(src_ptrs, dst_ptrs, nbytes, sms=0):
     """One launch copying nbytes[s] bytes from device address src_ptrs[s] to dst_ptrs[s] (int64 device
-    tensors; destinations may be peer-GPU memory): the exchange as block pushes over NVLink."""
+    tensors; destinations may be peer-GPU memory): the exchange as block pushes over NVLink.
+    sms > 0: the copy runs on that many whole SMs only (dpk_set_option "copy_sms") -- for a push that overlaps
+    another kernel."""
     _need_cuda(src_ptrs, dst_ptrs, nbytes)
     if not (src_ptrs.numel() == dst_ptrs.numel() == nbytes.numel()):
         raise ValueError("segment table columns differ in length")
-    _check(lib().dpk_copy_segments(_ptr(src_ptrs), _ptr(dst_ptrs), _ptr(nbytes), nbytes.numel(), _stream()))
+    if sms:
+        set_option("copy_sms", int(sms))
+    try:
+        _check(lib().dpk_copy_segments(_ptr(src_ptrs), _ptr(dst_ptrs), _ptr(nbytes), nbytes.numel(), _stream()))
+    finally:
+        if sms:
+            set_option("copy_sms", 0)
 
 
-def push_plan(all_counts, nranks, per_block, my_src, my_rank, keys, vals, dst_base, capacity, need_over, want_seg=True):
-    """dpk_push_plan: (src_ptrs, dst_ptrs, nbytes [ncols * nranks], seg [nsrc, own buckets] | None), one launch.
+def push_plan(all_counts, nranks, per_block, my_src, my_rank, keys, vals, dst_base, capacity, need_over, want_seg=True,
+              part=None, dst_row0=0):
+    """dpk_push_plan(_part): (src_ptrs, dst_ptrs, nbytes [ncols * nranks], seg [nsrc, own buckets] | None), one launch.
     keys / vals: my bucket-major columns (vals may be None); dst_base: device int64 [ncols * nranks] receive-buffer
-    addresses (column-major)."""
+    addresses (column-major).  part = (blk_lo, blk_hi): only those buckets of every destination's block, into the
+    region of `capacity` rows starting at row dst_row0 of the receive buffers."""
     _need_cuda(all_counts, dst_base, need_over)
     nsrc, F = int(all_counts.shape[0]), int(all_counts.shape[1])
     ncols = 1 if vals is None else 2
     dev = all_counts.device
+    lo, hi = (0, per_block) if part is None else part
     src = torch.empty(ncols * nranks, dtype=torch.int64, device=dev)
     dst = torch.empty(ncols * nranks, dtype=torch.int64, device=dev)
     nby = torch.empty(ncols * nranks, dtype=torch.int64, device=dev)
-    b0, b1 = min(F, my_rank * per_block), min(F, (my_rank + 1) * per_block)
-    seg = torch.empty((nsrc, b1 - b0), dtype=torch.int64, device=dev) if want_seg else None
-    _check(lib().dpk_push_plan(_ptr(all_counts), nsrc, nranks, F, per_block, my_src, my_rank, ncols,
+    b0, b1 = min(F, my_rank * per_block + lo), min(F, (my_rank + 1) * per_block, my_rank * per_block + hi)
+    seg = torch.empty((nsrc, max(0, b1 - b0)), dtype=torch.int64, device=dev) if want_seg else None
+    _check(lib().dpk_push_plan_part(_ptr(all_counts), nsrc, nranks, F, per_block, lo, hi, dst_row0, my_src, my_rank, ncols,
+                                    C.c_uint64(keys.data_ptr()), C.c_uint64(0 if vals is None else vals.data_ptr()),
+                                    _ptr(dst_base), keys.element_size(), 0 if vals is None else vals.element_size(),
+                                    capacity, _ptr(src), _ptr(dst), _ptr(nby), _ptr(need_over), _ptr(seg), _stream()))
+    return src, dst, nby, seg
+
+
+def pipe_plan(all_counts, nranks, per_block, nparts, region_rows, my_src, my_rank, keys, vals, dst_base, need_over,
+              want_seg=True):
+    """dpk_pipe_plan: (bucket_base[F], src_ptrs, dst_ptrs, nbytes [nparts, ncols * nranks], seg [nparts, nsrc, per_block /
+    nparts] | None) for one group of map splits; keys / vals: the group's SEND buffers (allocated with pipe_pad_rows()
+    spare rows)."""
+    _need_cuda(all_counts, dst_base, need_over, keys, vals)
+    nsrc, F = int(all_counts.shape[0]), int(all_counts.shape[1])
+    ncols = 1 if vals is None else 2
+    dev = all_counts.device
+    base = torch.empty(F, dtype=torch.int64, device=dev)
+    src = torch.empty((nparts, ncols * nranks), dtype=torch.int64, device=dev)
+    dst = torch.empty((nparts, ncols * nranks), dtype=torch.int64, device=dev)
+    nby = torch.empty((nparts, ncols * nranks), dtype=torch.int64, device=dev)
+    seg = torch.empty((nparts, nsrc, per_block // nparts), dtype=torch.int64, device=dev) if want_seg else None
+    _check(lib().dpk_pipe_plan(_ptr(all_counts), nsrc, nranks, F, per_block, nparts, region_rows, my_src, my_rank, ncols,
                                C.c_uint64(keys.data_ptr()), C.c_uint64(0 if vals is None else vals.data_ptr()),
                                _ptr(dst_base), keys.element_size(), 0 if vals is None else vals.element_size(),
-                               capacity, _ptr(src), _ptr(dst), _ptr(nby), _ptr(need_over), _ptr(seg), _stream()))
-    return src, dst, nby, seg
+                               _ptr(base), _ptr(src), _ptr(dst), _ptr(nby), _ptr(need_over), _ptr(seg), _stream()))
+    return base, src, dst, nby, seg
+
+
+def pipe_pad_rows(nranks, nparts, key_bytes, val_bytes=None):
+    """Spare rows a pipelined step's send buffer needs for the congruence pads (dpk_pipe_plan)."""
+    return nranks * nparts * (16 // min(key_bytes, val_bytes or key_bytes))
 
 
 def fused_plan(all_counts, nranks, per_block, my_rank, dst_base, key_bytes, val_bytes, capacity, dump_keys, dump_vals,

@@ -727,6 +727,21 @@ int dpk_set_option(const char *name, int64_t value) {
         g_scatter_seg_wide = value != 0;
         return DPK_OK;
     }
+    if (strcmp(name, "scatter_wide_from") == 0) {
+        if (value < 0 || value > DPK_MAX_PARTITIONS) return fail(DPK_ERR_INVALID, "scatter_wide_from out of range");
+        g_scatter_wide_from = (int)value;
+        return DPK_OK;
+    }
+    if (strcmp(name, "copy_tma") == 0) {
+        if (value != 0 && value != 1) return fail(DPK_ERR_INVALID, "copy_tma must be 0 or 1");
+        g_copy_tma = (int)value;
+        return DPK_OK;
+    }
+    if (strcmp(name, "copy_sms") == 0) {
+        if (value < 0 || value > 1024) return fail(DPK_ERR_INVALID, "copy_sms out of range");
+        g_copy_sms = (int)value;
+        return DPK_OK;
+    }
     if (strcmp(name, "scatter_ptr_bulk") == 0) {
         if (value != 0 && value != 1) return fail(DPK_ERR_INVALID, "scatter_ptr_bulk must be 0 or 1");
         g_scatter_ptr_bulk = (int)value;

@@ -33,6 +33,7 @@ extern int g_scatter_items;  // dpk_partition.cu, rows per thread and tile of th
 extern int g_count_mode;  // dpk_partition.cu, A/B switch of the histogram pass
 extern int g_scatter_threads;  // dpk_partition.cu, CTA size of the bulk multisplit (256 or 512)
 extern int g_scatter_seg_wide;  // dpk_partition.cu
+extern int g_scatter_wide_from, g_copy_sms, g_copy_tma;  // dpk_partition.cu / dpk_peer.cu
 extern int g_scatter_ptr_bulk, g_scatter_ptr_threads;  // dpk_partition.cu, pointer mode (fused scatter + exchange)
 extern int g_scatter_bulk;  // dpk_partition.cu, 1 = unordered multisplits use the TMA bulk-store kernel
 

@@ -47,6 +47,7 @@ int g_scatter_seg_wide = 1;
 // kernel for unordered multisplits; 0 = the round-1 kernel (per-thread 8-byte stores over NVLink).
 // dpk_set_option("scatter_ptr_threads"): CTA size of the bulk kernel in pointer mode: 1024 (default; 8192-row tiles: the
 // bucket runs that cross NVLink are twice as long) or 512
+int g_scatter_wide_from = 512;   // dpk_set_option("scatter_wide_from"): bucket count from which plain launches use 8192-row tiles (0 = never)
 int g_scatter_ptr_bulk = 1;
 int g_scatter_ptr_threads = 1024;   // dpk_set_option("scatter_seg_wide"): segmented launches use the 1024-thread / 8192-row form
 
@@ -742,6 +743,9 @@ static int launch_scatter_bulk(const void *keys, const void *vals, int64_t n, co
     // rows of 4-byte columns: a 4096-row tile's bucket runs are 64 bytes, where the bulk stores are issue-bound
     // (measured on C4: 1057 GB/s with 4096-row tiles against 2003 GB/s with 8192-row tiles)
     if (nt == 512 && g_scatter_seg_wide && sizeof(KeyT) <= 4 && (vb == 0 || vb <= 4)) nt = 1024;
+    // from 512 buckets up a 4096-row tile's runs are 64 bytes even for 8-byte rows: measured 1.49 ms (4096-row tiles)
+    // against 1.19 ms (8192-row tiles) per 1e8 (int64,int64) rows at 512 buckets
+    if (nt == 512 && g_scatter_wide_from > 0 && f.nbuckets() >= g_scatter_wide_from) nt = 1024;
     const bool ptr_mode = pl.seg.key_ptrs != nullptr;
     if (ptr_mode && nt == 512 && g_scatter_ptr_threads == 1024) nt = 1024;
     if (nt == 1024 && bulk_smem((int)sizeof(KeyT), vb, f.nbuckets(), 8192, ptr_mode).total > 220 * 1024) nt = 512;

@@ -65,6 +65,9 @@ class PeerExchange(object):
         self.err = torch.zeros(1, dtype=torch.int64, device=self.device)   # max rows any rank needed beyond capacity
         self._closed = False
         self._dump = None
+        # SMs an OVERLAPPED push may take (map_exchange_overlapped): the copy kernel is launched on the high-priority
+        # side stream as whole-SM CTAs, the multisplit of the next group runs on the SMs that are left
+        self.copy_sms = 16
 
     # the buffer set of the current step
     @property
@@ -223,7 +226,7 @@ def map_exchange_overlapped(px, key_chunks, val_chunks, P, thresholds=None, sub_
         ready.record(main)
         with torch.cuda.stream(px.side):
             px.side.wait_event(ready)
-            nv.copy_segments(src, dst, nby)
+            nv.copy_segments(src, dst, nby, sms=px.copy_sms if h + 1 < H else 0)   # the last push overlaps nothing
             for t in (out_k, out_v, src, dst, nby):
                 if t is not None:
                     t.record_stream(px.side)
@@ -234,6 +237,130 @@ def map_exchange_overlapped(px, key_chunks, val_chunks, P, thresholds=None, sub_
     keys, vals = px.keys, (px.vals if has_v else None)
     px.advance()
     return Received(keys, vals, seg, b0 >> sub_bits, (b1 - b0) >> sub_bits, sub_bits, bound=True)
+
+
+def shuffle_pipelined(px, key_chunks, val_chunks, P, op, thresholds=None, sub_bits=0, groups=2, parts=2):
+    """The whole reduceByKey step of one rank with the NVLink transfer hidden behind the kernels on both sides of it.
+
+    Two cuts, both along orders the data already has:
+      * the rank's map splits are cut into `groups` (consecutive row ranges), each multisplit into its own bucket-major
+        buffer; a group's blocks are pushed (side stream, a few whole SMs: PeerExchange.copy_sms) while the next
+        group is being partitioned on the remaining SMs;
+      * every destination's block of buckets is cut into `parts` (consecutive partitions: a rank owns `nparts`
+        partitions, part q covers partitions [q * nparts / parts, (q + 1) * nparts / parts)); the first parts of ALL
+        groups are pushed first, and as soon as they have landed everywhere (one barrier) the reduce side of those
+        partitions (dpk_combine) starts while the later parts are still crossing NVLink into their own region of the
+        receive buffers.
+    The reference's reducers likewise start merging a bucket as soon as its map outputs are fetched while other
+    fetches are in flight (ParallelShuffleFetcher, dpark/shuffle.py:365-420).  Nothing is read by the host.
+
+    Needs map splits that are consecutive slices of one buffer per group and nparts divisible into `parts` (else fewer
+    parts are used).  Returns [(keys, vals, part_offsets, counts, part_first, nparts)] -- one reduce_side result per
+    part, in partition order."""
+    from . import shuffle as sh
+    G, rank, dev = px.world, px.rank, px.device
+    F = P << sub_bits
+    M = len(key_chunks)
+    H = max(1, min(groups, M))
+    has_v = val_chunks[0] is not None
+    blocks = sh.owner_blocks(P, G)
+    per_parts = (P + G - 1) // G                       # partitions per rank (the last ranks may own fewer)
+    Q = max(1, min(parts, per_parts))
+    while per_parts % Q:
+        Q -= 1
+    bounds = [(M * h) // H for h in range(H + 1)]
+    gk, gv = [], []
+    for h in range(H):
+        sel = slice(bounds[h], bounds[h + 1])
+        k1 = sh._as_one(key_chunks[sel])
+        v1 = sh._as_one(val_chunks[sel]) if has_v else None
+        if k1 is None or (has_v and v1 is None) or k1.numel() >= (1 << 31):
+            raise ValueError("shuffle_pipelined needs every group's map splits to be consecutive slices of one buffer")
+        gk.append(k1)
+        gv.append(v1)
+    counts, wss = [], []
+    for k in gk:
+        c, ws = nv.partition_count(k, P, thresholds, False, sub_bits, None, None, True)
+        counts.append(c)
+        wss.append(ws)
+    gc = torch.stack(counts)                                            # [H, F] rows per group and bucket
+    all_counts = torch.empty(G * H * F, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(all_counts, gc.reshape(-1), group=px.group)   # the MapOutputTracker
+    all_counts = all_counts.view(G * H, F)                              # source (rank, group) major
+    per_block = per_parts << sub_bits
+    region = (px.capacity // Q) & ~15                                   # rows of one part's region in a receive buffer
+    dst_base = px.dst_base if has_v else px.key_base
+    pad = nv.pipe_pad_rows(G, Q, gk[0].element_size(), gv[0].element_size() if has_v else None)
+    main = torch.cuda.current_stream()
+    bufs, plans, segs = [], [[None] * H for _ in range(Q)], None
+    landed = [torch.cuda.Event() for _ in range(Q)]
+    for h in range(H):
+        n_h = int(gk[h].numel())
+        out_k = torch.empty(n_h + pad, dtype=gk[h].dtype, device=dev)
+        out_v = torch.empty(n_h + pad, dtype=gv[h].dtype, device=dev) if has_v else None
+        # one launch: where every bucket of this group goes in the send buffer (blocks padded so that every push is
+        # congruent mod 16 bytes to its landing place) + the segment tables of the Q pushes + my own segment matrices
+        base, src, dst, nby, sg = nv.pipe_plan(all_counts, G, per_block, Q, region, rank * H + h, rank, out_k, out_v,
+                                               dst_base, px.err, want_seg=(h == 0))
+        if h == 0:
+            segs = sg
+        nv.partition_scatter(gk[h], gv[h], P, base, out_k, out_v, wss[h], thresholds, False, sub_bits, None, True)
+        bufs.append((out_k, out_v))
+        for q in range(Q):
+            plans[q][h] = (src[q], dst[q], nby[q])
+        ready = torch.cuda.Event()
+        ready.record(main)
+        with torch.cuda.stream(px.side):                 # part 0 of this group leaves while the next group is partitioned
+            px.side.wait_event(ready)
+            nv.copy_segments(*plans[0][h], sms=px.copy_sms)
+    with torch.cuda.stream(px.side):
+        landed[0].record(px.side)
+        for q in range(1, Q):                            # the later parts cross NVLink under the reduce side of the earlier
+            for h in range(H):
+                nv.copy_segments(*plans[q][h], sms=px.copy_sms)
+            landed[q].record(px.side)
+        for out_k, out_v in bufs:
+            out_k.record_stream(px.side)
+            if out_v is not None:
+                out_v.record_stream(px.side)
+        for q in range(Q):
+            for t3 in plans[q]:
+                for t in t3:
+                    t.record_stream(px.side)
+    keys, vals = px.keys, (px.vals if has_v else None)
+    first = blocks[rank]
+    nparts = blocks[rank + 1] - blocks[rank]
+    results = []
+    for q in range(Q):
+        main.wait_event(landed[q])
+        px.barrier()                                     # part q of every peer's pushes has landed here
+        p0 = min(nparts, q * (per_parts // Q))
+        p1 = min(nparts, (q + 1) * (per_parts // Q))
+        if p1 <= p0:
+            continue
+        seg = segs[q][:, :(p1 - p0) << sub_bits].contiguous()         # [G * H sources, my buckets of part q]
+        rk = keys[q * region:(q + 1) * region]
+        rv = None if vals is None else vals[q * region:(q + 1) * region]
+        ok, ov, po, cnt = nv.combine(rk, rv, op, P, seg, first + p0, p1 - p0, thresholds, sub_bits)
+        results.append((ok, ov, po, cnt, first + p0, p1 - p0))
+    px.advance()
+    return results
+
+
+def merge_part_results(results):
+    """One (keys, vals, part_offsets, counts) like shuffle.reduce_side from shuffle_pipelined's per-part results
+    (copies; for checks and callers that want one buffer -- the pipelined step itself never needs it)."""
+    ks, vs, pos, cnts, base = [], [], [], [], 0
+    for ok, ov, po, cnt, _, _ in results:
+        n = int(po[-1].item())
+        ks.append(ok[:n])
+        vs.append(ov[:n])
+        pos.append(po[:-1] + base)
+        cnts.append(cnt)
+        base += n
+    dev = ks[0].device
+    pos.append(torch.tensor([base], dtype=torch.int64, device=dev))
+    return torch.cat(ks), torch.cat(vs), torch.cat(pos), torch.cat(cnts)
 
 
 def _map_exchange_overlapped_splits(px, key_chunks, val_chunks, P, thresholds=None, sub_bits=0, unordered=True, halves=2):

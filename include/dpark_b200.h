@@ -157,6 +157,28 @@ int dpk_push_plan(const int64_t *all_counts, int32_t nsrc, int32_t nranks, int32
                   int32_t my_src, int32_t my_rank, int32_t ncols, uint64_t src_keys, uint64_t src_vals,
                   const uint64_t *dst_base, int32_t key_bytes, int32_t val_bytes, int64_t capacity, uint64_t *src_ptrs,
                   uint64_t *dst_ptrs, int64_t *nbytes, int64_t *need_over, int64_t *seg_out, dpk_stream_t stream);
+/* dpk_push_plan for a PART of every destination's block: the buckets [blk_lo, blk_hi) relative to the block's first
+ * bucket, landing in the region of `capacity` rows that starts at row dst_row0 of every receive buffer (seg_out: my own
+ * part).  A pipelined shuffle pushes the blocks in parts so that the reduce side (dpk_combine over the part's
+ * partitions) runs on the first part while the next is still crossing NVLink. */
+int dpk_push_plan_part(const int64_t *all_counts, int32_t nsrc, int32_t nranks, int32_t nbuckets, int32_t per_block,
+                       int32_t blk_lo, int32_t blk_hi, int64_t dst_row0, int32_t my_src, int32_t my_rank, int32_t ncols,
+                       uint64_t src_keys, uint64_t src_vals, const uint64_t *dst_base, int32_t key_bytes, int32_t val_bytes,
+                       int64_t capacity, uint64_t *src_ptrs, uint64_t *dst_ptrs, int64_t *nbytes, int64_t *need_over,
+                       int64_t *seg_out, dpk_stream_t stream);
+/* The plan of a pipelined shuffle step, one launch per group of map splits: bucket_base[nbuckets] = where the multisplit
+ * (dpk_partition_scatter) puts every bucket of this group in the send buffer, and src_ptrs / dst_ptrs / nbytes
+ * [nparts][ncols][nranks] = the pushes of part q (the q-th of nparts equal slices of every destination's block of
+ * per_block buckets) into region q (region_rows rows, starting at row q * region_rows) of every receive buffer.  In
+ * front of every (destination, part) block the send buffer holds up to 16 / min(key_bytes, val_bytes) - 1 pad rows so
+ * that source and destination of every push are congruent mod 16 bytes (the copy then runs through the TMA); size it
+ * rows + nranks * nparts * (16 / min element size).  seg_out[nparts][nsrc][per_block / nparts]: the segment matrices of
+ * my own parts for dpk_combine (columns beyond my last bucket are 0).  need_over as in dpk_push_plan, per region. */
+int dpk_pipe_plan(const int64_t *all_counts, int32_t nsrc, int32_t nranks, int32_t nbuckets, int32_t per_block,
+                  int32_t nparts, int64_t region_rows, int32_t my_src, int32_t my_rank, int32_t ncols, uint64_t src_keys,
+                  uint64_t src_vals, const uint64_t *dst_base, int32_t key_bytes, int32_t val_bytes, int64_t *bucket_base,
+                  uint64_t *src_ptrs, uint64_t *dst_ptrs, int64_t *nbytes, int64_t *need_over, int64_t *seg_out,
+                  dpk_stream_t stream);
 /* The same lookup for the FUSED scatter + exchange (dpk_partition_scatter_ptrs): key_ptrs[b] / val_ptrs[b] (device
  * arrays of nbuckets entries) = the address of the slot of (source my_rank, bucket b) in its owner's receive buffer,
  * laid out source-rank-major then bucket-major exactly as the push delivers it.  A bucket that would end past

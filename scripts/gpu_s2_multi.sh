@@ -35,6 +35,23 @@ for extra in "$@"; do
     fusedold) DPK_OPTIONS=scatter_ptr_bulk=0 run c2fusedold --exchange fused $Q ;;
     ov2) run c2ov2 --exchange push --overlap-push 2 $Q ;;
     ov4) run c2ov4 --exchange push --overlap-push 4 $Q ;;
+    ov2s0) run c2ov2s0 --exchange push --overlap-push 2 --copy-sms 0 $Q ;;
+    ov2s16) run c2ov2s16 --exchange push --overlap-push 2 --copy-sms 16 $Q ;;
+    ov4s16) run c2ov4s16 --exchange push --overlap-push 4 --copy-sms 16 $Q ;;
+    ov4s32) run c2ov4s32 --exchange push --overlap-push 4 --copy-sms 32 $Q ;;
+    pushs16) DPK_OPTIONS=copy_sms=16 run c2pushs16 --exchange push $Q ;;
+    pushs32) DPK_OPTIONS=copy_sms=32 run c2pushs32 --exchange push $Q ;;
+    pushsb4) run c2pushsb4 --exchange push --sub-bits 4 $Q ;;
+    fusedsb4) run c2fusedsb4 --exchange fused --sub-bits 4 $Q ;;
+    text) echo "== text ingest tests + wc_e2e"; timeout 600 python -m pytest tests/test_gpu_textingest.py tests/test_gpu_rdd.py -m gpu -x -q 2>&1 | tail -3
+          timeout 300 python scripts/wc_e2e.py 2>&1 | tail -3; timeout 300 python scripts/wc_e2e.py 1000000 rowwise 2>&1 | tail -3 ;;
+    p1x2) run c2p1x2 --pipeline 1x2 $Q ;;
+    p2x2) run c2p2x2 --pipeline 2x2 $Q ;;
+    p4x2) run c2p4x2 --pipeline 4x2 $Q ;;
+    p4x1) run c2p4x1 --pipeline 4x1 $Q ;;
+    p4x4) run c2p4x4 --pipeline 4x4 $Q ;;
+    p4x2s32) run c2p4x2s32 --pipeline 4x2 --copy-sms 32 $Q ;;
+    p4x2s12) run c2p4x2s12 --pipeline 4x2 --copy-sms 12 $Q ;;
     c2) run c2 ;;
     c4) run c4 --config c4 --steps 5 --e2e-steps 1 --e2e-depth 2 ;;
     c4fused) run c4fused --config c4 --steps 5 --exchange fused $Q ;;

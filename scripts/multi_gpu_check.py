@@ -74,10 +74,30 @@ def main():
             rx_push = peer.exchange_push(px, shuffle.map_side(kd, vd, P, None, False, sb_eff), need_host_count=True)
             same = (same and torch.equal(rx_nccl.keys, rx_push.keys) and torch.equal(rx_nccl.vals, rx_push.vals)
                     and torch.equal(rx_nccl.seg, rx_push.seg) and rx_nccl.nparts == rx_push.nparts)
+            # the pipelined step (groups of map splits x parts of every block, push under the kernels on both sides)
+            kall, vall = torch.from_numpy(np.concatenate(ks)).to(dev), torch.from_numpy(np.concatenate(vs)).to(dev)
+            cuts = [0, n // 4, n // 2, n - 7, n]
+            kcs = [kall[a:b] for a, b in zip(cuts[:-1], cuts[1:])]
+            vcs = [vall[a:b] for a, b in zip(cuts[:-1], cuts[1:])]
+            for gq in ((2, 2), (4, 1), (3, 4)):
+                parts_res = peer.shuffle_pipelined(px, kcs, vcs, P, "sum", None, sb_eff, gq[0], gq[1])
+                px.check()
+                got_parts = {}
+                for ok_, ov_, po_, cnt_, pf_, np_ in parts_res:
+                    po_l, cnt_l = po_.cpu().tolist(), cnt_.cpu().tolist()
+                    for j in range(np_):
+                        got_parts[pf_ + j] = (ok_[po_l[j]:po_l[j] + cnt_l[j]].cpu().numpy(),
+                                              ov_[po_l[j]:po_l[j] + cnt_l[j]].cpu().numpy())
+                same = same and sorted(got_parts) == [p for p, _, _ in mine]
+                for p, wk_, wv_ in mine:
+                    if p in got_parts:
+                        gk_, gv_ = got_parts[p]
+                        o1, o2 = np.argsort(gk_), np.argsort(wk_)
+                        same = same and np.array_equal(gk_[o1], wk_[o2]) and np.array_equal(gv_[o1], wv_[o2])
             flags = [None] * world
             dist.all_gather_object(flags, bool(same))
             if rank == 0:
-                print("case %-14s fused scatter == block push == NCCL alltoallv on every rank: %s" % (case, all(flags)))
+                print("case %-14s fused scatter == block push == NCCL alltoallv, pipelined step == plain step on every rank: %s" % (case, all(flags)))
                 ok_all &= all(flags)
         gathered = [None] * world
         dist.all_gather_object(gathered, mine)

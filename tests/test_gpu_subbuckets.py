@@ -238,6 +238,144 @@ def test_fused_plan_matches_the_push_layout_and_diverts_overflow():
             assert int(err.item()) == max(0, over)
 
 
+@pytest.mark.parametrize("H,Q", [(1, 1), (2, 2), (3, 4)])
+def test_push_plan_parts_tile_the_blocks(H, Q):
+    """dpk_push_plan_part: pushing every destination's block in Q parts into Q regions of the receive buffers, from H
+    groups per rank, must (a) cover every row of the map output exactly once, (b) land each part's rows
+    (rank, group)-major then bucket-major inside its region -- the layout dpk_combine reads with the part's seg matrix."""
+    rng = np.random.default_rng(17)
+    G, P, sb = 4, 16, 3
+    F = P << sb
+    per_parts = P // G
+    per_block = per_parts << sb
+    part_blk = (per_parts // Q) << sb
+    S = G * H
+    counts = rng.integers(0, 40, (S, F)).astype(np.int64)
+    allc = dev(counts)
+    region = 5000
+    base = (np.arange(1, 2 * G + 1, dtype=np.int64) << 32)          # fake receive-buffer addresses [2][G]
+    for rank in range(G):
+        for h in range(H):
+            my = rank * H + h
+            n_mine = int(counts[my].sum())
+            out_k = torch.empty(max(n_mine, 1), dtype=torch.int64, device="cuda")
+            out_v = torch.empty(max(n_mine, 1), dtype=torch.float32, device="cuda")
+            covered = 0
+            for q in range(Q):
+                err = torch.zeros(1, dtype=torch.int64, device="cuda")
+                src, dst, nby, seg = nv().push_plan(allc, G, per_block, my, rank, out_k, out_v, dev(base), region, err,
+                                                    part=(q * part_blk, (q + 1) * part_blk), dst_row0=q * region)
+                src, dst, nby, seg = src.cpu().numpy(), dst.cpu().numpy(), nby.cpu().numpy(), seg.cpu().numpy()
+                assert int(err.item()) == 0
+                lo_r, hi_r = rank * per_block + q * part_blk, rank * per_block + (q + 1) * part_blk
+                assert np.array_equal(seg, counts[:, lo_r:hi_r])
+                for d in range(G):
+                    lo, hi = d * per_block + q * part_blk, d * per_block + (q + 1) * part_blk
+                    rows = counts[my, lo:hi].sum()
+                    first_src = counts[my, :lo].sum()
+                    first_dst = counts[:my, lo:hi].sum()
+                    assert nby[d] == rows * 8 and nby[G + d] == rows * 4
+                    assert src[d] == out_k.data_ptr() + first_src * 8 and src[G + d] == out_v.data_ptr() + first_src * 4
+                    assert dst[d] == base[d] + (q * region + first_dst) * 8
+                    assert dst[G + d] == base[G + d] + (q * region + first_dst) * 4
+                    covered += rows
+            assert covered == n_mine
+    # a region that is too small: clamped, and reported
+    err = torch.zeros(1, dtype=torch.int64, device="cuda")
+    out_k = torch.empty(int(counts[0].sum()), dtype=torch.int64, device="cuda")
+    src, dst, nby, _ = nv().push_plan(allc, G, per_block, S - 1, G - 1, out_k, None, dev(base[:G]), 100, err,
+                                      part=(0, part_blk), dst_row0=0)
+    need = max(counts[:, d * per_block:d * per_block + part_blk].sum() for d in range(G))
+    assert int(err.item()) == need - 100
+    for d in range(G):
+        first_dst = counts[:S - 1, d * per_block:d * per_block + part_blk].sum()
+        assert nby.cpu().numpy()[d] == 8 * max(0, min(counts[S - 1, d * per_block:d * per_block + part_blk].sum(), 100 - first_dst))
+
+
+@pytest.mark.parametrize("H,Q,kdt,vdt", [(1, 1, torch.int64, torch.int64), (2, 2, torch.int64, torch.int64),
+                                         (3, 4, torch.int32, torch.float32), (2, 2, torch.int64, None)])
+def test_pipe_plan_layout(H, Q, kdt, vdt):
+    """dpk_pipe_plan: the padded send layout (bucket_base) and the Q push tables of one group.  Blocks follow each other
+    in (destination, part) order, buckets inside a block are dense, every push is congruent mod 16 bytes to its landing
+    place, lands (rank, group)-major inside region q, and the pads fit the promised spare rows."""
+    rng = np.random.default_rng(23)
+    G, P, sb = 4, 16, 2
+    F = P << sb
+    per_block = (P // G) << sb
+    part_blk = per_block // Q
+    S = G * H
+    counts = rng.integers(0, 60, (S, F)).astype(np.int64)
+    allc = dev(counts)
+    region = 4096
+    ksz = torch.empty(0, dtype=kdt).element_size()
+    vsz = None if vdt is None else torch.empty(0, dtype=vdt).element_size()
+    A = 16 // min(ksz, vsz or ksz)
+    pad = nv().pipe_pad_rows(G, Q, ksz, vsz)
+    ncols = 1 if vdt is None else 2
+    base_addr = (np.arange(1, ncols * G + 1, dtype=np.int64) << 32)
+    for rank in (0, G - 1):
+        for h in range(H):
+            my = rank * H + h
+            n_mine = int(counts[my].sum())
+            out_k = torch.empty(n_mine + pad, dtype=kdt, device="cuda")
+            out_v = None if vdt is None else torch.empty(n_mine + pad, dtype=vdt, device="cuda")
+            err = torch.zeros(1, dtype=torch.int64, device="cuda")
+            bb, src, dst, nby, seg = nv().pipe_plan(allc, G, per_block, Q, region, my, rank, out_k, out_v, dev(base_addr), err)
+            bb, src, dst, nby, seg = (t.cpu().numpy() for t in (bb, src, dst, nby, seg))
+            assert int(err.item()) == 0
+            pos = 0
+            for d in range(G):
+                for q in range(Q):
+                    lo, hi = d * per_block + q * part_blk, d * per_block + (q + 1) * part_blk
+                    first_dst = counts[:my, lo:hi].sum()
+                    landing = q * region + first_dst
+                    start = bb[lo]
+                    assert pos <= start < pos + A and (start - landing) % A == 0
+                    assert np.array_equal(bb[lo:hi], start + np.cumsum(counts[my, lo:hi]) - counts[my, lo:hi])
+                    rows = counts[my, lo:hi].sum()
+                    assert nby[q, d] == rows * ksz and src[q, d] == out_k.data_ptr() + start * ksz
+                    assert dst[q, d] == base_addr[d] + landing * ksz and (src[q, d] - dst[q, d]) % 16 == 0
+                    if vdt is not None:
+                        assert nby[q, G + d] == rows * vsz and src[q, G + d] == out_v.data_ptr() + start * vsz
+                        assert dst[q, G + d] == base_addr[G + d] + landing * vsz and (src[q, G + d] - dst[q, G + d]) % 16 == 0
+                    pos = start + rows
+            assert pos <= n_mine + pad
+            for q in range(Q):
+                lo = rank * per_block + q * part_blk
+                assert np.array_equal(seg[q], counts[:, lo:lo + part_blk])
+
+
+@pytest.mark.parametrize("tma", [0, 1])
+def test_copy_segments_on_a_few_sms(tma):
+    """dpk_copy_segments restricted to whole SMs (the overlapped pushes): the TMA ring (congruent segments: head / aligned
+    middle / tail; incongruent ones by loads and stores) and the load/store form must both copy exactly the bytes of
+    every segment and nothing else."""
+    rng = np.random.default_rng(31 + tma)
+    sizes = [0, 1, 8, 15, 16, 17, 4096, 32768, 32769, 65536 + 24, 300000, 1 << 20]
+    src = torch.from_numpy(rng.integers(0, 256, 8 << 20, dtype=np.uint8)).cuda()
+    dst = torch.zeros(8 << 20, dtype=torch.uint8, device="cuda")
+    want = np.zeros(8 << 20, dtype=np.uint8)
+    srch = src.cpu().numpy()
+    so, do, nb = [], [], []
+    s_at, d_at = 5, 64
+    for i, n in enumerate(sizes * 2):
+        s_off = s_at + (i * 7) % 16              # every alignment of the source ...
+        d_off = d_at + ((s_off - d_at) % 16 if i < len(sizes) else (i * 3) % 16)   # ... congruent first, arbitrary after
+        so.append(src.data_ptr() + s_off)
+        do.append(dst.data_ptr() + d_off)
+        nb.append(n)
+        want[d_off:d_off + n] = srch[s_off:s_off + n]
+        s_at = s_off + n + 40
+        d_at = d_off + n + 40
+    nv().set_option("copy_tma", tma)
+    try:
+        nv().copy_segments(dev(np.array(so, dtype=np.int64)), dev(np.array(do, dtype=np.int64)), dev(np.array(nb, dtype=np.int64)), sms=3)
+        torch.cuda.synchronize()
+    finally:
+        nv().set_option("copy_tma", 1)
+    assert np.array_equal(dst.cpu().numpy(), want)
+
+
 def test_choose_sub_bits_bounds():
     from dpark_b200 import shuffle
     assert shuffle.choose_sub_bits(1000, 8) == 0
