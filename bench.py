@@ -86,6 +86,7 @@ def parse():
     ap.add_argument("--pipeline", default="", help="N>1, push exchange, reduceByKey configs: GxQ = map splits in G groups "
                     "(push of one overlaps the multisplit of the next) and every block in Q parts (reduce side of a part "
                     "overlaps the push of the next): dpark_b200.peer.shuffle_pipelined; '' or 'off' = one push, then reduce")
+    ap.add_argument("--copy-engine", type=int, default=-1, help="N>1, --pipeline: pushes by the copy engines (1) or by dpk_copy_segments on --copy-sms SMs (0)")
     ap.add_argument("--copy-sms", type=int, default=-1, help="N>1, overlapped push: whole SMs the overlapped copy kernel takes")
     ap.add_argument("--exchange", default="push", choices=["push", "fused", "peer", "nccl"],
                     help="N>1: push = local scatter, then one kernel pushing each peer's block over NVLink; "
@@ -533,6 +534,8 @@ def run_ours(args):
                                    mode="push" if args.exchange == "push" else "fused")
             if args.copy_sms >= 0:
                 px.copy_sms = args.copy_sms
+            if args.copy_engine >= 0:
+                px.copy_engine = args.copy_engine
         except Exception as e:  # symmetric memory unavailable on this box/build: say so, use NCCL
             sys.stderr.write("peer exchange unavailable (%s: %s); using NCCL alltoallv\n" % (type(e).__name__, e))
             px = None

@@ -49,6 +49,7 @@ class PeerExchange(object):
         self.nbuf = max(1, int(buffers))
         name = self.group.group_name
         self._keys, self._vals, self._hk, self._hv, self._kb, self._vb, self._db = [], [], [], [], [], [], []
+        self._pk, self._pv, self._kp, self._vp = [], [], [], []
         for _ in range(self.nbuf):
             k = symm.empty(self.capacity, dtype=key_dtype, device=self.device)
             v = symm.empty(self.capacity, dtype=val_dtype, device=self.device)
@@ -60,6 +61,11 @@ class PeerExchange(object):
             self._kb.append(torch.tensor([int(p) for p in hk.buffer_ptrs], dtype=torch.int64, device=self.device))
             self._vb.append(torch.tensor([int(p) for p in hv.buffer_ptrs], dtype=torch.int64, device=self.device))
             self._db.append(torch.cat([self._kb[-1], self._vb[-1]]).contiguous())     # [2][G] for dpk_push_plan
+            # every rank's buffers as tensors of THIS process (peer memory mapped over NVLink): targets of copy-engine pushes
+            self._pk.append([hk.get_buffer(r, (self.capacity,), key_dtype) for r in range(self.world)])
+            self._pv.append([hv.get_buffer(r, (self.capacity,), val_dtype) for r in range(self.world)])
+            self._kp.append([int(p) for p in hk.buffer_ptrs])
+            self._vp.append([int(p) for p in hv.buffer_ptrs])
         self.step = 0
         self.side = torch.cuda.Stream(device=self.device, priority=-1)     # pushes that overlap the map side
         self.err = torch.zeros(1, dtype=torch.int64, device=self.device)   # max rows any rank needed beyond capacity
@@ -68,6 +74,12 @@ class PeerExchange(object):
         # SMs an OVERLAPPED push may take (map_exchange_overlapped): the copy kernel is launched on the high-priority
         # side stream as whole-SM CTAs, the multisplit of the next group runs on the SMs that are left
         self.copy_sms = 16
+        # shuffle_pipelined: 1 = the pushes are cudaMemcpyAsync calls on the side stream (the GPU's copy engines move the
+        # blocks over NVLink while ALL SMs keep computing; costs one small device->host read of the segment tables per
+        # step, hidden behind the multisplit); 0 = dpk_copy_segments on copy_sms SMs (nothing read by the host)
+        self.copy_engine = 1
+        self.side2 = torch.cuda.Stream(device=self.device, priority=-1)
+        self._tab_host = None
 
     # the buffer set of the current step
     @property
@@ -121,6 +133,7 @@ class PeerExchange(object):
         if not self._closed:
             self._closed = True
             self._keys, self._vals, self._hk, self._hv, self._kb, self._vb, self._db = [], [], [], [], [], [], []
+            self._pk, self._pv = [], []
 
 
 def push_plan(all_counts, blocks, rank):
@@ -292,8 +305,10 @@ def shuffle_pipelined(px, key_chunks, val_chunks, P, op, thresholds=None, sub_bi
     dst_base = px.dst_base if has_v else px.key_base
     pad = nv.pipe_pad_rows(G, Q, gk[0].element_size(), gv[0].element_size() if has_v else None)
     main = torch.cuda.current_stream()
-    bufs, plans, segs = [], [[None] * H for _ in range(Q)], None
+    bufs, plans, bases, segs = [], [[None] * H for _ in range(Q)], [], None
     landed = [torch.cuda.Event() for _ in range(Q)]
+    ce = bool(px.copy_engine)
+    tabs = []
     for h in range(H):
         n_h = int(gk[h].numel())
         out_k = torch.empty(n_h + pad, dtype=gk[h].dtype, device=dev)
@@ -304,29 +319,68 @@ def shuffle_pipelined(px, key_chunks, val_chunks, P, op, thresholds=None, sub_bi
                                                dst_base, px.err, want_seg=(h == 0))
         if h == 0:
             segs = sg
-        nv.partition_scatter(gk[h], gv[h], P, base, out_k, out_v, wss[h], thresholds, False, sub_bits, None, True)
         bufs.append((out_k, out_v))
+        bases.append(base)
         for q in range(Q):
             plans[q][h] = (src[q], dst[q], nby[q])
-        ready = torch.cuda.Event()
-        ready.record(main)
-        with torch.cuda.stream(px.side):                 # part 0 of this group leaves while the next group is partitioned
-            px.side.wait_event(ready)
-            nv.copy_segments(*plans[0][h], sms=px.copy_sms)
+        tabs.append(torch.stack([src, dst, nby]))
+    tab_ready = None
+    if ce:      # the segment tables go to the host while the multisplit kernels run
+        ncg = (2 if has_v else 1) * G
+        if px._tab_host is None or tuple(px._tab_host.shape) != (H, 3, Q, ncg):
+            px._tab_host = torch.empty((H, 3, Q, ncg), dtype=torch.int64).pin_memory()
+        px._tab_host.copy_(torch.stack(tabs), non_blocking=True)
+        tab_ready = torch.cuda.Event()
+        tab_ready.record(main)
+    ready = []
+    for h in range(H):
+        nv.partition_scatter(gk[h], gv[h], P, bases[h], bufs[h][0], bufs[h][1], wss[h], thresholds, False, sub_bits, None, True)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        ready.append(ev)
+    kset, vset = px._pk[px.step % px.nbuf], px._pv[px.step % px.nbuf]
+    kptr, vptr = px._kp[px.step % px.nbuf], px._vp[px.step % px.nbuf]
+    if ce:
+        tab_ready.synchronize()
+        tab = px._tab_host.numpy()
+        ksz = gk[0].element_size()
+        vsz = gv[0].element_size() if has_v else 0
+
+    def push(q, h):
+        """Part q of group h to every rank (current stream)."""
+        if not ce:
+            nv.copy_segments(*plans[q][h], sms=px.copy_sms)
+            return
+        out_k, out_v = bufs[h]
+        k0 = out_k.data_ptr()
+        v0 = out_v.data_ptr() if has_v else 0
+        for i in range(G):
+            d = (rank + 1 + i) % G                       # staggered: no two ranks start on the same destination
+            rows = int(tab[h, 2, q, d]) // ksz
+            if rows:
+                s0 = (int(tab[h, 0, q, d]) - k0) // ksz
+                d0 = (int(tab[h, 1, q, d]) - kptr[d]) // ksz
+                kset[d][d0:d0 + rows].copy_(out_k[s0:s0 + rows], non_blocking=True)
+                if has_v:
+                    s0 = (int(tab[h, 0, q, G + d]) - v0) // vsz
+                    d0 = (int(tab[h, 1, q, G + d]) - vptr[d]) // vsz
+                    vset[d][d0:d0 + rows].copy_(out_v[s0:s0 + rows], non_blocking=True)
+
     with torch.cuda.stream(px.side):
+        for h in range(H):                               # part 0 of a group leaves while the next group is partitioned
+            px.side.wait_event(ready[h])
+            push(0, h)
         landed[0].record(px.side)
         for q in range(1, Q):                            # the later parts cross NVLink under the reduce side of the earlier
             for h in range(H):
-                nv.copy_segments(*plans[q][h], sms=px.copy_sms)
+                push(q, h)
             landed[q].record(px.side)
         for out_k, out_v in bufs:
             out_k.record_stream(px.side)
             if out_v is not None:
                 out_v.record_stream(px.side)
-        for q in range(Q):
-            for t3 in plans[q]:
-                for t in t3:
-                    t.record_stream(px.side)
+        for t in tabs + bases + [t for q in range(Q) for t3 in plans[q] for t in t3]:
+            t.record_stream(px.side)
     keys, vals = px.keys, (px.vals if has_v else None)
     first = blocks[rank]
     nparts = blocks[rank + 1] - blocks[rank]

@@ -45,13 +45,19 @@ for extra in "$@"; do
     fusedsb4) run c2fusedsb4 --exchange fused --sub-bits 4 $Q ;;
     text) echo "== text ingest tests + wc_e2e"; timeout 600 python -m pytest tests/test_gpu_textingest.py tests/test_gpu_rdd.py -m gpu -x -q 2>&1 | tail -3
           timeout 300 python scripts/wc_e2e.py 2>&1 | tail -3; timeout 300 python scripts/wc_e2e.py 1000000 rowwise 2>&1 | tail -3 ;;
-    p1x2) run c2p1x2 --pipeline 1x2 $Q ;;
+    p1x2) run c2p1x2 --pipeline 1x2 --copy-engine 0 $Q ;;
     p2x2) run c2p2x2 --pipeline 2x2 $Q ;;
     p4x2) run c2p4x2 --pipeline 4x2 $Q ;;
     p4x1) run c2p4x1 --pipeline 4x1 $Q ;;
     p4x4) run c2p4x4 --pipeline 4x4 $Q ;;
     p4x2s32) run c2p4x2s32 --pipeline 4x2 --copy-sms 32 $Q ;;
     p4x2s12) run c2p4x2s12 --pipeline 4x2 --copy-sms 12 $Q ;;
+    p1x1ce) run c2p1x1ce --pipeline 1x1 $Q ;;
+    p1x2ce) run c2p1x2ce --pipeline 1x2 $Q ;;
+    p2x2ce) run c2p2x2ce --pipeline 2x2 $Q ;;
+    p2x4ce) run c2p2x4ce --pipeline 2x4 $Q ;;
+    p4x2ce) run c2p4x2ce --pipeline 4x2 $Q ;;
+    p2x2sm32) run c2p2x2sm32 --pipeline 2x2 --copy-engine 0 --copy-sms 32 $Q ;;
     c2) run c2 ;;
     c4) run c4 --config c4 --steps 5 --e2e-steps 1 --e2e-depth 2 ;;
     c4fused) run c4fused --config c4 --steps 5 --exchange fused $Q ;;

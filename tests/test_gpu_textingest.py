@@ -32,7 +32,7 @@ WS = b" \t\n\r\x0b\x0c\x1c\x1d\x1e\x1f"
                                   b"tab\tsep\rcr\x0bvt\x0cff end", b"a" * 15 + b" " + b"b" * 16 + b"\n" + b"c" * 17,
                                   b"\x00nul\x00 is\x7fnot space"])
 def test_tokenize_edge_cases(case):
-    assert _tokens(case) == case.decode("ascii").split()
+    assert _tokens(case) == [w.encode("ascii") for w in case.decode("ascii").split()]
 
 
 @pytest.mark.parametrize("seed,n", [(1, 4095), (2, 4096), (3, 4097), (4, 70001), (5, 1 << 20)])
