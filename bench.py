@@ -51,6 +51,9 @@ CONFIGS = {
 }
 
 
+AUTO_PIPELINE = "2x2"     # N > 1 default of --pipeline (profiles/r02_ncu_findings.md, session 2)
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -83,9 +86,9 @@ def parse():
     ap.add_argument("--agg-impl", type=int, default=-1, help="A/B: reduce-side merge kernel (0 = round 1, 1 = row-index tags)")
     ap.add_argument("--overlap-push", type=int, default=1, help="N>1, push exchange: groups of map splits whose push "
                     "overlaps the scatter of the next group (1 = no overlap)")
-    ap.add_argument("--pipeline", default="", help="N>1, push exchange, reduceByKey configs: GxQ = map splits in G groups "
+    ap.add_argument("--pipeline", default="auto", help="N>1, push exchange, reduceByKey configs: GxQ = map splits in G groups "
                     "(push of one overlaps the multisplit of the next) and every block in Q parts (reduce side of a part "
-                    "overlaps the push of the next): dpark_b200.peer.shuffle_pipelined; '' or 'off' = one push, then reduce")
+                    "overlaps the push of the next): dpark_b200.peer.shuffle_pipelined; 'off' = one push, then reduce; 'auto' = AUTO_PIPELINE")
     ap.add_argument("--copy-engine", type=int, default=-1, help="N>1, --pipeline: pushes by the copy engines (1) or by dpk_copy_segments on --copy-sms SMs (0)")
     ap.add_argument("--copy-sms", type=int, default=-1, help="N>1, overlapped push: whole SMs the overlapped copy kernel takes")
     ap.add_argument("--exchange", default="push", choices=["push", "fused", "peer", "nccl"],
@@ -112,7 +115,7 @@ def workload_config(args, world):
         "map_splits_per_gpu": args.map_splits, "parallelism": "dp%d" % world,
         "exchange": None if world == 1 else args.exchange, "map_combine": bool(args.map_combine),
         "overlap_push_groups": args.overlap_push if world > 1 else None,
-        "pipeline": (args.pipeline or None) if world > 1 else None,
+        "pipeline": ((AUTO_PIPELINE if args.pipeline == "auto" else args.pipeline) or None) if world > 1 else None,
         "l2_policy": "inputs_larger_than_l2 (%.1f GB of rows per GPU per step vs 126 MB L2)"
                      % (args.rows_per_gpu * (_isz(cfg["kdt"]) + _isz(cfg["vdt"])) / 1e9),
         "sub_buckets_per_partition": 1 << shuffle.choose_sub_bits(args.rows_per_gpu, args.parts_per_gpu * world, world),
@@ -541,6 +544,8 @@ def run_ours(args):
             px = None
 
     pipe = None
+    if args.pipeline == "auto":
+        args.pipeline = AUTO_PIPELINE if world > 1 else "off"
     if args.pipeline and args.pipeline != "off" and px is not None and px.mode == "push" and not group and not args.map_combine:
         g_, q_ = args.pipeline.lower().split("x")
         pipe = (int(g_), int(q_))
@@ -724,12 +729,22 @@ def run_ours(args):
         sc = torch.tensor([sc_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(sc, op=dist.ReduceOp.MAX)
         sent = xb * n * (world - 1) / world          # bytes a rank pushes to OTHER ranks per step (uniform keys)
-        gbs = sent / (float(sc) * 1e-3) / 1e9
-        roofline_exchange = {"bound": "nvlink", "kernel": "k_part_scatter storing into peer receive buffers" if
-                             px.mode == "fused" else "k_copy_segments: one launch pushing every peer's block",
-                             "achieved": gbs, "peak": 770.0, "unit": "GB/s per GPU per direction",
-                             "frac": gbs / 770.0, "ms_per_step_max_over_ranks": float(sc),
-                             "peak_source": "measured peer copy on this pool (B200_PROFILING.md); nominal 900"}
+        if float(sc) > 0:
+            gbs = sent / (float(sc) * 1e-3) / 1e9
+            roofline_exchange = {"bound": "nvlink", "kernel": "k_part_scatter_bulk storing into peer receive buffers (TMA)" if
+                                 px.mode == "fused" else "k_copy_segments: one launch pushing every peer's block",
+                                 "achieved": gbs, "peak": 770.0, "unit": "GB/s per GPU per direction",
+                                 "frac": gbs / 770.0, "ms_per_step_max_over_ranks": float(sc),
+                                 "peak_source": "measured peer copy on this pool (B200_PROFILING.md); nominal 900"}
+        else:    # pipelined step with copy-engine pushes: no kernel of ours moves the bytes; they cross NVLink under the
+            # multisplit and the merge, so what the step pays for the exchange is its time beyond the kernels' sum
+            roofline_exchange = {"bound": "nvlink", "kernel": "copy engines (cudaMemcpyAsync on the peers' mapped receive "
+                                 "buffers), overlapped with the multisplit and the merge", "achieved": None, "peak": 770.0,
+                                 "unit": "GB/s per GPU per direction", "frac": None,
+                                 "bytes_pushed_per_gpu_per_step": sent,
+                                 "lower_bound_ms": sent / 770e9 * 1e3,
+                                 "step_ms_minus_kernel_ms": ms_step - ktotal / args.steps,
+                                 "peak_source": "measured peer copy on this pool (B200_PROFILING.md); nominal 900"}
 
     # ---- e2e: host buffers through the public HostShuffleStream call ---------------------------------------
     e2e = None

@@ -33,7 +33,7 @@ EXPORTS = [
     "dpk_launch_count", "dpk_prof_enable", "dpk_prof_count", "dpk_prof_get",
     "dpk_dict_encode_workspace_bytes", "dpk_dict_encode", "dpk_set_option",
     "dpk_key_or", "dpk_radix_pass", "dpk_group_heads_workspace_bytes", "dpk_group_heads", "dpk_gather_i64",
-    "dpk_partition_scatter_ptrs", "dpk_copy_segments", "dpk_hash_tuple", "dpk_push_plan", "dpk_push_plan_part", "dpk_pipe_plan", "dpk_fused_plan",
+    "dpk_partition_scatter_ptrs", "dpk_copy_segments", "dpk_hash_tuple", "dpk_push_plan", "dpk_push_plan_part", "dpk_pipe_plan", "dpk_fused_plan", "dpk_memcpy_batch",
     "dpk_tokenize_blocks", "dpk_tokenize_count", "dpk_tokenize_emit", "dpk_gather_bytes",
     "dpk_radix_pass_seg_workspace_bytes", "dpk_radix_pass_seg",
 ]
@@ -74,6 +74,7 @@ def lib():
         L.dpk_push_plan.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, C.c_uint64, C.c_uint64, vp, i32, i32, i64, vp, vp, vp, vp, vp, vp]
         L.dpk_push_plan_part.argtypes = [vp, i32, i32, i32, i32, i32, i32, i64, i32, i32, i32, C.c_uint64, C.c_uint64, vp, i32, i32, i64, vp, vp, vp, vp, vp, vp]
         L.dpk_pipe_plan.argtypes = [vp, i32, i32, i32, i32, i32, i64, i32, i32, i32, C.c_uint64, C.c_uint64, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp]
+        L.dpk_memcpy_batch.argtypes = [vp, vp, vp, i32, vp]
         L.dpk_fused_plan.argtypes = [vp, i32, i32, i32, i32, i32, vp, i32, i32, i64, C.c_uint64, C.c_uint64, vp, vp, vp, vp, vp]
         L.dpk_tokenize_blocks.restype = i64
         L.dpk_tokenize_blocks.argtypes = [i64]
@@ -270,6 +271,17 @@ def copy_segments(src_ptrs, dst_ptrs, nbytes, sms=0):
     finally:
         if sms:
             set_option("copy_sms", 0)
+
+
+def memcpy_batch(dst_ptrs, src_ptrs, nbytes):
+    """Block copies by the copy engines: one cudaMemcpyBatchAsync over HOST lists of device addresses and sizes."""
+    n = len(nbytes)
+    if not (len(dst_ptrs) == len(src_ptrs) == n):
+        raise ValueError("segment table columns differ in length")
+    if n == 0:
+        return
+    U, I = C.c_uint64 * n, C.c_int64 * n
+    _check(lib().dpk_memcpy_batch(U(*dst_ptrs), U(*src_ptrs), I(*nbytes), n, _stream()))
 
 
 def push_plan(all_counts, nranks, per_block, my_src, my_rank, keys, vals, dst_base, capacity, need_over, want_seg=True,

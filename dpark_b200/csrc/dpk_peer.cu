@@ -13,6 +13,7 @@
 //
 // Algorithmic bytes: (K+V) per row read locally + (K+V) per row stored through NVLink; the
 // bound is the NVLink egress/ingress of one GPU (900 GB/s per direction nominal), not HBM.
+#include <cstring>
 #include "dpk_common.cuh"
 
 namespace dpk {
@@ -467,6 +468,41 @@ extern "C" int dpk_pipe_plan(const int64_t *all_counts, int32_t nsrc, int32_t nr
                                                              region_rows, 16 / min_elem, my_src, my_rank, ncols, src_keys, src_vals,
                                                              dst_base, key_bytes, val_bytes, bucket_base, src_ptrs, dst_ptrs, nbytes,
                                                              (long long *)need_over, seg_out));
+    return DPK_OK;
+}
+
+// The same block pushes handed to the GPU's COPY ENGINES: one cudaMemcpyBatchAsync for a whole segment table that the HOST
+// holds (sizes read back from dpk_pipe_plan's tables while the multisplit runs).  The engines move the blocks over NVLink
+// without occupying a single SM, so a push issued this way overlaps the multisplit of the next group and the merge of the
+// previous part at their full speed; the batch call costs one driver round trip instead of one per block.
+extern "C" int dpk_memcpy_batch(const uint64_t *h_dst_ptrs, const uint64_t *h_src_ptrs, const int64_t *h_nbytes, int32_t count,
+                                dpk_stream_t stream) {
+    if (count < 0 || count > 4096) return fail(DPK_ERR_INVALID, "count=%d out of range [0, 4096]", count);
+    if (count == 0) return DPK_OK;
+    if (!h_dst_ptrs || !h_src_ptrs || !h_nbytes) return fail(DPK_ERR_INVALID, "NULL pointer");
+    void *dsts[4096], *srcs[4096];
+    size_t sizes[4096];
+    size_t m = 0;
+    for (int i = 0; i < count; i++) {
+        if (h_nbytes[i] < 0) return fail(DPK_ERR_INVALID, "negative size in segment %d", i);
+        if (h_nbytes[i] == 0) continue;
+        dsts[m] = reinterpret_cast<void *>(h_dst_ptrs[i]);
+        srcs[m] = reinterpret_cast<void *>(h_src_ptrs[i]);
+        sizes[m] = (size_t)h_nbytes[i];
+        m++;
+    }
+    if (m == 0) return DPK_OK;
+    cudaMemcpyAttributes attr;
+    memset(&attr, 0, sizeof(attr));
+    attr.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
+    size_t attr_idx = 0, fail_idx = 0;
+    cudaError_t e = cudaMemcpyBatchAsync(dsts, srcs, sizes, m, &attr, &attr_idx, 1, &fail_idx, (cudaStream_t)stream);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        // a driver without the batch entry point (or the legacy stream): one call per block
+        for (size_t i = 0; i < m; i++)
+            DPK_CUDA_TRY(cudaMemcpyAsync(dsts[i], srcs[i], sizes[i], cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    }
     return DPK_OK;
 }
 

@@ -77,7 +77,7 @@ class PeerExchange(object):
         # shuffle_pipelined: 1 = the pushes are cudaMemcpyAsync calls on the side stream (the GPU's copy engines move the
         # blocks over NVLink while ALL SMs keep computing; costs one small device->host read of the segment tables per
         # step, hidden behind the multisplit); 0 = dpk_copy_segments on copy_sms SMs (nothing read by the host)
-        self.copy_engine = 1
+        self.copy_engine = 2      # 2 = one cudaMemcpyBatchAsync per (part, group); 1 = one cudaMemcpyAsync per block
         self.side2 = torch.cuda.Stream(device=self.device, priority=-1)
         self._tab_host = None
 
@@ -351,11 +351,17 @@ def shuffle_pipelined(px, key_chunks, val_chunks, P, op, thresholds=None, sub_bi
         if not ce:
             nv.copy_segments(*plans[q][h], sms=px.copy_sms)
             return
+        if px.copy_engine == 2:     # one cudaMemcpyBatchAsync for the whole table of this (part, group)
+            order = [(rank + 1 + i) % G for i in range(G)]          # staggered: no two ranks start on the same destination
+            cols = [c * G + d for d in order for c in range(2 if has_v else 1)]
+            nv.memcpy_batch([int(tab[h, 1, q, o]) for o in cols], [int(tab[h, 0, q, o]) for o in cols],
+                            [int(tab[h, 2, q, o]) for o in cols])
+            return
         out_k, out_v = bufs[h]
         k0 = out_k.data_ptr()
         v0 = out_v.data_ptr() if has_v else 0
         for i in range(G):
-            d = (rank + 1 + i) % G                       # staggered: no two ranks start on the same destination
+            d = (rank + 1 + i) % G
             rows = int(tab[h, 2, q, d]) // ksz
             if rows:
                 s0 = (int(tab[h, 0, q, d]) - k0) // ksz

@@ -145,6 +145,11 @@ int dpk_partition_scatter_ptrs(const void *keys, int key_kind, const int64_t *ke
  * and sizes of any alignment (16/8/4/1-byte accesses are chosen per item). */
 int dpk_copy_segments(const uint64_t *src_ptrs, const uint64_t *dst_ptrs, const int64_t *nbytes,
                       int32_t nseg, dpk_stream_t stream);
+/* The same pushes issued to the GPU's copy engines (no SM is used, so they overlap other kernels at full speed): one
+ * cudaMemcpyBatchAsync over a segment table held by the HOST (h_* are host arrays; addresses are device addresses, peer
+ * buffers included).  Stream-ordered like everything else; zero-sized segments are skipped. */
+int dpk_memcpy_batch(const uint64_t *h_dst_ptrs, const uint64_t *h_src_ptrs, const int64_t *h_nbytes, int32_t count,
+                     dpk_stream_t stream);
 /* The MapOutputTracker lookup (dpark/shuffle.py:809-826) for the push: from the gathered counts matrix
  * all_counts[nsrc][nbuckets] (device) to the segment table dpk_copy_segments takes, in ONE launch.  Destination d owns
  * the buckets [d * per_block, (d + 1) * per_block); this rank is source row my_src (= my_rank, or my_rank * H + group

@@ -29,8 +29,12 @@ PY
 Q="--no-e2e"
 for extra in "$@"; do
   case $extra in
-    push) run c2push --exchange push $Q ;;
-    fused) run c2fused --exchange fused $Q ;;
+    push) run c2push --exchange push --pipeline off $Q ;;
+    p1x2b) run c2p1x2b --pipeline 1x2 --copy-engine 2 $Q ;;
+    p2x2b) run c2p2x2b --pipeline 2x2 --copy-engine 2 $Q ;;
+    p2x1b) run c2p2x1b --pipeline 2x1 --copy-engine 2 $Q ;;
+    p1x1b) run c2p1x1b --pipeline 1x1 --copy-engine 2 $Q ;;
+    fused) run c2fused --exchange fused --pipeline off $Q ;;
     fused512) DPK_OPTIONS=scatter_ptr_threads=512 run c2fused512 --exchange fused $Q ;;
     fusedold) DPK_OPTIONS=scatter_ptr_bulk=0 run c2fusedold --exchange fused $Q ;;
     ov2) run c2ov2 --exchange push --overlap-push 2 $Q ;;
@@ -42,7 +46,7 @@ for extra in "$@"; do
     pushs16) DPK_OPTIONS=copy_sms=16 run c2pushs16 --exchange push $Q ;;
     pushs32) DPK_OPTIONS=copy_sms=32 run c2pushs32 --exchange push $Q ;;
     pushsb4) run c2pushsb4 --exchange push --sub-bits 4 $Q ;;
-    fusedsb4) run c2fusedsb4 --exchange fused --sub-bits 4 $Q ;;
+    fusedsb4) run c2fusedsb4 --exchange fused --sub-bits 4 --pipeline off $Q ;;
     text) echo "== text ingest tests + wc_e2e"; timeout 600 python -m pytest tests/test_gpu_textingest.py tests/test_gpu_rdd.py -m gpu -x -q 2>&1 | tail -3
           timeout 300 python scripts/wc_e2e.py 2>&1 | tail -3; timeout 300 python scripts/wc_e2e.py 1000000 rowwise 2>&1 | tail -3 ;;
     p1x2) run c2p1x2 --pipeline 1x2 --copy-engine 0 $Q ;;

@@ -43,6 +43,10 @@ def main():
             yield (wd, 1)
 
     out = os.path.join(tmp, "out")
+    import torch
+    torch.zeros(1, device="cuda")          # CUDA context + library load are not part of the job
+    nv.lib()
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
     rdd = dc.textFile(inp, numSplits=4).flatMap(fm)
     sh = rdd.reduceByKey(lambda x, y: x + y, numSplits=6)
@@ -52,6 +56,13 @@ def main():
     t2 = time.perf_counter()
     sh.map(lambda x: " ".join(list(map(str, x)))).saveAsTextFile(out, overwrite=False)
     t3 = time.perf_counter()
+    # the same job again on fresh RDDs: kernels loaded, allocator warm (what a long-running driver sees)
+    tw0 = time.perf_counter()
+    sh2 = dc.textFile(inp, numSplits=4).flatMap(fm).reduceByKey(lambda x, y: x + y, numSplits=6)
+    sh2._materialize()
+    tw1 = time.perf_counter()
+    sh2.map(lambda x: " ".join(list(map(str, x)))).saveAsTextFile(out + "2", overwrite=False)
+    tw2 = time.perf_counter()
     got = {}
     for fn in sorted(os.listdir(out)):
         for line in open(os.path.join(out, fn)):
@@ -64,6 +75,8 @@ def main():
           ("row-wise Python tokeniser" if rowwise else "device tokeniser", lines_n, rows, len(got)))
     print("  ingest + GPU shuffle %.2f s, egress + save %.2f s, total %.2f s (%.2e tokens/s end to end); "
           "%d kernel launches" % (t2 - t1, t3 - t2, t3 - t0, rows / (t3 - t0), nv.launch_count() - l0))
+    print("  second run of the same job: ingest + GPU shuffle %.3f s, egress + save %.3f s, total %.3f s (%.2e tokens/s)"
+          % (tw1 - tw0, tw2 - tw1, tw2 - tw0, rows / (tw2 - tw0)))
 
 
 if __name__ == "__main__":
