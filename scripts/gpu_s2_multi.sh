@@ -20,7 +20,9 @@ try:
     d=json.load(open("gpurun_out/bench_${tag}_n$N.json"))
     print("ms/step", round(d["ms_per_step"],3), "value %.3e"%d["value"], "parity", d.get("parity",{}).get("parity_checked"), d.get("parity",{}).get("seconds"))
     for k in d["kernels"][:8]: print("  ", k["kernel"], k["n"], k["ms"], "alg_gbs", k["alg_gbs"])
-    if d.get("roofline_exchange"): print("  exchange", round(d["roofline_exchange"]["achieved"]), "GB/s", round(d["roofline_exchange"]["ms_per_step_max_over_ranks"],3), "ms")
+    rx = d.get("roofline_exchange") or {}
+    if rx.get("achieved"): print("  exchange", round(rx["achieved"]), "GB/s", round(rx["ms_per_step_max_over_ranks"],3), "ms")
+    elif rx: print("  exchange by copy engines: step - kernels =", round(rx["step_ms_minus_kernel_ms"],3), "ms; NVLink lower bound", round(rx["lower_bound_ms"],3), "ms")
     if d.get("e2e"): print("  e2e ms/step", round(d["e2e"]["ms_per_step"],2), "value %.3e"%d["e2e"]["value"])
 except Exception as e:
     print("no json:", e); print(open("gpurun_out/bench_${tag}_n$N.err").read()[-3000:])

@@ -406,3 +406,17 @@ def test_int_sums_that_could_wrap_are_refused_and_float_zero_keys_are_canonical(
     engine._check_int_sum_range([ok], {columnar.VAL_I64}, "sum")
     c = columnar.ingest_pairs([(-0.0, 1), (0.0, 2)])
     assert np.signbit(c.keys).tolist() == [False, False]
+
+
+def test_merge_part_results_concatenates_partitions_in_order():
+    """peer.merge_part_results: the per-part results of a pipelined step as one reduce_side-shaped result."""
+    import torch
+    from dpark_b200 import peer
+    # part A: partitions 4,5 with 3 + 1 distinct rows (received-row offsets 0, 5, 7); part B: partitions 6,7
+    a = (torch.tensor([10, 11, 12, 0, 0, 20, 0]), torch.tensor([1, 2, 3, 0, 0, 4, 0]),
+         torch.tensor([0, 5, 7]), torch.tensor([3, 1]), 4, 2)
+    b = (torch.tensor([30, 0, 40, 41]), torch.tensor([5, 0, 6, 7]), torch.tensor([0, 2, 4]), torch.tensor([1, 2]), 6, 2)
+    k, v, po, cnt = peer.merge_part_results([a, b])
+    assert po.tolist() == [0, 5, 7, 9, 11] and cnt.tolist() == [3, 1, 1, 2]
+    got = [(k[po[j]:po[j] + cnt[j]].tolist(), v[po[j]:po[j] + cnt[j]].tolist()) for j in range(4)]
+    assert got == [([10, 11, 12], [1, 2, 3]), ([20], [4]), ([30], [5]), ([40, 41], [6, 7])]
