@@ -248,4 +248,36 @@ DPK_HD uint32_t slot_hash32(uint64_t kb) {
     return x;
 }
 
+// ------------------------------------------------------------- f4: tokeniser arithmetic (dpk_strings.cu)
+// str.split() without arguments on ASCII text: whitespace = ' ', \t \n \v \f \r, \x1c..\x1f
+constexpr int TK_BYTES = 16;   // bytes per thread
+__host__ __device__ __forceinline__ bool tok_ws(uint8_t c) { return c == 0x20 || (c >= 0x09 && c <= 0x0d) || (c >= 0x1c && c <= 0x1f); }
+
+// bit j of the result: a token starts at byte i0 + j; *hi |= any byte >= 0x80
+__host__ __device__ __forceinline__ uint32_t tok_starts16(const uint8_t *__restrict__ data, int64_t n, int64_t i0, bool *hi) {
+    uint8_t c[TK_BYTES];
+    if (i0 + TK_BYTES <= n && (((uintptr_t)(data + i0)) & 15u) == 0) {
+        const uint4 q = *reinterpret_cast<const uint4 *>(data + i0);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int j = 0; j < TK_BYTES; j++) c[j] = (uint8_t)(w[j >> 2] >> ((j & 3) * 8));
+    } else {
+#pragma unroll
+        for (int j = 0; j < TK_BYTES; j++) c[j] = i0 + j < n ? data[i0 + j] : (uint8_t)0x20;
+    }
+    bool prev_ws = i0 == 0 ? true : tok_ws(data[i0 - 1]);
+    uint32_t m = 0;
+    bool h = false;
+#pragma unroll
+    for (int j = 0; j < TK_BYTES; j++) {
+        const bool ws = tok_ws(c[j]);
+        h |= c[j] >= 0x80;
+        if (!ws && prev_ws) m |= 1u << j;
+        prev_ws = ws;
+    }
+    *hi = h;
+    return m;
+}
+
+
 }  // namespace dpk

@@ -49,37 +49,11 @@ k_dict_encode(const uint8_t *__restrict__ data, const int64_t *__restrict__ offs
 // \x1c..\x1f).  Two passes over the bytes: count the token starts per 4096-byte block, then -- after the host-side scan
 // of the block counts -- write (start, length) of every token in text order.  A byte >= 0x80 raises `flags` bit 0: the
 // caller then leaves the split to the row-wise path (Unicode whitespace and decoding errors are Python's business).
-constexpr int TK_THREADS = 256;
-constexpr int TK_BYTES = 16;
+constexpr int TK_THREADS = 256;   // TK_BYTES (16 bytes per thread): dpk_common.cuh
 constexpr int TK_CHUNK = TK_THREADS * TK_BYTES;
 
-__device__ __forceinline__ bool tok_ws(uint8_t c) { return c == 0x20 || (c >= 0x09 && c <= 0x0d) || (c >= 0x1c && c <= 0x1f); }
-
-// bit j of the result: a token starts at byte i0 + j; *hi |= any byte >= 0x80
-__device__ __forceinline__ uint32_t tok_starts16(const uint8_t *__restrict__ data, int64_t n, int64_t i0, bool *hi) {
-    uint8_t c[TK_BYTES];
-    if (i0 + TK_BYTES <= n && (((uintptr_t)(data + i0)) & 15u) == 0) {
-        const uint4 q = *reinterpret_cast<const uint4 *>(data + i0);
-        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-        for (int j = 0; j < TK_BYTES; j++) c[j] = (uint8_t)(w[j >> 2] >> ((j & 3) * 8));
-    } else {
-#pragma unroll
-        for (int j = 0; j < TK_BYTES; j++) c[j] = i0 + j < n ? data[i0 + j] : (uint8_t)0x20;
-    }
-    bool prev_ws = i0 == 0 ? true : tok_ws(data[i0 - 1]);
-    uint32_t m = 0;
-    bool h = false;
-#pragma unroll
-    for (int j = 0; j < TK_BYTES; j++) {
-        const bool ws = tok_ws(c[j]);
-        h |= c[j] >= 0x80;
-        if (!ws && prev_ws) m |= 1u << j;
-        prev_ws = ws;
-    }
-    *hi = h;
-    return m;
-}
+// tok_ws / tok_starts16 (the per-thread token-start mask) live in dpk_common.cuh: __host__ __device__, so that
+// tests/hostcheck.cu can run the same arithmetic on the CPU against Python's str.split()
 
 __global__ void __launch_bounds__(TK_THREADS)
 k_tok_count(const uint8_t *__restrict__ data, int64_t n, int64_t *__restrict__ block_counts, unsigned long long *__restrict__ flags) {

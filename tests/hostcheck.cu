@@ -21,6 +21,27 @@ int hc_partition(const int64_t *h, int64_t n, int32_t P, const int64_t *thr, int
     for (int64_t i = 0; i < n; i++) o[i] = f(h[i]);
     return 0;
 }
+// the tokeniser's per-thread arithmetic (dpk_strings.cu k_tok_count / k_tok_emit) walked sequentially: token starts from
+// the 16-byte masks, token ends by the forward scan; returns the token count, -1 if a byte >= 0x80 was seen
+int64_t hc_tokenize(const uint8_t *data, int64_t n, int64_t *starts, int64_t *lens) {
+    int64_t m = 0;
+    bool any_hi = false;
+    for (int64_t i0 = 0; i0 < n; i0 += dpk::TK_BYTES) {
+        bool hi = false;
+        uint32_t mask = dpk::tok_starts16(data, n, i0, &hi);
+        any_hi |= hi;
+        for (int j = 0; j < dpk::TK_BYTES; j++)
+            if (mask & (1u << j)) {
+                const int64_t b = i0 + j;
+                int64_t e = b + 1;
+                while (e < n && !dpk::tok_ws(data[e])) e++;
+                starts[m] = b;
+                lens[m] = e - b;
+                m++;
+            }
+    }
+    return any_hi ? -1 : m;
+}
 int hc_bucket(const int64_t *h, int64_t n, int32_t P, int32_t sub_bits, int32_t *o) {
     dpk::PartFn f;
     int rc = dpk::make_partfn(P, nullptr, 0, sub_bits, &f);

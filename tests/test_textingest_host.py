@@ -109,3 +109,50 @@ def test_owned_ranges_are_the_lines_a_split_yields(tmp_path, split_size):
         assert (lines == want) if chunk else (lines == [])
         prev_end = b
     assert prev_end == size
+
+
+def _hostcheck():
+    import ctypes as C
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = os.path.join(root, "tests", "_hostcheck.so")
+    if not os.path.exists(path):
+        pytest.skip("hostcheck not built")
+    L = C.CDLL(path)
+    L.hc_tokenize.restype = C.c_int64
+    L.hc_tokenize.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    return L
+
+
+def _hc_tokens(L, data):
+    import numpy as np
+    buf = np.frombuffer(data, dtype=np.uint8).copy() if data else np.zeros(1, np.uint8)
+    # the kernel's vector path needs the 16-byte alignment a device buffer has: give the host copy the same
+    raw = np.zeros(len(buf) + 64, np.uint8)
+    off = (-raw.ctypes.data) % 16
+    view = raw[off:off + len(buf)]
+    view[:] = buf
+    starts = np.zeros(len(data) + 1, np.int64)
+    lens = np.zeros(len(data) + 1, np.int64)
+    m = L.hc_tokenize(view.ctypes.data, len(data), starts.ctypes.data, lens.ctypes.data)
+    if m < 0:
+        return None
+    return [data[a:a + b] for a, b in zip(starts[:m].tolist(), lens[:m].tolist())]
+
+
+def test_tokeniser_arithmetic_equals_str_split_on_the_cpu():
+    """The product's __host__ __device__ tokeniser arithmetic (dpk_common.cuh tok_ws / tok_starts16, the per-thread
+    step of k_tok_count / k_tok_emit) run on the CPU through tests/hostcheck.cu: every ASCII byte is whitespace exactly
+    when Python's str.split() treats it as such, and the tokens of random ASCII text are str.split()'s."""
+    import numpy as np
+    L = _hostcheck()
+    for b in range(128):
+        s = b"a" + bytes([b]) + b"b"
+        assert _hc_tokens(L, s) == [w.encode("ascii") for w in s.decode("ascii").split()], b
+    for case in (b"", b" ", b"a", b" a  b ", b"x" * 100, b"a" * 15 + b" " + b"b" * 16 + b"\n" + b"c" * 17):
+        assert _hc_tokens(L, case) == [w.encode("ascii") for w in case.decode("ascii").split()]
+    rng = np.random.default_rng(3)
+    alphabet = np.frombuffer(bytes(range(0x21, 0x7f)) * 3 + b" \t\n\r\x0b\x0c\x1c\x1d\x1e\x1f" * 4 + b"\x00\x01\x7f", dtype=np.uint8)
+    for n in (17, 4095, 4096, 4097, 100003):
+        data = alphabet[rng.integers(0, len(alphabet), n)].tobytes()
+        assert _hc_tokens(L, data) == [w.encode("ascii") for w in data.decode("ascii").split()]
+    assert _hc_tokens(L, "café au lait".encode("utf-8")) is None
