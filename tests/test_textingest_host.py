@@ -156,3 +156,35 @@ def test_tokeniser_arithmetic_equals_str_split_on_the_cpu():
         data = alphabet[rng.integers(0, len(alphabet), n)].tobytes()
         assert _hc_tokens(L, data) == [w.encode("ascii") for w in data.decode("ascii").split()]
     assert _hc_tokens(L, "café au lait".encode("utf-8")) is None
+
+
+def test_owned_ranges_and_tokens_equal_what_the_reference_hands_out(tmp_path):
+    """tests/golden/textfile_cases.json was written by the REAL reference (make_textfile_golden.py): for five split sizes,
+    the lines every split of `textFile(path, splitSize)` yields and the tokens wc.py's flatMap makes of them.  The
+    product must (a) cut the same splits, (b) own exactly the bytes of those lines, and (c) tokenise that byte range --
+    the device kernels' arithmetic, run here on the CPU -- into the same tokens in the same order."""
+    import json
+    from dpark_b200.rdd import TextFileRDD
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "textfile_cases.json")) as f:
+        gold = json.load(f)
+    body = gold["text"].encode("ascii")
+    p = tmp_path / "in.txt"
+    p.write_bytes(body)
+    L = _hostcheck()
+    dc = ctx()
+    for case in gold["cases"]:
+        tf = TextFileRDD(dc, str(p), splitSize=case["split_size"])
+        assert [[sp.begin, sp.end] for sp in tf.splits] == case["ranges"]
+        prev = 0
+        for sp, want_lines, want_tokens in zip(tf.splits, case["lines"], case["tokens"]):
+            a, b = ti.owned_range(str(p), sp.begin, sp.end, len(body))
+            chunk = body[a:b]
+            got_lines = chunk.decode("ascii").split("\n")
+            if chunk.endswith(b"\n"):
+                got_lines = got_lines[:-1]
+            assert (got_lines if chunk else []) == want_lines
+            assert list(tf.compute(sp)) == want_lines
+            assert _hc_tokens(L, chunk) == [w.encode("ascii") for w in want_tokens]
+            assert a >= prev
+            prev = b
+        assert prev == len(body)
