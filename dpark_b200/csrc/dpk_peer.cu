@@ -477,11 +477,11 @@ extern "C" int dpk_pipe_plan(const int64_t *all_counts, int32_t nsrc, int32_t nr
 // previous part at their full speed; the batch call costs one driver round trip instead of one per block.
 extern "C" int dpk_memcpy_batch(const uint64_t *h_dst_ptrs, const uint64_t *h_src_ptrs, const int64_t *h_nbytes, int32_t count,
                                 dpk_stream_t stream) {
-    if (count < 0 || count > 4096) return fail(DPK_ERR_INVALID, "count=%d out of range [0, 4096]", count);
+    if (count < 0 || count > 1024) return fail(DPK_ERR_INVALID, "count=%d out of range [0, 1024]", count);
     if (count == 0) return DPK_OK;
     if (!h_dst_ptrs || !h_src_ptrs || !h_nbytes) return fail(DPK_ERR_INVALID, "NULL pointer");
-    void *dsts[4096], *srcs[4096];
-    size_t sizes[4096];
+    void *dsts[1024], *srcs[1024];     // 24 KB of stack: a step pushes 2 columns x (ranks <= 64) blocks per call
+    size_t sizes[1024];
     size_t m = 0;
     for (int i = 0; i < count; i++) {
         if (h_nbytes[i] < 0) return fail(DPK_ERR_INVALID, "negative size in segment %d", i);
