@@ -96,6 +96,25 @@ def owned_range(path, begin, end, size):
     return line_start_at_or_after(begin), line_start_at_or_after(end)
 
 
+MAX_PIECE_BYTES = 1 << 30      # a byte range longer than this is tokenised in pieces cut at line starts
+
+
+def cut_pieces(path, a, b, size, max_bytes=None):
+    """[a, b) (both line starts) as consecutive pieces of at most ~max_bytes bytes, every cut on a line start (a token
+    never straddles a piece: newlines are whitespace)."""
+    max_bytes = max_bytes or MAX_PIECE_BYTES
+    out = []
+    while b - a > max_bytes:
+        cut = owned_range(path, a + max_bytes, a + max_bytes, size)[0]     # first line start at or after a + max_bytes
+        if cut >= b:
+            break
+        out.append([a, cut])
+        a = cut
+    if b > a:
+        out.append([a, b])
+    return out
+
+
 def reduce_tokens(text_rdd, split_indices, P, thresholds, op, dev, res, local_only=True):
     """reduceByKey(op) over (token, 1) for the tokens of the given splits of `text_rdd`, on the device.  Fills
     res.parts[p] = (keys, values) for every partition and returns res; returns None (nothing done) when a split
@@ -113,7 +132,7 @@ def reduce_tokens(text_rdd, split_indices, P, thresholds, op, dev, res, local_on
             else:
                 ranges.append([a, b])
     pieces = []
-    for a, b in ranges:
+    for a, b in [piece for r in ranges for piece in cut_pieces(path, r[0], r[1], size)]:
         host = np.fromfile(path, dtype=np.uint8, count=b - a, offset=a)
         d_text = torch.from_numpy(host).to(dev)
         starts, lens, ascii_ok = nv.tokenize(d_text)

@@ -188,3 +188,21 @@ def test_owned_ranges_and_tokens_equal_what_the_reference_hands_out(tmp_path):
             assert a >= prev
             prev = b
         assert prev == len(body)
+
+
+def test_long_ranges_are_cut_at_line_starts(tmp_path):
+    """cut_pieces: a byte range longer than the piece limit is tokenised in pieces; every cut is a line start, the pieces
+    tile the range, and a line longer than the limit stays whole."""
+    body = b"".join(b"line %d has some words\n" % i for i in range(200)) + b"x" * 500 + b"\n" + b"tail"
+    p = tmp_path / "t.txt"
+    p.write_bytes(body)
+    size = len(body)
+    for limit in (1, 10, 64, 300, 10 ** 6):
+        pieces = ti.cut_pieces(str(p), 0, size, size, limit)
+        assert pieces[0][0] == 0 and pieces[-1][1] == size
+        for (a0, b0), (a1, b1) in zip(pieces[:-1], pieces[1:]):
+            assert b0 == a1 and body[a1 - 1:a1] == b"\n"
+        assert all(b0 > a0 for a0, b0 in pieces)
+        tokens = [w for a0, b0 in pieces for w in body[a0:b0].split()]
+        assert tokens == body.split()
+    assert ti.cut_pieces(str(p), 0, size, size, 10 ** 6) == [[0, size]]
